@@ -1,0 +1,419 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native gpu-benchmarking hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json metric "GDoF/s per operator ..."; configs[3]/[4]):
+benchmark05 hex BwdTrans, nq = 8x8x8, FP64, element-major, the reference's
+synthetic input (in[e][k] = sin(k+1), B[k] = cos(k)), 262144 elements
+(128 Mi quadrature points, 0.72 GB in + 1.07 GB out -- far larger than L2)
+PER GPU; elements are sharded over ranks with no data-path collective (weak
+scaling; at 8 GPUs this is the 1 Gi-point case of configs[4]).  One step = one
+launch of the operator over the rank's shard through the C ABI
+(b200fe_BwdTransHexKernel_QP_Shared_f64), exactly the reference's timed region
+(benchmark05.cc:1319-1332).  GDoF/s counts MODES like the reference
+(1e-9 * nelmt * nm^3 / t, benchmark05.cc:1408).
+
+Prints ONE JSON line on rank 0 (see the keys at the bottom of main()).
+The oracle (oracle/) is used here only as the checker of the result norm and
+as the timed CPU baseline / --impl reference arm; it is never on the GPU path.
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NQ = 8
+NM = NQ - 1
+NELMT_PER_GPU = 262144
+KERNEL = "BwdTransHexKernel_QP_Shared"
+METRIC = "GDoF/s hex BwdTrans nq=8 FP64 (1e-9*nelmt*nm^3/t), whole job"
+GOLDEN_NORM_128 = 189.3141665  # reference benchmark05/nq8x8x8.log line 6 (nelmt = 128)
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def alg_bytes_per_elem(dim, nq, size):
+    return size * ((nq - 1) ** dim + nq ** dim)
+
+
+class ClockSampler:
+    """samples SM clock and throttle reasons through NVML while the GPU is under load"""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        self.index = index
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa
+            self.nv = None
+            log("clock sampler: NVML unavailable:", e)
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def start(self):
+        if self.nv:
+            self.samples, self.reasons = [], set()
+            self._stop.clear()
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        if self._thr:
+            self._stop.set()
+            self._thr.join()
+            self._thr = None
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def cpu_reference_rate(sample_target_s, threads=None):
+    """time the oracle's port of the reference loop nest (benchmark05.cc:57-101) on host cores"""
+    import numpy as np
+    import oracle
+    if threads:
+        oracle.set_num_threads(threads)
+    cores = oracle.num_threads()
+    b = oracle.gen_basis(NM, NQ)
+
+    def run(nelmt):
+        inp = oracle.gen_in(nelmt, NM ** 3)
+        t0 = time.perf_counter()
+        out = oracle.bwdtrans_hex(NQ, NQ, NQ, nelmt, b, b, b, inp, use_fma=True)
+        dt = time.perf_counter() - t0
+        return dt, out
+
+    probe = 2048 * max(1, cores // 4)
+    dt, _ = run(probe)  # also warms the thread pool
+    dt, _ = run(probe)
+    rate = probe / dt
+    nelmt = int(max(probe, min(NELMT_PER_GPU, rate * sample_target_s / 3)) // 32 * 32)
+    best = None
+    for _ in range(3):
+        dt, out = run(nelmt)
+        best = dt if best is None else min(best, dt)
+    norm = math.sqrt(oracle.sumsq(out))
+    ok = abs(norm - GOLDEN_NORM_128 * math.sqrt(nelmt / 128)) / norm < 6e-10
+    return {"value": 1e-9 * nelmt * NM ** 3 / best, "unit": "GDoF/s", "cores": cores, "kind": "port",
+            "sample": f"{nelmt} of the workload's elements (hex nq=8 FP64), best of 3 passes of the oracle's "
+                      f"OpenMP port of benchmark05.cc:57-101, {best:.3f} s per pass",
+            "norm_ok": bool(ok), "seconds_per_pass": best, "nelmt": nelmt}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path (oracle port; the reference ships no CPU build and
+    its CUDA/Kokkos sources do not build here -- DESIGN.md) on the box's host cores, rank 0 only"""
+    if rank != 0:
+        return
+    res = None
+    times = []
+    import oracle
+    import numpy as np
+    cores = oracle.num_threads()
+    b = oracle.gen_basis(NM, NQ)
+    nelmt = 16384 * max(1, cores // 8)
+    inp = oracle.gen_in(nelmt, NM ** 3)
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        res = oracle.bwdtrans_hex(NQ, NQ, NQ, nelmt, b, b, b, inp, use_fma=True)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = 1e-9 * nelmt * NM ** 3 * len(times) / total
+    norm = math.sqrt(oracle.sumsq(res))
+    sample = (f"each step = {nelmt} elements of the workload (hex nq=8 FP64) through the oracle's OpenMP port of "
+              f"benchmark05.cc:57-101 on {cores} host threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GDoF/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "GDoF/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "GDoF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "norm_ok": bool(abs(norm - GOLDEN_NORM_128 * math.sqrt(nelmt / 128)) / norm < 6e-10),
+    }), flush=True)
+
+
+def workload_config(ngpus):
+    return {
+        "workload": f"benchmark05 hex BwdTrans nq=8x8x8 FP64, {NELMT_PER_GPU} elements (128 Mi quadrature points) "
+                    f"per GPU, element-major, reference synthetic input",
+        "entry_point": f"b200fe_{KERNEL}_f64",
+        "nelmt_per_gpu": NELMT_PER_GPU, "nelmt_total": NELMT_PER_GPU * ngpus,
+        "sharding": "contiguous element ranges, no data-path collective; NCCL all-reduce of the scalar norm only",
+        "l2": "inputs larger than L2: 0.72 GB read + 1.07 GB written per step vs 126 MB L2",
+    }
+
+
+def sweep(fe, torch, oracle, peak, reps=5):
+    """GDoF/s and HBM-roofline fraction for every operator/nq of configs[2]/[3] at ~64 Mi quadrature points"""
+    import numpy as np
+    out = []
+    st = torch.cuda.current_stream().cuda_stream
+    for dim, nqs, kern in ((2, (2, 4, 6, 8, 10, 12, 14, 16, 32), "BwdTransQuadKernel_QP_Shared"),
+                           (3, (2, 4, 6, 8, 10), "BwdTransHexKernel_QP_Shared")):
+        for suf, tdt, npdt, size in (("f64", torch.float64, np.float64, 8), ("f32", torch.float32, np.float32, 4)):
+            for nq in nqs:
+                nm = nq - 1
+                nelmt = max(32, ((1 << 26) // nq ** dim) // 32 * 32)
+                b = torch.from_numpy(oracle.gen_basis(nm, nq, npdt)).cuda()
+                one = torch.from_numpy(oracle.gen_in(32, nm ** dim, npdt)).cuda()
+                d_in = one.view(32, -1).repeat(nelmt // 32, 1).reshape(-1).contiguous()
+                d_out = torch.empty(nelmt * nq ** dim, dtype=tdt, device="cuda")
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * reps)]
+
+                def call():
+                    if dim == 2:
+                        fe.bwdtrans_quad(kern, suf, nq, nq, nelmt, b.data_ptr(), b.data_ptr(), d_in.data_ptr(),
+                                         d_out.data_ptr(), stream=st)
+                    else:
+                        fe.bwdtrans_hex(kern, suf, nq, nq, nq, nelmt, b.data_ptr(), b.data_ptr(), b.data_ptr(),
+                                        d_in.data_ptr(), d_out.data_ptr(), stream=st)
+                for _ in range(3):
+                    call()
+                for r in range(reps):
+                    ev[2 * r].record()
+                    call()
+                    ev[2 * r + 1].record()
+                torch.cuda.synchronize()
+                ms = min(ev[2 * r].elapsed_time(ev[2 * r + 1]) for r in range(reps))
+                gdof = 1e-9 * nelmt * nm ** dim / (ms * 1e-3)
+                gbs = 1e-9 * nelmt * alg_bytes_per_elem(dim, nq, size) / (ms * 1e-3)
+                out.append({"op": "quad" if dim == 2 else "hex", "nq": nq, "dtype": suf, "nelmt": nelmt,
+                            "backend": fe.last_backend(), "ms": round(ms, 4), "gdof_s": round(gdof, 2),
+                            "gb_s": round(gbs, 1), "hbm_frac": round(gbs / peak, 4)})
+                del d_in, d_out
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-sweep", action="store_true", help="skip the per-operator sweep (extra key `sweep`)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import b200fe_loader
+    fe = b200fe_loader.load()  # raises if libb200fe.so is missing: no fallback
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if fe.check_device() != 0:
+        raise SystemExit("bench.py: device is not compute capability 10.x (B200)")
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ngpus = world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    import oracle  # checker + CPU baseline only
+    peak, peak_src = hbm_peak()
+    st = torch.cuda.current_stream().cuda_stream
+
+    # ---- this rank's shard: elements [rank*NELMT_PER_GPU, (rank+1)*NELMT_PER_GPU) -----------------
+    nelmt = NELMT_PER_GPU
+    h_b = torch.from_numpy(oracle.gen_basis(NM, NQ))
+    h_one = torch.from_numpy(oracle.gen_in(1024, NM ** 3))       # reference generator (oracle port)
+    h_in = h_one.view(1024, -1).repeat(nelmt // 1024, 1).reshape(-1).contiguous().pin_memory()
+    d_b = h_b.cuda()
+    d_in = h_in.cuda()
+    d_out = torch.empty(nelmt * NQ ** 3, dtype=torch.float64, device="cuda")
+    d_res = torch.zeros(1, dtype=torch.float64, device="cuda")
+    d_scr = torch.empty(fe.sumsq_scratch_bytes(), dtype=torch.uint8, device="cuda")
+
+    def step():
+        fe.bwdtrans_hex(KERNEL, "f64", NQ, NQ, NQ, nelmt, d_b.data_ptr(), d_b.data_ptr(), d_b.data_ptr(),
+                        d_in.data_ptr(), d_out.data_ptr(), stream=st)
+
+    sampler = ClockSampler(local)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream ----------------------
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = fe.launch_count()
+    sampler.start()
+    barrier()
+    t_begin.record()
+    for k in range(args.steps):
+        ev[2 * k].record()
+        step()
+        ev[2 * k + 1].record()
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = fe.launch_count() - launches0
+    total_ms = t_begin.elapsed_time(t_end)
+    kern_ms = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)) / args.steps
+    backend = fe.last_backend()
+    if world > 1:
+        t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, kern_ms = float(t[0]), float(t[1])
+    ms_per_step = total_ms / args.steps
+    value = 1e-9 * nelmt * ngpus * NM ** 3 / (ms_per_step * 1e-3)
+
+    # ---- result check: global norm (NCCL scalar all-reduce) vs the reference's golden checksum ----
+    fe.sumsq("f64", d_out.data_ptr(), d_out.numel(), d_res.data_ptr(), d_scr.data_ptr(), st)
+    if world > 1:
+        dist.all_reduce(d_res, op=dist.ReduceOp.SUM)
+    norm = math.sqrt(float(d_res.item()))
+    want = GOLDEN_NORM_128 * math.sqrt(nelmt * ngpus / 128)
+    norm_ok = abs(norm - want) / want < 6e-10
+    el0 = d_out[: NQ ** 3].cpu().numpy()
+    elem_ok = bool(np.array_equal(el0, oracle.bwdtrans_hex(NQ, NQ, NQ, 1, h_b.numpy(), h_b.numpy(), h_b.numpy(),
+                                                            h_one.numpy()[: NM ** 3])))
+
+    # ---- end to end: host buffers in, host checksum out, copies inside the timed region -----------
+    hb = [h_b.data_ptr()] * 3
+    fe.bwdtrans_host("f64", (NQ, NQ, NQ), nelmt, hb, h_in.data_ptr(), 0)  # warm-up: allocs the chunk ring
+    fe.bwdtrans_host("f64", (NQ, NQ, NQ), nelmt, hb, h_in.data_ptr(), 0)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        ss = fe.bwdtrans_host("f64", (NQ, NQ, NQ), nelmt, hb, h_in.data_ptr(), 0)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.e2e_steps
+    e2e_norm_ok = abs(math.sqrt(ss) - GOLDEN_NORM_128 * math.sqrt(nelmt / 128)) / math.sqrt(ss) < 6e-10
+    # variant that also copies `out` back (the reference never does; reported as extra)
+    h_out = torch.empty(nelmt * NQ ** 3, dtype=torch.float64).pin_memory()
+    fe.bwdtrans_host("f64", (NQ, NQ, NQ), nelmt, hb, h_in.data_ptr(), h_out.data_ptr())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(max(2, args.e2e_steps // 2)):
+        fe.bwdtrans_host("f64", (NQ, NQ, NQ), nelmt, hb, h_in.data_ptr(), h_out.data_ptr())
+    barrier()
+    e2e_full_ms = (time.perf_counter() - t0) * 1e3 / max(2, args.e2e_steps // 2)
+    del h_out
+    if world > 1:
+        t = torch.tensor([e2e_ms, e2e_full_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms, e2e_full_ms = float(t[0]), float(t[1])
+    chunk = max(32, ((24 << 20) // (NM ** 3 * 8)) // 32 * 32)
+    nchunk = (nelmt + chunk - 1) // chunk
+    e2e = {"value": 1e-9 * nelmt * ngpus * NM ** 3 / (e2e_ms * 1e-3), "unit": "GDoF/s",
+           "h2d_bytes_per_step": (nelmt * NM ** 3 + 3 * NM * NQ) * 8, "d2h_bytes_per_step": nchunk * 8,
+           "ms_per_step": e2e_ms, "steps": args.e2e_steps, "norm_ok": bool(e2e_norm_ok),
+           "api": "b200fe_bwdtrans_hex_host_f64 (pinned host input -> chunked H2D/kernel/checksum pipeline -> "
+                  "host checksum; `out` stays on the device as in the reference)",
+           "with_out_copied_back": {"value": 1e-9 * nelmt * ngpus * NM ** 3 / (e2e_full_ms * 1e-3),
+                                    "d2h_bytes_per_step": nelmt * NQ ** 3 * 8 + nchunk * 8,
+                                    "ms_per_step": e2e_full_ms}}
+
+    # ---- roofline of the dominant (only) kernel ----------------------------------------------------
+    bytes_per_launch = nelmt * alg_bytes_per_elem(3, NQ, 8)
+    achieved = 1e-9 * bytes_per_launch / (kern_ms * 1e-3)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
+            traffic = json.load(f).get("hex8_f64_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": f"bwdtrans_hex_{backend}_kernel<double,8>",
+                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": kern_ms}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    cpu = None
+    if ngpus == 1 and not args.no_cpu:
+        cpu = cpu_reference_rate(sample_target_s=12.0)
+    sw = None
+    if ngpus == 1 and not args.no_sweep:
+        del d_in, d_out
+        torch.cuda.empty_cache()
+        sw = sweep(fe, torch, oracle, peak)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "GDoF/s", "n_gpus": ngpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(ngpus),
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "backend": backend, "norm": norm, "norm_ok": bool(norm_ok and elem_ok), "impl": "b200",
+        "lib": fe.version(),
+    }
+    if sw is not None:
+        line["sweep"] = sw
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0 if (norm_ok and elem_ok) else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,96 @@
+// bwdtrans_hex.cu -- hex BwdTrans dispatch for one dtype.  Compiled twice:
+//   -DB200FE_T=double -DB200FE_ROWS_TABLE='"rows_table_3_f64.inc"'
+//   -DB200FE_T=float  -DB200FE_ROWS_TABLE='"rows_table_3_f32.inc"'
+#include "bwdtrans_impl.cuh"
+
+namespace b200fe
+{
+
+using T = B200FE_T;
+
+static int hex_rows_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
+{
+    switch (nq)
+    {
+#define ROWS_CASE(NQ, E, TH)                                                                                 \
+    case NQ:                                                                                                 \
+        return launch_hex_rows<T, NQ, E, TH>(nelmt, in, out, s);
+#include B200FE_ROWS_TABLE
+#undef ROWS_CASE
+    default:
+        return B200FE_EUNSUPPORTED;
+    }
+}
+
+// registers hold nm^3 + nm^2 + nm values per thread
+constexpr unsigned kHexTpeMaxNq = 5;
+
+static int hex_tpe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
+{
+    switch (nq)
+    {
+#define TPE_CASE(NQ)                                                                                         \
+    case NQ:                                                                                                 \
+        return launch_hex_tpe_coa<T, NQ>(nelmt, in, out, s);
+        TPE_CASE(2)
+        TPE_CASE(3)
+        TPE_CASE(4)
+        TPE_CASE(5)
+#undef TPE_CASE
+    default:
+        return B200FE_EUNSUPPORTED;
+    }
+}
+
+static bool hex_rows_has(unsigned nq)
+{
+    switch (nq)
+    {
+#define ROWS_CASE(NQ, E, TH)                                                                                 \
+    case NQ:                                                                                                 \
+        return true;
+#include B200FE_ROWS_TABLE
+#undef ROWS_CASE
+    default:
+        return false;
+    }
+}
+
+template <>
+int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsigned nm2, unsigned nq0, unsigned nq1,
+                        unsigned nq2, unsigned nelmt, const T *b0, const T *b1, const T *b2, const T *in, T *out,
+                        cudaStream_t stream)
+{
+    const bool regular = (nq0 == nq1) && (nq1 == nq2) && (nm0 + 1 == nq0) && (nm1 + 1 == nq1) &&
+                         (nm2 + 1 == nq2) && nq0 >= 2 && nq0 <= 16;
+    if (be == Backend::Auto)
+    {
+        if (!regular)
+            be = Backend::Generic;
+        else if (coa)
+            be = nq0 <= kHexTpeMaxNq ? Backend::Tpe : Backend::Generic;
+        else
+            be = hex_rows_has(nq0) ? Backend::Rows : Backend::Generic;
+    }
+    if (be == Backend::Generic)
+    {
+        t_last_backend = "generic";
+        return launch_hex_generic<T>(nm0, nm1, nm2, nq0, nq1, nq2, nelmt, b0, b1, b2, in, out, coa, stream);
+    }
+    if (!regular || (be == Backend::Rows && coa) || (be == Backend::Tpe && !coa))
+        return B200FE_EUNSUPPORTED;
+
+    std::lock_guard<std::mutex> lock(g_bank_lock);
+    const T *bases[3]   = {b0, b1, b2};
+    const int counts[3] = {(int)(nm0 * nq0), (int)(nm1 * nq1), (int)(nm2 * nq2)};
+    int rc              = fill_basis_bank<T>(g_bank, 3, bases, counts, stream);
+    if (rc)
+        return rc;
+    rc = (be == Backend::Rows) ? hex_rows_switch(nq0, nelmt, in, out, stream)
+                               : hex_tpe_switch(nq0, nelmt, in, out, stream);
+    if (rc)
+        return rc;
+    return release_basis_bank(g_bank, stream);
+}
+
+} // namespace b200fe

@@ -1,0 +1,85 @@
+// bwdtrans_quad.cu -- quad BwdTrans dispatch for one dtype.  Compiled twice:
+//   -DB200FE_T=double -DB200FE_ROWS_TABLE='"rows_table_2_f64.inc"'
+//   -DB200FE_T=float  -DB200FE_ROWS_TABLE='"rows_table_2_f32.inc"'
+#include "bwdtrans_impl.cuh"
+
+namespace b200fe
+{
+
+using T = B200FE_T;
+
+static int quad_rows_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
+{
+    switch (nq)
+    {
+#define ROWS_CASE(NQ, E, TH)                                                                                 \
+    case NQ:                                                                                                 \
+        return launch_quad_rows<T, NQ, E, TH>(nelmt, in, out, s);
+#include B200FE_ROWS_TABLE
+#undef ROWS_CASE
+    default:
+        return B200FE_EUNSUPPORTED;
+    }
+}
+
+// registers hold nm^2 + nm values per thread
+constexpr unsigned kQuadTpeMaxNq = 10;
+
+static int quad_tpe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
+{
+    switch (nq)
+    {
+#define TPE_CASE(NQ)                                                                                         \
+    case NQ:                                                                                                 \
+        return launch_quad_tpe_coa<T, NQ>(nelmt, in, out, s);
+        TPE_CASE(2)
+        TPE_CASE(3)
+        TPE_CASE(4)
+        TPE_CASE(5)
+        TPE_CASE(6)
+        TPE_CASE(7)
+        TPE_CASE(8)
+        TPE_CASE(9)
+        TPE_CASE(10)
+#undef TPE_CASE
+    default:
+        return B200FE_EUNSUPPORTED;
+    }
+}
+
+template <>
+int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsigned nq0, unsigned nq1,
+                         unsigned nelmt, const T *b0, const T *b1, const T *in, T *out, cudaStream_t stream)
+{
+    const bool regular = (nq0 == nq1) && (nm0 + 1 == nq0) && (nm1 + 1 == nq1) && nq0 >= 2 && nq0 <= 32;
+    if (be == Backend::Auto)
+    {
+        if (!regular)
+            be = Backend::Generic;
+        else if (coa)
+            be = nq0 <= kQuadTpeMaxNq ? Backend::Tpe : Backend::Generic;
+        else
+            be = Backend::Rows;
+    }
+    if (be == Backend::Generic)
+    {
+        t_last_backend = "generic";
+        return launch_quad_generic<T>(nm0, nm1, nq0, nq1, nelmt, b0, b1, in, out, coa, stream);
+    }
+    if (!regular || (be == Backend::Rows && coa) || (be == Backend::Tpe && !coa))
+        return B200FE_EUNSUPPORTED;
+
+    std::lock_guard<std::mutex> lock(g_bank_lock);
+    const T *bases[2]   = {b0, b1};
+    const int counts[2] = {(int)(nm0 * nq0), (int)(nm1 * nq1)};
+    int rc              = fill_basis_bank<T>(g_bank, 2, bases, counts, stream);
+    if (rc)
+        return rc;
+    rc = (be == Backend::Rows) ? quad_rows_switch(nq0, nelmt, in, out, stream)
+                               : quad_tpe_switch(nq0, nelmt, in, out, stream);
+    if (rc)
+        return rc;
+    return release_basis_bank(g_bank, stream);
+}
+
+} // namespace b200fe

@@ -1,0 +1,425 @@
+// capi.cu -- the extern "C" surface of libb200fe.so (include/b200fe.h):
+// argument checking, back-end routing and the host-buffer pipeline.
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "dispatch.h"
+#include "vec_kernels.h"
+
+namespace b200fe
+{
+std::atomic<unsigned long long> g_launch_count{0};
+thread_local const char *t_last_backend = "none";
+static std::atomic<int> g_forced_backend{-1}; // -1: per-entry-point default
+
+static Backend pick(Backend preferred)
+{
+    const int f = g_forced_backend.load(std::memory_order_relaxed);
+    return f < 0 ? preferred : (Backend)f;
+}
+
+template <typename T> static bool misaligned(const T *p)
+{
+    return (reinterpret_cast<uintptr_t>(p) % sizeof(T)) != 0;
+}
+
+template <typename T>
+static int quad_entry(Backend preferred, bool coa, unsigned nm0, unsigned nm1, unsigned nmTot, unsigned nq0,
+                      unsigned nq1, unsigned nelmt, const T *b0, const T *b1, const T *in, T *out, void *stream)
+{
+    if (!b0 || !b1 || !in || !out || nm0 == 0 || nm1 == 0 || nq0 == 0 || nq1 == 0 || nmTot != nm0 * nm1)
+        return B200FE_EINVAL;
+    if (coa && (nelmt % 32u) != 0)
+        return B200FE_EINVAL; // the interleaved layout is only defined for whole groups of 32
+    if (misaligned(b0) || misaligned(b1) || misaligned(in) || misaligned(out))
+        return B200FE_EALIGN;
+    if (nelmt == 0)
+        return B200FE_OK;
+    return run_bwdtrans_quad<T>(pick(preferred), coa, nm0, nm1, nq0, nq1, nelmt, b0, b1, in, out,
+                                (cudaStream_t)stream);
+}
+
+template <typename T>
+static int hex_entry(Backend preferred, bool coa, unsigned nm0, unsigned nm1, unsigned nm2, unsigned nmTot,
+                     unsigned nq0, unsigned nq1, unsigned nq2, unsigned nelmt, const T *b0, const T *b1, const T *b2,
+                     const T *in, T *out, void *stream)
+{
+    if (!b0 || !b1 || !b2 || !in || !out || nm0 == 0 || nm1 == 0 || nm2 == 0 || nq0 == 0 || nq1 == 0 || nq2 == 0 ||
+        nmTot != nm0 * nm1 * nm2)
+        return B200FE_EINVAL;
+    if (coa && (nelmt % 32u) != 0)
+        return B200FE_EINVAL;
+    if (misaligned(b0) || misaligned(b1) || misaligned(b2) || misaligned(in) || misaligned(out))
+        return B200FE_EALIGN;
+    if (nelmt == 0)
+        return B200FE_OK;
+    return run_bwdtrans_hex<T>(pick(preferred), coa, nm0, nm1, nm2, nq0, nq1, nq2, nelmt, b0, b1, b2, in, out,
+                               (cudaStream_t)stream);
+}
+
+// ---- host-buffer pipeline -------------------------------------------------------
+// chunk ring: H2D(in) -> BwdTrans -> sum out^2 [-> D2H(out)], one stream per slot,
+// so the copy of chunk c+1 overlaps the kernel of chunk c and the copy-back of
+// chunk c-1.  Device buffers live in a per-thread context and are reused.
+struct HostPipe
+{
+    static constexpr int kSlots = 3;
+    int device                  = -1;
+    cudaStream_t stream[kSlots] = {};
+    void *d_in[kSlots]          = {};
+    void *d_out[kSlots]         = {};
+    void *d_scratch[kSlots]     = {};
+    size_t in_cap = 0, out_cap = 0;
+    void *d_basis    = nullptr;
+    size_t basis_cap = 0;
+    double *d_sums   = nullptr;
+    size_t sums_cap  = 0;
+    double *h_sums   = nullptr;
+
+    int ensure(size_t in_bytes, size_t out_bytes, size_t basis_bytes, size_t nchunk)
+    {
+        int dev = 0;
+        B200FE_CUDA_TRY(cudaGetDevice(&dev));
+        if (dev != device)
+        {
+            release();
+            device = dev;
+        }
+        for (int s = 0; s < kSlots; ++s)
+            if (!stream[s])
+                B200FE_CUDA_TRY(cudaStreamCreateWithFlags(&stream[s], cudaStreamNonBlocking));
+        if (in_bytes > in_cap || out_bytes > out_cap)
+        {
+            for (int s = 0; s < kSlots; ++s)
+            {
+                cudaFree(d_in[s]);
+                cudaFree(d_out[s]);
+                d_in[s] = d_out[s] = nullptr;
+                B200FE_CUDA_TRY(cudaMalloc(&d_in[s], in_bytes));
+                B200FE_CUDA_TRY(cudaMalloc(&d_out[s], out_bytes));
+            }
+            in_cap  = in_bytes;
+            out_cap = out_bytes;
+        }
+        for (int s = 0; s < kSlots; ++s)
+            if (!d_scratch[s])
+                B200FE_CUDA_TRY(cudaMalloc(&d_scratch[s], sumsq_scratch_bytes()));
+        if (basis_bytes > basis_cap)
+        {
+            cudaFree(d_basis);
+            d_basis = nullptr;
+            B200FE_CUDA_TRY(cudaMalloc(&d_basis, basis_bytes));
+            basis_cap = basis_bytes;
+        }
+        if (nchunk > sums_cap)
+        {
+            cudaFree(d_sums);
+            cudaFreeHost(h_sums);
+            d_sums = nullptr;
+            h_sums = nullptr;
+            B200FE_CUDA_TRY(cudaMalloc((void **)&d_sums, nchunk * sizeof(double)));
+            B200FE_CUDA_TRY(cudaMallocHost((void **)&h_sums, nchunk * sizeof(double)));
+            sums_cap = nchunk;
+        }
+        return 0;
+    }
+
+    void release()
+    {
+        for (int s = 0; s < kSlots; ++s)
+        {
+            if (stream[s])
+                cudaStreamDestroy(stream[s]);
+            cudaFree(d_in[s]);
+            cudaFree(d_out[s]);
+            cudaFree(d_scratch[s]);
+            stream[s] = nullptr;
+            d_in[s] = d_out[s] = d_scratch[s] = nullptr;
+        }
+        cudaFree(d_basis);
+        cudaFree(d_sums);
+        if (h_sums)
+            cudaFreeHost(h_sums);
+        d_basis = nullptr;
+        d_sums  = nullptr;
+        h_sums  = nullptr;
+        in_cap = out_cap = basis_cap = sums_cap = 0;
+    }
+};
+
+static thread_local HostPipe t_pipe;
+
+// dim = 2 or 3; nq[d], basis_host[d]
+template <typename T>
+static int host_pipeline(int dim, const unsigned *nq, size_t nelmt, const T *const *basis_host, const T *in_host,
+                         T *out_host, double *sumsq_host)
+{
+    if (!in_host || !sumsq_host || nelmt > 0xffffffffull)
+        return B200FE_EINVAL;
+    unsigned nm[3] = {0, 0, 0};
+    size_t nmTot = 1, nqTot = 1, basis_elems = 0;
+    for (int d = 0; d < dim; ++d)
+    {
+        if (!basis_host[d] || nq[d] < 2)
+            return B200FE_EINVAL;
+        nm[d] = nq[d] - 1;
+        nmTot *= nm[d];
+        nqTot *= nq[d];
+        basis_elems += (size_t)nm[d] * nq[d];
+    }
+    *sumsq_host = 0.0;
+    if (nelmt == 0)
+        return B200FE_OK;
+
+    // ~24 MB of input per chunk, whole multiples of 32 elements
+    size_t chunk = (24u << 20) / (nmTot * sizeof(T));
+    chunk        = chunk < 32 ? 32 : chunk / 32 * 32;
+    if (chunk > nelmt)
+        chunk = nelmt;
+    const size_t nchunk = (nelmt + chunk - 1) / chunk;
+
+    HostPipe &P = t_pipe;
+    int rc = P.ensure(chunk * nmTot * sizeof(T), chunk * nqTot * sizeof(T), basis_elems * sizeof(T), nchunk);
+    if (rc)
+        return rc;
+
+    T *d_b[3]  = {nullptr, nullptr, nullptr};
+    size_t off = 0;
+    for (int d = 0; d < dim; ++d)
+    {
+        d_b[d] = reinterpret_cast<T *>(P.d_basis) + off;
+        B200FE_CUDA_TRY(cudaMemcpyAsync(d_b[d], basis_host[d], (size_t)nm[d] * nq[d] * sizeof(T),
+                                        cudaMemcpyHostToDevice, P.stream[0]));
+        off += (size_t)nm[d] * nq[d];
+    }
+    B200FE_CUDA_TRY(cudaStreamSynchronize(P.stream[0]));
+
+    for (size_t c = 0; c < nchunk; ++c)
+    {
+        const int s       = (int)(c % HostPipe::kSlots);
+        cudaStream_t st   = P.stream[s];
+        const size_t e0   = c * chunk;
+        const unsigned ne = (unsigned)((nelmt - e0 < chunk) ? nelmt - e0 : chunk);
+        T *din            = reinterpret_cast<T *>(P.d_in[s]);
+        T *dout           = reinterpret_cast<T *>(P.d_out[s]);
+        B200FE_CUDA_TRY(cudaMemcpyAsync(din, in_host + e0 * nmTot, (size_t)ne * nmTot * sizeof(T),
+                                        cudaMemcpyHostToDevice, st));
+        if (dim == 2)
+            rc = run_bwdtrans_quad<T>(pick(Backend::Auto), false, nm[0], nm[1], nq[0], nq[1], ne, d_b[0], d_b[1], din,
+                                      dout, st);
+        else
+            rc = run_bwdtrans_hex<T>(pick(Backend::Auto), false, nm[0], nm[1], nm[2], nq[0], nq[1], nq[2], ne, d_b[0],
+                                     d_b[1], d_b[2], din, dout, st);
+        if (rc)
+            return rc;
+        rc = launch_sumsq<T>(dout, (size_t)ne * nqTot, P.d_sums + c, P.d_scratch[s], false, st);
+        if (rc)
+            return rc;
+        if (out_host)
+            B200FE_CUDA_TRY(cudaMemcpyAsync(out_host + e0 * nqTot, dout, (size_t)ne * nqTot * sizeof(T),
+                                            cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < HostPipe::kSlots; ++s)
+        B200FE_CUDA_TRY(cudaStreamSynchronize(P.stream[s]));
+    B200FE_CUDA_TRY(cudaMemcpy(P.h_sums, P.d_sums, nchunk * sizeof(double), cudaMemcpyDeviceToHost));
+    double total = 0.0;
+    for (size_t c = 0; c < nchunk; ++c)
+        total += P.h_sums[c]; // fixed order: deterministic
+    *sumsq_host = total;
+    return B200FE_OK;
+}
+
+} // namespace b200fe
+
+using namespace b200fe;
+
+extern "C" {
+
+const char *b200fe_version(void)
+{
+    return "b200fe 0.1 sm_100a";
+}
+
+unsigned long long b200fe_launch_count(void)
+{
+    return g_launch_count.load(std::memory_order_relaxed);
+}
+
+const char *b200fe_last_backend(void)
+{
+    return t_last_backend;
+}
+
+int b200fe_check_device(void)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return B200FE_ENODEVICE;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return B200FE_ENODEVICE;
+    }
+    return prop.major == 10 ? B200FE_OK : B200FE_ENODEVICE;
+}
+
+int b200fe_set_backend(const char *name)
+{
+    if (!name)
+        return B200FE_EINVAL;
+    if (!strcmp(name, "auto"))
+        g_forced_backend = -1;
+    else if (!strcmp(name, "rows"))
+        g_forced_backend = (int)Backend::Rows;
+    else if (!strcmp(name, "tpe"))
+        g_forced_backend = (int)Backend::Tpe;
+    else if (!strcmp(name, "generic"))
+        g_forced_backend = (int)Backend::Generic;
+    else
+        return B200FE_EINVAL;
+    return B200FE_OK;
+}
+
+// ---- quad -------------------------------------------------------------------------
+#define QUAD_WSP(NAME, SUF, T, BE, COA)                                                                      \
+    int b200fe_##NAME##_##SUF(unsigned nm0, unsigned nm1, unsigned nmTot, unsigned nq0, unsigned nq1,        \
+                              unsigned nelmt, const T *basis0, const T *basis1, const T *in, T *wsp, T *out, \
+                              void *stream)                                                                  \
+    {                                                                                                        \
+        (void)wsp;                                                                                           \
+        return quad_entry<T>(BE, COA, nm0, nm1, nmTot, nq0, nq1, nelmt, basis0, basis1, in, out, stream);    \
+    }
+#define QUAD_NOWSP(NAME, SUF, T, BE)                                                                         \
+    int b200fe_##NAME##_##SUF(unsigned nm0, unsigned nm1, unsigned nmTot, unsigned nq0, unsigned nq1,        \
+                              unsigned nelmt, const T *basis0, const T *basis1, const T *in, T *out,         \
+                              void *stream)                                                                  \
+    {                                                                                                        \
+        return quad_entry<T>(BE, false, nm0, nm1, nmTot, nq0, nq1, nelmt, basis0, basis1, in, out, stream);  \
+    }
+
+QUAD_WSP(BwdTransQuadKernel, f64, double, Backend::Auto, false)
+QUAD_WSP(BwdTransQuadKernel, f32, float, Backend::Auto, false)
+QUAD_WSP(BwdTransQuadKernel_Coa, f64, double, Backend::Auto, true)
+QUAD_WSP(BwdTransQuadKernel_Coa, f32, float, Backend::Auto, true)
+QUAD_WSP(BwdTransQuadKernel_QP, f64, double, Backend::Auto, false)
+QUAD_WSP(BwdTransQuadKernel_QP, f32, float, Backend::Auto, false)
+QUAD_NOWSP(BwdTransQuadKernel_QP_Shared, f64, double, Backend::Auto)
+QUAD_NOWSP(BwdTransQuadKernel_QP_Shared, f32, float, Backend::Auto)
+QUAD_WSP(BwdTransQuadKernel_QP_1D, f64, double, Backend::Auto, false)
+QUAD_WSP(BwdTransQuadKernel_QP_1D, f32, float, Backend::Auto, false)
+QUAD_NOWSP(BwdTransQuadKernel_QP_1D_Shared, f64, double, Backend::Auto)
+QUAD_NOWSP(BwdTransQuadKernel_QP_1D_Shared, f32, float, Backend::Auto)
+
+// ---- hex --------------------------------------------------------------------------
+#define HEX_WSP(NAME, SUF, T, BE, COA)                                                                       \
+    int b200fe_##NAME##_##SUF(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nmTot, unsigned nq0,        \
+                              unsigned nq1, unsigned nq2, unsigned nelmt, const T *basis0, const T *basis1,  \
+                              const T *basis2, const T *in, T *wspa, T *wspb, T *out, void *stream)          \
+    {                                                                                                        \
+        (void)wspa;                                                                                          \
+        (void)wspb;                                                                                          \
+        return hex_entry<T>(BE, COA, nm0, nm1, nm2, nmTot, nq0, nq1, nq2, nelmt, basis0, basis1, basis2, in, \
+                            out, stream);                                                                    \
+    }
+#define HEX_NOWSP(NAME, SUF, T, BE)                                                                          \
+    int b200fe_##NAME##_##SUF(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nmTot, unsigned nq0,        \
+                              unsigned nq1, unsigned nq2, unsigned nelmt, const T *basis0, const T *basis1,  \
+                              const T *basis2, const T *in, T *out, void *stream)                            \
+    {                                                                                                        \
+        return hex_entry<T>(BE, false, nm0, nm1, nm2, nmTot, nq0, nq1, nq2, nelmt, basis0, basis1, basis2,   \
+                            in, out, stream);                                                                \
+    }
+
+HEX_WSP(BwdTransHexKernel, f64, double, Backend::Auto, false)
+HEX_WSP(BwdTransHexKernel, f32, float, Backend::Auto, false)
+HEX_WSP(BwdTransHexKernel_Coa, f64, double, Backend::Auto, true)
+HEX_WSP(BwdTransHexKernel_Coa, f32, float, Backend::Auto, true)
+HEX_WSP(BwdTransHexKernel_QP, f64, double, Backend::Auto, false)
+HEX_WSP(BwdTransHexKernel_QP, f32, float, Backend::Auto, false)
+HEX_NOWSP(BwdTransHexKernel_QP_Shared, f64, double, Backend::Auto)
+HEX_NOWSP(BwdTransHexKernel_QP_Shared, f32, float, Backend::Auto)
+HEX_WSP(BwdTransHexKernel_QP_1D, f64, double, Backend::Auto, false)
+HEX_WSP(BwdTransHexKernel_QP_1D, f32, float, Backend::Auto, false)
+HEX_NOWSP(BwdTransHexKernel_QP_1D_Shared, f64, double, Backend::Auto)
+HEX_NOWSP(BwdTransHexKernel_QP_1D_Shared, f32, float, Backend::Auto)
+
+// ---- benchmark01-03 -----------------------------------------------------------------
+#define VEC_API(SUF, T)                                                                                      \
+    int b200fe_set_data_##SUF(T *data, unsigned n, void *stream)                                             \
+    {                                                                                                        \
+        return launch_set_data<T>(data, n, false, (cudaStream_t)stream);                                     \
+    }                                                                                                        \
+    int b200fe_set_data2_##SUF(T *data, unsigned n, void *stream)                                            \
+    {                                                                                                        \
+        return launch_set_data<T>(data, n, true, (cudaStream_t)stream);                                      \
+    }                                                                                                        \
+    int b200fe_l2norm_vl_##SUF(T *sums, const T *data, unsigned n, unsigned blocks, int vl, void *stream)    \
+    {                                                                                                        \
+        return launch_reduce_partials<T>(sums, data, 0u, n, blocks, vl != 0, true, (cudaStream_t)stream);    \
+    }                                                                                                        \
+    int b200fe_reduce_vl_##SUF(T *sums, const T *data, unsigned n, int vl, void *stream)                     \
+    {                                                                                                        \
+        return launch_reduce_partials<T>(sums, data, 0u, n, 1u, vl != 0, false, (cudaStream_t)stream);       \
+    }                                                                                                        \
+    int b200fe_reduceSumKernel_sumsq_##SUF(unsigned begin, unsigned end, T *buffer, const T *data,           \
+                                           unsigned blocks, void *stream)                                    \
+    {                                                                                                        \
+        return launch_reduce_partials<T>(buffer, data, begin, end, blocks, false, true, (cudaStream_t)stream); \
+    }                                                                                                        \
+    int b200fe_add_vector_##SUF(T *x, const T *y, unsigned n, int vl, void *stream)                          \
+    {                                                                                                        \
+        return launch_add_vector<T>(x, y, 0u, n, vl != 0, (cudaStream_t)stream);                             \
+    }                                                                                                        \
+    int b200fe_vector_kernel_add_##SUF(unsigned begin, unsigned end, T *x, const T *y, void *stream)         \
+    {                                                                                                        \
+        return launch_add_vector<T>(x, y, begin, end, false, (cudaStream_t)stream);                          \
+    }                                                                                                        \
+    int b200fe_compute_matvec_##SUF(unsigned N, unsigned M, const T *A, const T *x, T *y, int vl,            \
+                                    void *stream)                                                            \
+    {                                                                                                        \
+        return launch_matvec<T>(N, M, A, x, y, vl != 0, (cudaStream_t)stream);                               \
+    }                                                                                                        \
+    int b200fe_sumsq_##SUF(const T *x, size_t n, double *result, void *scratch, void *stream)                \
+    {                                                                                                        \
+        return launch_sumsq<T>(x, n, result, scratch, false, (cudaStream_t)stream);                          \
+    }
+
+VEC_API(f64, double)
+VEC_API(f32, float)
+
+size_t b200fe_sumsq_scratch_bytes(void)
+{
+    return sumsq_scratch_bytes();
+}
+
+// ---- host-buffer operator ---------------------------------------------------------------
+#define HOST_API(SUF, T)                                                                                     \
+    int b200fe_bwdtrans_quad_host_##SUF(unsigned nq0, unsigned nq1, size_t nelmt, const T *basis0_host,      \
+                                        const T *basis1_host, const T *in_host, T *out_host,                 \
+                                        double *sumsq_host)                                                  \
+    {                                                                                                        \
+        const unsigned nq[3]  = {nq0, nq1, 0};                                                               \
+        const T *const bs[3]  = {basis0_host, basis1_host, nullptr};                                         \
+        return host_pipeline<T>(2, nq, nelmt, bs, in_host, out_host, sumsq_host);                            \
+    }                                                                                                        \
+    int b200fe_bwdtrans_hex_host_##SUF(unsigned nq0, unsigned nq1, unsigned nq2, size_t nelmt,               \
+                                       const T *basis0_host, const T *basis1_host, const T *basis2_host,     \
+                                       const T *in_host, T *out_host, double *sumsq_host)                    \
+    {                                                                                                        \
+        const unsigned nq[3]  = {nq0, nq1, nq2};                                                             \
+        const T *const bs[3]  = {basis0_host, basis1_host, basis2_host};                                     \
+        return host_pipeline<T>(3, nq, nelmt, bs, in_host, out_host, sumsq_host);                            \
+    }
+
+HOST_API(f64, double)
+HOST_API(f32, float)
+
+} // extern "C"

@@ -1,0 +1,147 @@
+// common.cuh -- shared device/host helpers of libb200fe (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+
+#include "../../include/b200fe.h"
+
+namespace b200fe
+{
+
+// ---- host-side bookkeeping ---------------------------------------------------
+extern std::atomic<unsigned long long> g_launch_count; // defined in capi.cu
+extern thread_local const char *t_last_backend;
+
+inline void count_launch(unsigned n = 1u)
+{
+    g_launch_count.fetch_add(n, std::memory_order_relaxed);
+}
+
+#define B200FE_CUDA_TRY(expr)                                                                                \
+    do                                                                                                       \
+    {                                                                                                        \
+        cudaError_t err__ = (expr);                                                                          \
+        if (err__ != cudaSuccess)                                                                            \
+            return (int)err__;                                                                               \
+    } while (0)
+
+inline int launch_status()
+{
+    return (int)cudaGetLastError();
+}
+
+constexpr int kSmemMax = 227 * 1024; // opt-in dynamic shared memory per CTA on sm_100
+
+// ---- 16-byte vector types ----------------------------------------------------
+template <typename T> struct Vec16;
+template <> struct Vec16<double>
+{
+    using type             = double2;
+    static constexpr int W = 2;
+};
+template <> struct Vec16<float>
+{
+    using type             = float4;
+    static constexpr int W = 4;
+};
+
+// streaming (evict-first) global accesses: every field is touched exactly once
+template <typename V> __device__ __forceinline__ V ld_stream(const V *p)
+{
+    return __ldcs(p);
+}
+template <typename V> __device__ __forceinline__ void st_stream(V *p, const V &v)
+{
+    __stcs(p, v);
+}
+
+__device__ __forceinline__ double fmadd(double a, double b, double c)
+{
+    return __fma_rn(a, b, c);
+}
+__device__ __forceinline__ float fmadd(float a, float b, float c)
+{
+    return __fmaf_rn(a, b, c);
+}
+
+// ---- per-device basis bank in constant memory -------------------------------------
+// With every (p, i) loop unrolled the basis index is a compile-time constant, so
+// the FMA takes its basis operand straight from the constant bank (c[3][imm]):
+// no load instruction, no register, no shared-memory traffic.  Sized for quad
+// nq <= 32 (2*31*32) and hex nq <= 16 (3*15*16).  `static`: one bank per
+// translation unit, filled by that unit's launcher.
+constexpr int kBasisBankElems = 1984;
+static __constant__ double c_basis_f64[kBasisBankElems];
+static __constant__ float c_basis_f32[kBasisBankElems];
+
+template <typename T> __device__ __forceinline__ T cbasis(int i);
+template <> __device__ __forceinline__ double cbasis<double>(int i)
+{
+    return c_basis_f64[i];
+}
+template <> __device__ __forceinline__ float cbasis<float>(int i)
+{
+    return c_basis_f32[i];
+}
+
+template <typename T> inline const void *basis_bank_symbol();
+template <> inline const void *basis_bank_symbol<double>()
+{
+    return (const void *)c_basis_f64;
+}
+template <> inline const void *basis_bank_symbol<float>()
+{
+    return (const void *)c_basis_f32;
+}
+
+// Stream-ordered device->constant copy of up to three basis matrices.
+// The bank is per device and per translation unit; two streams of one device
+// must not overwrite it under each other's kernels, so each fill waits for the
+// previous user of the bank (event) unless it is the same stream.
+struct BankGuard
+{
+    cudaEvent_t done[64] = {};
+    cudaStream_t last[64] = {};
+    bool used[64]         = {};
+};
+
+template <typename T>
+inline int fill_basis_bank(BankGuard &g, int nb, const T *const *basis, const int *count, cudaStream_t stream)
+{
+    int dev = 0;
+    B200FE_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64)
+        return B200FE_EUNSUPPORTED;
+    if (g.used[dev] && g.last[dev] != stream)
+        B200FE_CUDA_TRY(cudaStreamWaitEvent(stream, g.done[dev], 0));
+    size_t off = 0;
+    for (int b = 0; b < nb; ++b)
+    {
+        const size_t bytes = (size_t)count[b] * sizeof(T);
+        if (std::is_same<T, double>::value)
+            B200FE_CUDA_TRY(cudaMemcpyToSymbolAsync(c_basis_f64, basis[b], bytes, off, cudaMemcpyDeviceToDevice,
+                                                    stream));
+        else
+            B200FE_CUDA_TRY(cudaMemcpyToSymbolAsync(c_basis_f32, basis[b], bytes, off, cudaMemcpyDeviceToDevice,
+                                                    stream));
+        off += bytes;
+    }
+    return 0;
+}
+
+inline int release_basis_bank(BankGuard &g, cudaStream_t stream)
+{
+    int dev = 0;
+    B200FE_CUDA_TRY(cudaGetDevice(&dev));
+    if (!g.done[dev])
+        B200FE_CUDA_TRY(cudaEventCreateWithFlags(&g.done[dev], cudaEventDisableTiming));
+    B200FE_CUDA_TRY(cudaEventRecord(g.done[dev], stream));
+    g.last[dev] = stream;
+    g.used[dev] = true;
+    return 0;
+}
+
+} // namespace b200fe

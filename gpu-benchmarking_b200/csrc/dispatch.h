@@ -1,0 +1,27 @@
+// dispatch.h -- internal C++ interface between the C ABI (capi.cu) and the
+// per-dtype kernel translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+
+namespace b200fe
+{
+
+enum class Backend : int
+{
+    Auto    = 0,
+    Rows    = 1, // element-batched row contractions through shared memory (element-major)
+    Tpe     = 2, // thread per element, registers only (interleaved layout)
+    Generic = 3, // run-time sizes, any shape
+};
+
+// element-major unless coa; return 0 / cudaError_t / negative B200FE_E*
+template <typename T>
+int run_bwdtrans_quad(Backend be, bool coa, unsigned nm0, unsigned nm1, unsigned nq0, unsigned nq1, unsigned nelmt,
+                      const T *b0, const T *b1, const T *in, T *out, cudaStream_t stream);
+template <typename T>
+int run_bwdtrans_hex(Backend be, bool coa, unsigned nm0, unsigned nm1, unsigned nm2, unsigned nq0, unsigned nq1,
+                     unsigned nq2, unsigned nelmt, const T *b0, const T *b1, const T *b2, const T *in, T *out,
+                     cudaStream_t stream);
+
+} // namespace b200fe

@@ -1,0 +1,526 @@
+// vec_kernels.cu -- the 1-D streaming / reduction / row-dot kernels behind
+// benchmark01-03 (reference: utils/cuda_vectors.h users) and the checksum that
+// replaces thrust::transform_reduce.
+//
+// Common shape: grid-stride loops over 16-byte vectors (double2 / float4) with
+// four independent loads in flight per thread, scalar tail taken from the END
+// of the array exactly like the reference (benchmark01.cc:56-63), per-thread
+// partial sums, xor-shuffle warp reduction, fixed-order combination of the warp
+// sums through shared memory.  No atomics anywhere: unlike the reference's
+// per-warp atomicAdd (benchmark01.cc:72-76) every result is reproducible run to
+// run.
+#include <type_traits>
+
+#include "common.cuh"
+#include "vec_kernels.h"
+
+namespace b200fe
+{
+
+constexpr int kRedThreads = 256;
+
+template <typename A> __device__ __forceinline__ A warp_sum(A v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// block-wide sum, result valid in thread 0; fixed combination order
+template <typename A, int THREADS> __device__ __forceinline__ A block_sum(A v)
+{
+    __shared__ A warp_part[THREADS / 32];
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0)
+        warp_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    A total = A(0);
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int w = 0; w < THREADS / 32; ++w)
+            total += warp_part[w];
+    }
+    __syncthreads(); // warp_part is reused by the next call
+    return total;
+}
+
+// component-wise vector accumulation, the device-side counterpart of the
+// reference's float4/double2 operators (utils/cuda_vectors.h:7-141)
+__device__ __forceinline__ void sq_acc(double2 &a, const double2 v)
+{
+    a.x = fmadd(v.x, v.x, a.x);
+    a.y = fmadd(v.y, v.y, a.y);
+}
+__device__ __forceinline__ void sq_acc(float4 &a, const float4 v)
+{
+    a.x = fmadd(v.x, v.x, a.x);
+    a.y = fmadd(v.y, v.y, a.y);
+    a.z = fmadd(v.z, v.z, a.z);
+    a.w = fmadd(v.w, v.w, a.w);
+}
+__device__ __forceinline__ void dot_acc(double2 &a, const double2 u, const double2 v)
+{
+    a.x = fmadd(u.x, v.x, a.x);
+    a.y = fmadd(u.y, v.y, a.y);
+}
+__device__ __forceinline__ void dot_acc(float4 &a, const float4 u, const float4 v)
+{
+    a.x = fmadd(u.x, v.x, a.x);
+    a.y = fmadd(u.y, v.y, a.y);
+    a.z = fmadd(u.z, v.z, a.z);
+    a.w = fmadd(u.w, v.w, a.w);
+}
+__device__ __forceinline__ void add_acc(double2 &a, const double2 v)
+{
+    a.x += v.x;
+    a.y += v.y;
+}
+__device__ __forceinline__ void add_acc(float4 &a, const float4 v)
+{
+    a.x += v.x;
+    a.y += v.y;
+    a.z += v.z;
+    a.w += v.w;
+}
+__device__ __forceinline__ double hsum(const double2 v)
+{
+    return v.x + v.y;
+}
+__device__ __forceinline__ float hsum(const float4 v)
+{
+    return v.x + v.y + v.z + v.w;
+}
+template <typename V> __device__ __forceinline__ V vzero();
+template <> __device__ __forceinline__ double2 vzero<double2>()
+{
+    return make_double2(0.0, 0.0);
+}
+template <> __device__ __forceinline__ float4 vzero<float4>()
+{
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// ---- benchmark01 ----------------------------------------------------------------
+
+// sums[blockIdx.x] = partial of sum_{i in [begin,end)} f(data[i]); SQUARE picks
+// x*x (l2norm_vl / reduceSumKernel functor) or x (reduce_vl).  Entries
+// sums[gridDim.x .. slots) are zeroed so that a consumer may add all `slots`.
+template <typename T, bool VL, bool SQUARE>
+__global__ void __launch_bounds__(kRedThreads)
+    reduce_partials_kernel(T *__restrict__ sums, const T *__restrict__ data, unsigned begin, unsigned end,
+                           unsigned slots)
+{
+    using V         = typename Vec16<T>::type;
+    constexpr int W = Vec16<T>::W;
+    const unsigned n      = end - begin;
+    const T *x            = data + begin;
+    const unsigned rank   = blockIdx.x * kRedThreads + threadIdx.x;
+    const unsigned stride = gridDim.x * kRedThreads;
+    T v                   = T(0);
+
+    if (VL)
+    {
+        const unsigned nv = n / W;
+        const V *xv       = reinterpret_cast<const V *>(x);
+        V acc0 = vzero<V>(), acc1 = vzero<V>(), acc2 = vzero<V>(), acc3 = vzero<V>();
+        unsigned t = rank;
+        for (; t + 3 * (size_t)stride < nv; t += 4 * stride)
+        {
+            const V a = ld_stream(xv + t), b = ld_stream(xv + t + stride), c = ld_stream(xv + t + 2 * stride),
+                    d = ld_stream(xv + t + 3 * stride);
+            if (SQUARE)
+            {
+                sq_acc(acc0, a);
+                sq_acc(acc1, b);
+                sq_acc(acc2, c);
+                sq_acc(acc3, d);
+            }
+            else
+            {
+                add_acc(acc0, a);
+                add_acc(acc1, b);
+                add_acc(acc2, c);
+                add_acc(acc3, d);
+            }
+        }
+        for (; t < nv; t += stride)
+        {
+            const V a = ld_stream(xv + t);
+            if (SQUARE)
+                sq_acc(acc0, a);
+            else
+                add_acc(acc0, a);
+        }
+        add_acc(acc0, acc1);
+        add_acc(acc2, acc3);
+        add_acc(acc0, acc2);
+        v = hsum(acc0);
+        // final n % W values, taken from the end like benchmark01.cc:56-63
+        if (rank < n % W)
+        {
+            const T a = x[n - 1u - rank];
+            v += SQUARE ? a * a : a;
+        }
+    }
+    else
+    {
+        T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
+        unsigned t = rank;
+        for (; t + 3 * (size_t)stride < n; t += 4 * stride)
+        {
+            const T a = ld_stream(x + t), b = ld_stream(x + t + stride), c = ld_stream(x + t + 2 * stride),
+                    d = ld_stream(x + t + 3 * stride);
+            a0 = SQUARE ? fmadd(a, a, a0) : a0 + a;
+            a1 = SQUARE ? fmadd(b, b, a1) : a1 + b;
+            a2 = SQUARE ? fmadd(c, c, a2) : a2 + c;
+            a3 = SQUARE ? fmadd(d, d, a3) : a3 + d;
+        }
+        for (; t < n; t += stride)
+        {
+            const T a = ld_stream(x + t);
+            a0        = SQUARE ? fmadd(a, a, a0) : a0 + a;
+        }
+        v = (a0 + a1) + (a2 + a3);
+    }
+
+    const T total = block_sum<T, kRedThreads>(v);
+    if (threadIdx.x == 0)
+        sums[blockIdx.x] = total;
+    if (blockIdx.x == 0)
+        for (unsigned s = gridDim.x + threadIdx.x; s < slots; s += kRedThreads)
+            sums[s] = T(0);
+}
+
+template <typename T>
+__global__ void set_data_kernel(T *__restrict__ data, unsigned n, int second)
+{
+    // i % 13 + (0.2 + 1e-5 * (i % 100191))  (benchmark01.cc:178), or the
+    // benchmark02.cc:143 variant.  Integer modulo on unsigned, then double
+    // arithmetic with each operation rounded separately (no FMA contraction),
+    // so the values equal the host-side generator bit for bit.
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    {
+        double v;
+        if (second)
+            v = __dadd_rn((double)(i % 8u), __dadd_rn(0.4, __dmul_rn(0.00003, (double)(i % 100721u))));
+        else
+            v = __dadd_rn((double)(i % 13u), __dadd_rn(0.2, __dmul_rn(0.00001, (double)(i % 100191u))));
+        data[i] = (T)v;
+        if (i + stride < i)
+            break; // unsigned wrap guard for n close to 2^32
+    }
+}
+
+// ---- benchmark02 --------------------------------------------------------------------
+
+template <typename T, bool VL>
+__global__ void __launch_bounds__(256) add_vector_kernel(T *__restrict__ x, const T *__restrict__ y, unsigned begin,
+                                                         unsigned end)
+{
+    using V         = typename Vec16<T>::type;
+    constexpr int W = Vec16<T>::W;
+    const unsigned n      = end - begin;
+    T *xs                 = x + begin;
+    const T *ys           = y + begin;
+    const unsigned rank   = blockIdx.x * 256u + threadIdx.x;
+    const unsigned stride = gridDim.x * 256u;
+    if (VL)
+    {
+        const unsigned nv = n / W;
+        V *xv             = reinterpret_cast<V *>(xs);
+        const V *yv       = reinterpret_cast<const V *>(ys);
+        unsigned t        = rank;
+        for (; t + (size_t)stride < nv; t += 2 * stride)
+        {
+            V a = ld_stream(xv + t), c = ld_stream(xv + t + stride);
+            const V b = ld_stream(yv + t), d = ld_stream(yv + t + stride);
+            add_acc(a, b);
+            add_acc(c, d);
+            st_stream(xv + t, a);
+            st_stream(xv + t + stride, c);
+        }
+        for (; t < nv; t += stride)
+        {
+            V a = ld_stream(xv + t);
+            add_acc(a, ld_stream(yv + t));
+            st_stream(xv + t, a);
+        }
+        if (rank < n % W)
+        {
+            const unsigned id = n - 1u - rank; // benchmark02.cc:50-57
+            xs[id] += ys[id];
+        }
+    }
+    else
+    {
+        unsigned t = rank;
+        for (; t + 3 * (size_t)stride < n; t += 4 * stride)
+        {
+            const T a = ld_stream(xs + t), b = ld_stream(xs + t + stride), c = ld_stream(xs + t + 2 * stride),
+                    d = ld_stream(xs + t + 3 * stride);
+            const T e = ld_stream(ys + t), f = ld_stream(ys + t + stride), g = ld_stream(ys + t + 2 * stride),
+                    h = ld_stream(ys + t + 3 * stride);
+            st_stream(xs + t, a + e);
+            st_stream(xs + t + stride, b + f);
+            st_stream(xs + t + 2 * stride, c + g);
+            st_stream(xs + t + 3 * stride, d + h);
+        }
+        for (; t < n; t += stride)
+            st_stream(xs + t, ld_stream(xs + t) + ld_stream(ys + t));
+    }
+}
+
+// ---- benchmark03 --------------------------------------------------------------------
+
+// y[i] = A[i,:] . x.  LANES threads cooperate on a row (32: a warp per row, for
+// short rows; 256: a CTA per row); A is streamed once, x stays cache resident.
+template <typename T, bool VL, int LANES>
+__global__ void __launch_bounds__(256)
+    matvec_kernel(unsigned N, unsigned M, const T *__restrict__ A, const T *__restrict__ x, T *__restrict__ y)
+{
+    using V                = typename Vec16<T>::type;
+    constexpr int W        = Vec16<T>::W;
+    constexpr int ROWS_CTA = 256 / LANES;
+    const unsigned lane    = threadIdx.x % LANES;
+    const unsigned sub     = threadIdx.x / LANES;
+    for (unsigned row0 = blockIdx.x * ROWS_CTA; row0 < M; row0 += gridDim.x * ROWS_CTA)
+    {
+        const unsigned i = row0 + sub;
+        T v              = T(0);
+        if (i < M)
+        {
+            const T *a = A + (size_t)i * N;
+            // rows start 16-byte aligned only if N*sizeof(T) is a multiple of 16
+            const bool vec = VL && (((size_t)N * sizeof(T)) % 16 == 0);
+            if (vec)
+            {
+                const unsigned nv = N / W;
+                const V *av       = reinterpret_cast<const V *>(a);
+                const V *xv       = reinterpret_cast<const V *>(x);
+                V acc0 = vzero<V>(), acc1 = vzero<V>();
+                unsigned t = lane;
+                for (; t + LANES < nv; t += 2 * LANES)
+                {
+                    const V a0 = ld_stream(av + t), a1 = ld_stream(av + t + LANES);
+                    dot_acc(acc0, a0, __ldg(xv + t));
+                    dot_acc(acc1, a1, __ldg(xv + t + LANES));
+                }
+                for (; t < nv; t += LANES)
+                    dot_acc(acc0, ld_stream(av + t), __ldg(xv + t));
+                add_acc(acc0, acc1);
+                v = hsum(acc0);
+            }
+            else
+            {
+                T a0 = T(0), a1 = T(0);
+                unsigned t = lane;
+                for (; t + LANES < N; t += 2 * LANES)
+                {
+                    a0 = fmadd(ld_stream(a + t), __ldg(x + t), a0);
+                    a1 = fmadd(ld_stream(a + t + LANES), __ldg(x + t + LANES), a1);
+                }
+                for (; t < N; t += LANES)
+                    a0 = fmadd(ld_stream(a + t), __ldg(x + t), a0);
+                v = a0 + a1;
+            }
+        }
+        if (LANES == 32)
+        {
+            v = warp_sum(v);
+            if (lane == 0 && i < M)
+                y[i] = v;
+        }
+        else
+        {
+            const T total = block_sum<T, 256>(v);
+            if (threadIdx.x == 0 && i < M)
+                y[i] = total;
+        }
+    }
+}
+
+// ---- checksum -------------------------------------------------------------------------
+
+constexpr int kSumsqBlocks = 148 * 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kRedThreads) sumsq_partials_kernel(const T *__restrict__ x, size_t n,
+                                                                     double *__restrict__ part)
+{
+    using V         = typename Vec16<T>::type;
+    constexpr int W = Vec16<T>::W;
+    const size_t rank   = (size_t)blockIdx.x * kRedThreads + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * kRedThreads;
+    double a0 = 0.0, a1 = 0.0;
+    const bool vec = (reinterpret_cast<uintptr_t>(x) & 15u) == 0;
+    size_t done    = 0;
+    if (vec)
+    {
+        const size_t nv = n / W;
+        const V *xv     = reinterpret_cast<const V *>(x);
+        size_t t        = rank;
+        for (; t + stride < nv; t += 2 * stride)
+        {
+            const V a = ld_stream(xv + t), b = ld_stream(xv + t + stride);
+            const T *pa = reinterpret_cast<const T *>(&a), *pb = reinterpret_cast<const T *>(&b);
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+            {
+                a0 = fmadd((double)pa[k], (double)pa[k], a0);
+                a1 = fmadd((double)pb[k], (double)pb[k], a1);
+            }
+        }
+        for (; t < nv; t += stride)
+        {
+            const V a   = ld_stream(xv + t);
+            const T *pa = reinterpret_cast<const T *>(&a);
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+                a0 = fmadd((double)pa[k], (double)pa[k], a0);
+        }
+        done = nv * W;
+    }
+    for (size_t t = done + rank; t < n; t += stride)
+    {
+        const double a = (double)x[t];
+        a0             = fmadd(a, a, a0);
+    }
+    const double total = block_sum<double, kRedThreads>(a0 + a1);
+    if (threadIdx.x == 0)
+        part[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kRedThreads) sum_final_kernel(const double *__restrict__ part, unsigned n,
+                                                                double *__restrict__ result, int accumulate)
+{
+    double v = 0.0;
+    for (unsigned t = threadIdx.x; t < n; t += kRedThreads)
+        v += part[t];
+    const double total = block_sum<double, kRedThreads>(v);
+    if (threadIdx.x == 0)
+        *result = accumulate ? *result + total : total;
+}
+
+// ---- launchers ----------------------------------------------------------------------------
+
+static inline unsigned clampu(unsigned v, unsigned lo, unsigned hi)
+{
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
+template <typename T>
+int launch_reduce_partials(T *sums, const T *data, unsigned begin, unsigned end, unsigned slots, bool vl, bool square,
+                           cudaStream_t s)
+{
+    if (!sums || !data || end < begin || slots == 0)
+        return B200FE_EINVAL;
+    constexpr unsigned W = Vec16<T>::W;
+    if (vl && ((reinterpret_cast<uintptr_t>(data + begin) & 15u) != 0))
+        vl = false; // unaligned sub-range: scalar loads, same result
+    const unsigned n    = end - begin;
+    const unsigned work = vl ? n / W : n;
+    unsigned grid       = clampu((work + kRedThreads * 4 - 1) / (kRedThreads * 4), 1u, slots);
+    grid                = grid > 148u * 8u ? 148u * 8u : grid;
+    if (vl && square)
+        reduce_partials_kernel<T, true, true><<<grid, kRedThreads, 0, s>>>(sums, data, begin, end, slots);
+    else if (vl)
+        reduce_partials_kernel<T, true, false><<<grid, kRedThreads, 0, s>>>(sums, data, begin, end, slots);
+    else if (square)
+        reduce_partials_kernel<T, false, true><<<grid, kRedThreads, 0, s>>>(sums, data, begin, end, slots);
+    else
+        reduce_partials_kernel<T, false, false><<<grid, kRedThreads, 0, s>>>(sums, data, begin, end, slots);
+    count_launch();
+    return launch_status();
+}
+
+template <typename T> int launch_set_data(T *data, unsigned n, bool second, cudaStream_t s)
+{
+    if (!data)
+        return B200FE_EINVAL;
+    if (n == 0)
+        return 0;
+    const unsigned grid = clampu((n + 1023u) / 1024u, 1u, 148u * 16u);
+    set_data_kernel<T><<<grid, 256, 0, s>>>(data, n, second ? 1 : 0);
+    count_launch();
+    return launch_status();
+}
+
+template <typename T> int launch_add_vector(T *x, const T *y, unsigned begin, unsigned end, bool vl, cudaStream_t s)
+{
+    if (!x || !y || end < begin)
+        return B200FE_EINVAL;
+    if (end == begin)
+        return 0;
+    constexpr unsigned W = Vec16<T>::W;
+    if (vl && (((reinterpret_cast<uintptr_t>(x + begin) | reinterpret_cast<uintptr_t>(y + begin)) & 15u) != 0))
+        vl = false;
+    const unsigned n    = end - begin;
+    const unsigned work = vl ? n / W : n;
+    // ~2 vectors (or 4 scalars) per thread per trip, at most 16 CTAs of 256 threads per SM
+    const unsigned per  = vl ? 2u : 4u;
+    const unsigned grid = clampu((work + 256u * per - 1) / (256u * per), 1u, 148u * 16u);
+    if (vl)
+        add_vector_kernel<T, true><<<grid, 256, 0, s>>>(x, y, begin, end);
+    else
+        add_vector_kernel<T, false><<<grid, 256, 0, s>>>(x, y, begin, end);
+    count_launch();
+    return launch_status();
+}
+
+template <typename T> int launch_matvec(unsigned N, unsigned M, const T *A, const T *x, T *y, bool vl, cudaStream_t s)
+{
+    if (!A || !x || !y)
+        return B200FE_EINVAL;
+    if (M == 0)
+        return 0;
+    if (vl && (((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(x)) & 15u) != 0))
+        vl = false;
+    const bool warp_rows = N <= 2048u;
+    const unsigned rows  = warp_rows ? 8u : 1u;
+    const unsigned grid  = clampu((M + rows - 1) / rows, 1u, 148u * 8u);
+#define MV(VL_, LANES_) matvec_kernel<T, VL_, LANES_><<<grid, 256, 0, s>>>(N, M, A, x, y)
+    if (vl && warp_rows)
+        MV(true, 32);
+    else if (vl)
+        MV(true, 256);
+    else if (warp_rows)
+        MV(false, 32);
+    else
+        MV(false, 256);
+#undef MV
+    count_launch();
+    return launch_status();
+}
+
+size_t sumsq_scratch_bytes()
+{
+    return (size_t)kSumsqBlocks * sizeof(double);
+}
+
+template <typename T> int launch_sumsq(const T *x, size_t n, double *result, void *scratch, bool accumulate, cudaStream_t s)
+{
+    if (!x || !result || !scratch)
+        return B200FE_EINVAL;
+    double *part = reinterpret_cast<double *>(scratch);
+    size_t want  = (n + (size_t)kRedThreads * 8 - 1) / ((size_t)kRedThreads * 8);
+    const unsigned grid = (unsigned)(want < 1 ? 1 : (want > (size_t)kSumsqBlocks ? (size_t)kSumsqBlocks : want));
+    sumsq_partials_kernel<T><<<grid, kRedThreads, 0, s>>>(x, n, part);
+    sum_final_kernel<<<1, kRedThreads, 0, s>>>(part, grid, result, accumulate ? 1 : 0);
+    count_launch(2);
+    return launch_status();
+}
+
+#define INST(T)                                                                                              \
+    template int launch_reduce_partials<T>(T *, const T *, unsigned, unsigned, unsigned, bool, bool, cudaStream_t); \
+    template int launch_set_data<T>(T *, unsigned, bool, cudaStream_t);                                       \
+    template int launch_add_vector<T>(T *, const T *, unsigned, unsigned, bool, cudaStream_t);                \
+    template int launch_matvec<T>(unsigned, unsigned, const T *, const T *, T *, bool, cudaStream_t);         \
+    template int launch_sumsq<T>(const T *, size_t, double *, void *, bool, cudaStream_t);
+INST(double)
+INST(float)
+#undef INST
+
+} // namespace b200fe

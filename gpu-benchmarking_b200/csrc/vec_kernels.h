@@ -1,0 +1,16 @@
+// vec_kernels.h -- launchers of vec_kernels.cu (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace b200fe
+{
+template <typename T>
+int launch_reduce_partials(T *sums, const T *data, unsigned begin, unsigned end, unsigned slots, bool vl, bool square,
+                           cudaStream_t s);
+template <typename T> int launch_set_data(T *data, unsigned n, bool second, cudaStream_t s);
+template <typename T> int launch_add_vector(T *x, const T *y, unsigned begin, unsigned end, bool vl, cudaStream_t s);
+template <typename T> int launch_matvec(unsigned N, unsigned M, const T *A, const T *x, T *y, bool vl, cudaStream_t s);
+size_t sumsq_scratch_bytes();
+template <typename T> int launch_sumsq(const T *x, size_t n, double *result, void *scratch, bool accumulate, cudaStream_t s);
+} // namespace b200fe

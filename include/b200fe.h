@@ -1,0 +1,265 @@
+/*
+ * b200fe.h -- C ABI of libb200fe.so: B200 (sm_100a) kernels for the hot path
+ * of CFD-Xing/gpu-benchmarking.
+ *
+ * The reference has no FFI: run_test<T>() launches its templated __global__
+ * functions inline with <<<grid, block, smem>>>.  This header declares one
+ * extern "C" entry point per reference kernel and dtype; each takes the same
+ * scalars and device pointers in the same order as the kernel it replaces
+ * (cited at each declaration, paths relative to the reference root), plus a
+ * stream.  Conventions:
+ *
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - the caller owns every buffer (cudaMalloc/cudaFree), including the
+ *     scratch wsp* arrays of the reference signatures, which these kernels
+ *     accept and ignore (all intermediates stay on chip);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *     calls are asynchronous exactly like a kernel launch;
+ *   - return value: 0 on success, a positive cudaError_t on a CUDA failure,
+ *     a negative B200FE_E* code on a rejected argument.  Nothing throws,
+ *     nothing calls exit(), nothing falls back to the CPU;
+ *   - the grid/block/smem of the reference launch are chosen internally;
+ *     where the reference's launch shape is observable through a buffer size
+ *     (benchmark01's `sums[blocks]`) the entry point takes it as an argument;
+ *   - thread safety: any number of host threads may call concurrently on
+ *     different devices; calls on one device from several streams are
+ *     serialised with events where they share the per-device basis bank.
+ *
+ * Data layouts:  nm = nq - 1 modes per direction.
+ *   element-major  in[e*nmTot + (r*nm1 + q)*nm0 + p]   out[e*nqTot + (k*nq1 + j)*nq0 + i]
+ *   interleaved    x[(e/32)*32*len + 32*idx + e%32]    (idx = in-element index above)
+ *   basis          B[p*nq + i]
+ */
+#ifndef B200FE_H
+#define B200FE_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
+#endif
+
+#define B200FE_OK 0
+#define B200FE_EINVAL (-1)      /* null pointer, zero size, nm != nq-1 ... */
+#define B200FE_EUNSUPPORTED (-2) /* shape outside what the library instantiates */
+#define B200FE_EALIGN (-3)      /* pointer not aligned to sizeof(T) */
+#define B200FE_ENODEVICE (-4)   /* no CUDA device / not an sm_100 device */
+
+/* ---- library ------------------------------------------------------------- */
+
+/* "b200fe <ver> sm_100a" */
+const char *b200fe_version(void);
+/* number of CUDA kernels this library has launched in the calling process
+ * (bench.py reports the delta over the timed region as gpu_launches) */
+unsigned long long b200fe_launch_count(void);
+/* name of the back-end the last BwdTrans call on this thread dispatched to */
+const char *b200fe_last_backend(void);
+/* 0 if the current device is usable (compute capability 10.x), else an error */
+int b200fe_check_device(void);
+
+/* ---- benchmark04: quad BwdTrans -------------------------------------------
+ * out[e][j][i] = sum_q ( sum_p in[e][q][p] B0[p][i] ) B1[q][j]
+ * p-then-q summation order per output, identical to every reference variant.
+ * nmTot = nm0*nm1.  All six compute the same operator; they differ in the
+ * layout they accept (only _Coa is interleaved and needs nelmt % 32 == 0) and
+ * in the back-end they prefer (DESIGN.md "entry point -> back-end"). */
+
+/* replaces BwdTransQuadKernel<T,true>            benchmark04/benchmark04.cc:15-76 */
+int b200fe_BwdTransQuadKernel_f64(unsigned nm0, unsigned nm1, unsigned nmTot, unsigned nq0, unsigned nq1,
+                                  unsigned nelmt, const double *basis0, const double *basis1,
+                                  const double *in, double *wsp, double *out, void *stream);
+int b200fe_BwdTransQuadKernel_f32(unsigned nm0, unsigned nm1, unsigned nmTot, unsigned nq0, unsigned nq1,
+                                  unsigned nelmt, const float *basis0, const float *basis1, const float *in,
+                                  float *wsp, float *out, void *stream);
+/* replaces BwdTransQuadKernel_Coa<T,true>        benchmark04/benchmark04.cc:78-147 */
+int b200fe_BwdTransQuadKernel_Coa_f64(unsigned nm0, unsigned nm1, unsigned nmTot, unsigned nq0, unsigned nq1,
+                                      unsigned nelmt, const double *basis0, const double *basis1,
+                                      const double *in, double *wsp, double *out, void *stream);
+int b200fe_BwdTransQuadKernel_Coa_f32(unsigned nm0, unsigned nm1, unsigned nmTot, unsigned nq0, unsigned nq1,
+                                      unsigned nelmt, const float *basis0, const float *basis1,
+                                      const float *in, float *wsp, float *out, void *stream);
+/* replaces BwdTransQuadKernel_QP<T> (global wsp)  benchmark04/benchmark04.cc:149-204 */
+int b200fe_BwdTransQuadKernel_QP_f64(unsigned nm0, unsigned nm1, unsigned nmTot, unsigned nq0, unsigned nq1,
+                                     unsigned nelmt, const double *basis0, const double *basis1,
+                                     const double *in, double *wsp, double *out, void *stream);
+int b200fe_BwdTransQuadKernel_QP_f32(unsigned nm0, unsigned nm1, unsigned nmTot, unsigned nq0, unsigned nq1,
+                                     unsigned nelmt, const float *basis0, const float *basis1, const float *in,
+                                     float *wsp, float *out, void *stream);
+/* replaces BwdTransQuadKernel_QP<T> (shared)      benchmark04/benchmark04.cc:206-300 */
+int b200fe_BwdTransQuadKernel_QP_Shared_f64(unsigned nm0, unsigned nm1, unsigned nmTot, unsigned nq0,
+                                            unsigned nq1, unsigned nelmt, const double *basis0,
+                                            const double *basis1, const double *in, double *out, void *stream);
+int b200fe_BwdTransQuadKernel_QP_Shared_f32(unsigned nm0, unsigned nm1, unsigned nmTot, unsigned nq0,
+                                            unsigned nq1, unsigned nelmt, const float *basis0,
+                                            const float *basis1, const float *in, float *out, void *stream);
+/* replaces BwdTransQuadKernel_QP_1D<T> (global)   benchmark04/benchmark04.cc:302-351 */
+int b200fe_BwdTransQuadKernel_QP_1D_f64(unsigned nm0, unsigned nm1, unsigned nmTot, unsigned nq0, unsigned nq1,
+                                        unsigned nelmt, const double *basis0, const double *basis1,
+                                        const double *in, double *wsp, double *out, void *stream);
+int b200fe_BwdTransQuadKernel_QP_1D_f32(unsigned nm0, unsigned nm1, unsigned nmTot, unsigned nq0, unsigned nq1,
+                                        unsigned nelmt, const float *basis0, const float *basis1,
+                                        const float *in, float *wsp, float *out, void *stream);
+/* replaces BwdTransQuadKernel_QP_1D<T> (shared)   benchmark04/benchmark04.cc:353-426 */
+int b200fe_BwdTransQuadKernel_QP_1D_Shared_f64(unsigned nm0, unsigned nm1, unsigned nmTot, unsigned nq0,
+                                               unsigned nq1, unsigned nelmt, const double *basis0,
+                                               const double *basis1, const double *in, double *out,
+                                               void *stream);
+int b200fe_BwdTransQuadKernel_QP_1D_Shared_f32(unsigned nm0, unsigned nm1, unsigned nmTot, unsigned nq0,
+                                               unsigned nq1, unsigned nelmt, const float *basis0,
+                                               const float *basis1, const float *in, float *out, void *stream);
+
+/* ---- benchmark05: hex BwdTrans ---------------------------------------------
+ * out[e][k][j][i] = sum_r ( sum_q ( sum_p in[e][r][q][p] B0[p][i] ) B1[q][j] ) B2[r][k]
+ * nmTot = nm0*nm1*nm2.  _Coa implements the INTENDED interleaved output
+ * offset (e/32)*32*nq0*nq1*nq2 (reference Kokkos twin, benchmark05.cc:810-812);
+ * the reference CUDA kernel drops *nq2 at benchmark05.cc:193 (a bug). */
+
+/* replaces BwdTransHexKernel<T,true>             benchmark05/benchmark05.cc:15-102 */
+int b200fe_BwdTransHexKernel_f64(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nmTot, unsigned nq0,
+                                 unsigned nq1, unsigned nq2, unsigned nelmt, const double *basis0,
+                                 const double *basis1, const double *basis2, const double *in, double *wsp0,
+                                 double *wsp1, double *out, void *stream);
+int b200fe_BwdTransHexKernel_f32(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nmTot, unsigned nq0,
+                                 unsigned nq1, unsigned nq2, unsigned nelmt, const float *basis0,
+                                 const float *basis1, const float *basis2, const float *in, float *wsp0,
+                                 float *wsp1, float *out, void *stream);
+/* replaces BwdTransHexKernel_Coa<T,true>         benchmark05/benchmark05.cc:104-201 */
+int b200fe_BwdTransHexKernel_Coa_f64(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nmTot, unsigned nq0,
+                                     unsigned nq1, unsigned nq2, unsigned nelmt, const double *basis0,
+                                     const double *basis1, const double *basis2, const double *in,
+                                     double *wsp0, double *wsp1, double *out, void *stream);
+int b200fe_BwdTransHexKernel_Coa_f32(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nmTot, unsigned nq0,
+                                     unsigned nq1, unsigned nq2, unsigned nelmt, const float *basis0,
+                                     const float *basis1, const float *basis2, const float *in, float *wsp0,
+                                     float *wsp1, float *out, void *stream);
+/* replaces BwdTransHexKernel_QP<T> (global wsp)   benchmark05/benchmark05.cc:203-289 */
+int b200fe_BwdTransHexKernel_QP_f64(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nmTot, unsigned nq0,
+                                    unsigned nq1, unsigned nq2, unsigned nelmt, const double *basis0,
+                                    const double *basis1, const double *basis2, const double *in,
+                                    double *wsp1, double *wsp2, double *out, void *stream);
+int b200fe_BwdTransHexKernel_QP_f32(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nmTot, unsigned nq0,
+                                    unsigned nq1, unsigned nq2, unsigned nelmt, const float *basis0,
+                                    const float *basis1, const float *basis2, const float *in, float *wsp1,
+                                    float *wsp2, float *out, void *stream);
+/* replaces BwdTransHexKernel_QP<T> (shared)       benchmark05/benchmark05.cc:291-429 */
+int b200fe_BwdTransHexKernel_QP_Shared_f64(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nmTot,
+                                           unsigned nq0, unsigned nq1, unsigned nq2, unsigned nelmt,
+                                           const double *basis0, const double *basis1, const double *basis2,
+                                           const double *in, double *out, void *stream);
+int b200fe_BwdTransHexKernel_QP_Shared_f32(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nmTot,
+                                           unsigned nq0, unsigned nq1, unsigned nq2, unsigned nelmt,
+                                           const float *basis0, const float *basis1, const float *basis2,
+                                           const float *in, float *out, void *stream);
+/* replaces BwdTransHexKernel_QP_1D<T> (global)    benchmark05/benchmark05.cc:431-508 */
+int b200fe_BwdTransHexKernel_QP_1D_f64(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nmTot, unsigned nq0,
+                                       unsigned nq1, unsigned nq2, unsigned nelmt, const double *basis0,
+                                       const double *basis1, const double *basis2, const double *in,
+                                       double *wsp1, double *wsp2, double *out, void *stream);
+int b200fe_BwdTransHexKernel_QP_1D_f32(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nmTot, unsigned nq0,
+                                       unsigned nq1, unsigned nq2, unsigned nelmt, const float *basis0,
+                                       const float *basis1, const float *basis2, const float *in, float *wsp1,
+                                       float *wsp2, float *out, void *stream);
+/* replaces BwdTransHexKernel_QP_1D<T> (shared)    benchmark05/benchmark05.cc:510-617 */
+int b200fe_BwdTransHexKernel_QP_1D_Shared_f64(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nmTot,
+                                              unsigned nq0, unsigned nq1, unsigned nq2, unsigned nelmt,
+                                              const double *basis0, const double *basis1,
+                                              const double *basis2, const double *in, double *out,
+                                              void *stream);
+int b200fe_BwdTransHexKernel_QP_1D_Shared_f32(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nmTot,
+                                              unsigned nq0, unsigned nq1, unsigned nq2, unsigned nelmt,
+                                              const float *basis0, const float *basis1, const float *basis2,
+                                              const float *in, float *out, void *stream);
+
+/* ---- benchmark01: L2-norm reduction ------------------------------------------
+ * `blocks` is the reference's grid size: sums[] holds `blocks` partials
+ * (benchmark01.cc:236-241).  The partials are written, not accumulated, and
+ * every combination step runs in a fixed order: results are deterministic
+ * (the reference's per-warp atomicAdd order is not) and the cudaMemset calls
+ * of the reference's timed region are unnecessary but harmless. */
+
+/* replaces set_data<T>                            benchmark01/benchmark01.cc:171-181 */
+int b200fe_set_data_f64(double *data, unsigned n, void *stream);
+int b200fe_set_data_f32(float *data, unsigned n, void *stream);
+/* second generator y[i] = i%8 + (0.4 + 3e-5*(i%100721))   benchmark02/benchmark02.cc:143 */
+int b200fe_set_data2_f64(double *data, unsigned n, void *stream);
+int b200fe_set_data2_f32(float *data, unsigned n, void *stream);
+/* replaces l2norm_vl<T,vl>: sums[b] = partial sum of data[i]^2   benchmark01.cc:15-77 */
+int b200fe_l2norm_vl_f64(double *sums, const double *data, unsigned n, unsigned blocks, int vl, void *stream);
+int b200fe_l2norm_vl_f32(float *sums, const float *data, unsigned n, unsigned blocks, int vl, void *stream);
+/* replaces reduce_vl<T,vl><<<1,blocks>>>: sums[0] = sum of data[0..n)   benchmark01.cc:112-169 */
+int b200fe_reduce_vl_f64(double *sums, const double *data, unsigned n, int vl, void *stream);
+int b200fe_reduce_vl_f32(float *sums, const float *data, unsigned n, int vl, void *stream);
+/* replaces reduceSumKernel<T,Functor> with the one functor the reference
+ * passes, sum += d[i]*d[i] over [begin,end)      benchmark01.cc:79-110,304-306 */
+int b200fe_reduceSumKernel_sumsq_f64(unsigned begin, unsigned end, double *buffer, const double *data,
+                                     unsigned blocks, void *stream);
+int b200fe_reduceSumKernel_sumsq_f32(unsigned begin, unsigned end, float *buffer, const float *data,
+                                     unsigned blocks, void *stream);
+
+/* ---- benchmark02: vector add -------------------------------------------------- */
+
+/* replaces add_vector<T,vl>: x[i] += y[i]         benchmark02/benchmark02.cc:16-58 */
+int b200fe_add_vector_f64(double *x, const double *y, unsigned n, int vl, void *stream);
+int b200fe_add_vector_f32(float *x, const float *y, unsigned n, int vl, void *stream);
+/* replaces vector_kernel<Functor> with the one functor the reference passes,
+ * x[i] += y[i] over [begin,end)                   benchmark02.cc:60-71,227-229 */
+int b200fe_vector_kernel_add_f64(unsigned begin, unsigned end, double *x, const double *y, void *stream);
+int b200fe_vector_kernel_add_f32(unsigned begin, unsigned end, float *x, const float *y, void *stream);
+
+/* ---- benchmark03: dense mat-vec ------------------------------------------------- */
+
+/* replaces compute_matvec<T,vl>: y[i] = sum_j A[i*N+j] x[j], A row-major M x N
+ * (argument order N, M as in the reference)       benchmark03/benchmark03.cc:80-104 */
+int b200fe_compute_matvec_f64(unsigned N, unsigned M, const double *A, const double *x, double *y, int vl,
+                              void *stream);
+int b200fe_compute_matvec_f32(unsigned N, unsigned M, const float *A, const float *x, float *y, int vl,
+                              void *stream);
+
+/* ---- checksum ----------------------------------------------------------------------
+ * replaces thrust::transform_reduce(x -> x*x, plus) behind every `norm:` column
+ * (benchmark04.cc:920-923).  *result (device, double) = sum x[i]^2, accumulated
+ * in double whatever T is, deterministic.  scratch: >= b200fe_sumsq_scratch_bytes()
+ * bytes of device memory. */
+size_t b200fe_sumsq_scratch_bytes(void);
+int b200fe_sumsq_f64(const double *x, size_t n, double *result, void *scratch, void *stream);
+int b200fe_sumsq_f32(const float *x, size_t n, double *result, void *scratch, void *stream);
+
+/* ---- host-buffer operator (end-to-end path) --------------------------------------
+ * Whole-operator call on HOST arrays, as an application holding its field on
+ * the CPU would issue it: the element range is cut into chunks that are
+ * copied to the device, transformed and reduced in a 3-stage stream pipeline.
+ * in_host: nelmt*nmTot values (element-major, pinned memory gives full PCIe
+ * rate), basis*_host: nm*nq values each.  out_host may be NULL (then only
+ * the checksum leaves the device -- the reference never copies `out` back
+ * either, benchmark05.cc:1189-1385); *sumsq_host receives sum out^2.
+ * Synchronous: returns when the results are in host memory. */
+int b200fe_bwdtrans_quad_host_f64(unsigned nq0, unsigned nq1, size_t nelmt, const double *basis0_host,
+                                  const double *basis1_host, const double *in_host, double *out_host,
+                                  double *sumsq_host);
+int b200fe_bwdtrans_hex_host_f64(unsigned nq0, unsigned nq1, unsigned nq2, size_t nelmt,
+                                 const double *basis0_host, const double *basis1_host,
+                                 const double *basis2_host, const double *in_host, double *out_host,
+                                 double *sumsq_host);
+int b200fe_bwdtrans_quad_host_f32(unsigned nq0, unsigned nq1, size_t nelmt, const float *basis0_host,
+                                  const float *basis1_host, const float *in_host, float *out_host,
+                                  double *sumsq_host);
+int b200fe_bwdtrans_hex_host_f32(unsigned nq0, unsigned nq1, unsigned nq2, size_t nelmt,
+                                 const float *basis0_host, const float *basis1_host, const float *basis2_host,
+                                 const float *in_host, float *out_host, double *sumsq_host);
+
+/* ---- tuning / introspection (not part of the reference surface) -----------------
+ * Force a back-end for the BwdTrans entry points of the calling process:
+ * "auto" (default routing), "rows", "tpe", "generic".  Returns 0 or
+ * B200FE_EINVAL for an unknown name.  Used by the tuner and the parity tests to
+ * exercise every back-end through the same C ABI. */
+int b200fe_set_backend(const char *name);
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200FE_H */

@@ -1,0 +1,57 @@
+"""CPU-side checks of the boundary: the shared library loads without a GPU and
+exports exactly the entry points include/b200fe.h declares."""
+import ctypes
+import os
+import re
+
+import b200fe_loader
+
+fe = b200fe_loader.load()
+
+
+def test_library_loads_and_reports_version():
+    assert fe.version().startswith("b200fe ") and "sm_100a" in fe.version()
+    assert fe.launch_count() >= 0
+    assert fe.sumsq_scratch_bytes() > 0
+
+
+def test_every_declared_symbol_is_exported():
+    names = fe.declared_symbols()
+    assert len(names) >= 50
+    missing = [n for n in names if not hasattr(fe.lib(), n)]
+    assert not missing, missing
+
+
+def test_header_covers_every_reference_kernel_in_both_dtypes():
+    names = set(fe.declared_symbols())
+    ref_kernels = ["BwdTransQuadKernel", "BwdTransQuadKernel_Coa", "BwdTransQuadKernel_QP",
+                   "BwdTransQuadKernel_QP_Shared", "BwdTransQuadKernel_QP_1D", "BwdTransQuadKernel_QP_1D_Shared",
+                   "BwdTransHexKernel", "BwdTransHexKernel_Coa", "BwdTransHexKernel_QP",
+                   "BwdTransHexKernel_QP_Shared", "BwdTransHexKernel_QP_1D", "BwdTransHexKernel_QP_1D_Shared",
+                   "l2norm_vl", "reduce_vl", "reduceSumKernel_sumsq", "set_data", "add_vector",
+                   "vector_kernel_add", "compute_matvec"]
+    for k in ref_kernels:
+        for suf in ("f64", "f32"):
+            assert f"b200fe_{k}_{suf}" in names, (k, suf)
+
+
+def test_header_cites_the_reference_for_each_kernel_family():
+    text = open(fe.HEADER).read()
+    for cite in ("benchmark04/benchmark04.cc:15-76", "benchmark04/benchmark04.cc:78-147",
+                 "benchmark05/benchmark05.cc:291-429", "benchmark01/benchmark01.cc:171-181",
+                 "benchmark02/benchmark02.cc:16-58", "benchmark03/benchmark03.cc:80-104"):
+        assert cite in text
+
+
+def test_library_has_no_oracle_or_cpu_fallback_linked():
+    # the product must not route through oracle/: no oracle symbol, no libgomp dependency
+    out = os.popen(f"nm -D {fe.LIB_PATH}").read()
+    assert "oracle_" not in out
+    deps = os.popen(f"ldd {fe.LIB_PATH}").read()
+    assert "liboracle" not in deps and "libgomp" not in deps
+
+
+def test_sass_is_sm100_only():
+    out = os.popen(f"/usr/local/cuda/bin/cuobjdump -lelf {fe.LIB_PATH} 2>/dev/null").read()
+    archs = set(re.findall(r"sm_(\d+\w*)", out))
+    assert archs == {"100a"}, archs
