@@ -1,0 +1,190 @@
+#pragma once
+// bench_common.h -- host-side helpers shared by the five benchmark drivers
+// (plain C++17, no CUDA syntax: the drivers talk to the GPU only through the
+// C ABI of libb200fe.so and the CUDA runtime API).
+#include <cuda_runtime_api.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iomanip>
+#include <iostream>
+#include <limits>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/b200fe.h"
+#include "timer.h"
+
+namespace bench
+{
+
+inline void die(const char *what, int code, const char *file, int line)
+{
+    std::fprintf(stderr, "%s:%d: %s failed with code %d%s%s\n", file, line, what, code, code > 0 ? ": " : "",
+                 code > 0 ? cudaGetErrorString((cudaError_t)code) : "");
+    std::exit(2);
+}
+
+// every CUDA runtime call and every library call is checked (the reference checks none)
+#define CUDA_OK(expr)                                                                                        \
+    do                                                                                                       \
+    {                                                                                                        \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess)                                                                              \
+            bench::die(#expr, (int)e__, __FILE__, __LINE__);                                                 \
+    } while (0)
+#define FE_OK(expr)                                                                                          \
+    do                                                                                                       \
+    {                                                                                                        \
+        int rc__ = (expr);                                                                                   \
+        if (rc__ != 0)                                                                                       \
+            bench::die(#expr, rc__, __FILE__, __LINE__);                                                     \
+    } while (0)
+
+template <typename T> class DeviceArray
+{
+public:
+    DeviceArray() = default;
+    explicit DeviceArray(size_t n) { resize(n); }
+    DeviceArray(const DeviceArray &)            = delete;
+    DeviceArray &operator=(const DeviceArray &) = delete;
+    ~DeviceArray() { release(); }
+    void resize(size_t n)
+    {
+        release();
+        m_n = n;
+        if (n)
+            CUDA_OK(cudaMalloc((void **)&m_p, n * sizeof(T)));
+    }
+    void release()
+    {
+        if (m_p)
+            cudaFree(m_p);
+        m_p = nullptr;
+        m_n = 0;
+    }
+    void upload(const std::vector<T> &h) { CUDA_OK(cudaMemcpy(m_p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice)); }
+    void download(std::vector<T> &h) const
+    {
+        h.resize(m_n);
+        CUDA_OK(cudaMemcpy(h.data(), m_p, m_n * sizeof(T), cudaMemcpyDeviceToHost));
+    }
+    void zero() { CUDA_OK(cudaMemset(m_p, 0, m_n * sizeof(T))); }
+    T *get() const { return m_p; }
+    size_t size() const { return m_n; }
+
+private:
+    T *m_p     = nullptr;
+    size_t m_n = 0;
+};
+
+inline std::string env_str(const char *name, const char *dflt)
+{
+    const char *v = std::getenv(name);
+    return v && *v ? std::string(v) : std::string(dflt);
+}
+
+inline long env_long(const char *name, long dflt)
+{
+    const char *v = std::getenv(name);
+    return v && *v ? std::atol(v) : dflt;
+}
+
+inline double env_double(const char *name, double dflt)
+{
+    const char *v = std::getenv(name);
+    return v && *v ? std::atof(v) : dflt;
+}
+
+// "a,b,c" -> {a,b,c}
+inline std::vector<unsigned> env_list(const char *name)
+{
+    std::vector<unsigned> out;
+    std::stringstream ss(env_str(name, ""));
+    std::string tok;
+    while (std::getline(ss, tok, ','))
+        if (!tok.empty())
+            out.push_back((unsigned)std::strtoul(tok.c_str(), nullptr, 10));
+    return out;
+}
+
+inline int host_threads()
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+// measured copy bandwidth of this pool's B200s (MEASURED_PEAKS.json: hbm_gbs); B200FE_HBM_GBS overrides
+inline double hbm_peak_gbs()
+{
+    return env_double("B200FE_HBM_GBS", 6546.9);
+}
+
+// min over `reps` of host time around fn() + device synchronise -- the reference's timing method
+template <typename F> double time_min(unsigned reps, F &&fn)
+{
+    Timer t;
+    double best = std::numeric_limits<double>::max();
+    for (unsigned r = 0; r < reps; ++r)
+    {
+        t.start();
+        fn();
+        CUDA_OK(cudaDeviceSynchronize());
+        t.stop();
+        best = std::min(best, t.elapsedSeconds());
+    }
+    return best;
+}
+
+template <typename F> double time_min_host(unsigned reps, F &&fn)
+{
+    Timer t;
+    double best = std::numeric_limits<double>::max();
+    for (unsigned r = 0; r < reps; ++r)
+    {
+        t.start();
+        fn();
+        t.stop();
+        best = std::min(best, t.elapsedSeconds());
+    }
+    return best;
+}
+
+// device checksum sum(x^2), the library's replacement of thrust::transform_reduce
+template <typename T> struct Checksum
+{
+    DeviceArray<double> result{1};
+    DeviceArray<unsigned char> scratch{b200fe_sumsq_scratch_bytes()};
+    double operator()(const T *x, size_t n)
+    {
+        if constexpr (std::is_same<T, double>::value)
+            FE_OK(b200fe_sumsq_f64(x, n, result.get(), scratch.get(), nullptr));
+        else
+            FE_OK(b200fe_sumsq_f32(x, n, result.get(), scratch.get(), nullptr));
+        double h = 0.0;
+        CUDA_OK(cudaMemcpy(&h, result.get(), sizeof(double), cudaMemcpyDeviceToHost));
+        return h;
+    }
+};
+
+template <typename T> double host_sumsq(const std::vector<T> &v)
+{
+    long double s = 0.0L;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+    for (long long i = 0; i < (long long)v.size(); ++i)
+        s += (long double)v[i] * (long double)v[i];
+    return (double)s;
+}
+
+} // namespace bench
