@@ -28,12 +28,46 @@ template <typename K> inline int opt_in_smem(K kernel, size_t bytes)
 }
 
 // ---- quad ---------------------------------------------------------------------
-template <typename T, int NQ, int E, int THREADS>
+// resident CTAs per SM of a kernel at its block size / shared memory, cached per device
+template <typename K> inline int ctas_per_sm(K kernel, int threads, size_t smem, int *cache)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64)
+        return 1;
+    if (cache[dev] == 0)
+    {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1)
+            n = 1;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
+inline int sm_count()
+{
+    static int cache[64] = {};
+    int dev              = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64)
+        return 148;
+    if (cache[dev] == 0)
+    {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
+            n = 148;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
+template <typename T, int NQ, int E, int THREADS, int R, int V>
 int launch_quad_rows(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
 {
-    using C = QuadRows<T, NQ, E, THREADS>;
+    using C = QuadRows<T, NQ, E, THREADS, R, V>;
     static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
-    auto kernel = bwdtrans_quad_rows_kernel<T, NQ, E, THREADS>;
+    auto kernel = bwdtrans_quad_rows_kernel<T, NQ, E, THREADS, R, V>;
     int rc      = opt_in_smem(kernel, C::SMEM);
     if (rc)
         return rc;
@@ -43,6 +77,28 @@ int launch_quad_rows(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
     kernel<<<grid, THREADS, C::SMEM, stream>>>(in, out, nelmt, in_vec, out_vec);
     count_launch();
     t_last_backend = "rows";
+    return launch_status();
+}
+
+// persistent, TMA-fed variant; needs a 16-byte aligned input slab (else the caller uses rows)
+template <typename T, int NQ, int E, int THREADS, int R, int V>
+int launch_quad_pipe(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
+{
+    using C = QuadPipe<T, NQ, E, THREADS, R, V>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
+    static_assert(C::IN_VEC_OK, "pipe tiles must be 16-byte granular");
+    static int occ[64] = {};
+    auto kernel        = bwdtrans_quad_pipe_kernel<T, NQ, E, THREADS, R, V>;
+    int rc             = opt_in_smem(kernel, C::SMEM);
+    if (rc)
+        return rc;
+    const unsigned ntiles = (nelmt + E - 1) / E;
+    const unsigned fit    = (unsigned)(sm_count() * ctas_per_sm(kernel, THREADS, C::SMEM, occ));
+    const unsigned grid   = ntiles < fit ? ntiles : fit;
+    const int out_vec     = C::OUT_VEC_OK && aligned16(out);
+    kernel<<<grid, THREADS, C::SMEM, stream>>>(in, out, nelmt, ntiles, out_vec);
+    count_launch();
+    t_last_backend = "pipe";
     return launch_status();
 }
 
@@ -57,12 +113,12 @@ template <typename T, int NQ> int launch_quad_tpe_coa(unsigned nelmt, const T *i
 }
 
 // ---- hex ----------------------------------------------------------------------
-template <typename T, int NQ, int E, int THREADS>
+template <typename T, int NQ, int E, int THREADS, int R, int V>
 int launch_hex_rows(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
 {
-    using C = HexRows<T, NQ, E, THREADS>;
+    using C = HexRows<T, NQ, E, THREADS, R, V>;
     static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
-    auto kernel = bwdtrans_hex_rows_kernel<T, NQ, E, THREADS>;
+    auto kernel = bwdtrans_hex_rows_kernel<T, NQ, E, THREADS, R, V>;
     int rc      = opt_in_smem(kernel, C::SMEM);
     if (rc)
         return rc;
@@ -71,6 +127,26 @@ int launch_hex_rows(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
     kernel<<<grid, THREADS, C::SMEM, stream>>>(in, out, nelmt, in_vec);
     count_launch();
     t_last_backend = "rows";
+    return launch_status();
+}
+
+template <typename T, int NQ, int E, int THREADS, int R, int V>
+int launch_hex_pipe(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
+{
+    using C = HexPipe<T, NQ, E, THREADS, R, V>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
+    static_assert(C::IN_VEC_OK, "pipe tiles must be 16-byte granular");
+    static int occ[64] = {};
+    auto kernel        = bwdtrans_hex_pipe_kernel<T, NQ, E, THREADS, R, V>;
+    int rc             = opt_in_smem(kernel, C::SMEM);
+    if (rc)
+        return rc;
+    const unsigned ntiles = (nelmt + E - 1) / E;
+    const unsigned fit    = (unsigned)(sm_count() * ctas_per_sm(kernel, THREADS, C::SMEM, occ));
+    const unsigned grid   = ntiles < fit ? ntiles : fit;
+    kernel<<<grid, THREADS, C::SMEM, stream>>>(in, out, nelmt, ntiles);
+    count_launch();
+    t_last_backend = "pipe";
     return launch_status();
 }
 

@@ -1,6 +1,9 @@
 // bwdtrans_quad.cu -- quad BwdTrans dispatch for one dtype.  Compiled twice:
 //   -DB200FE_T=double -DB200FE_ROWS_TABLE='"rows_table_2_f64.inc"'
 //   -DB200FE_T=float  -DB200FE_ROWS_TABLE='"rows_table_2_f32.inc"'
+// The table (tools/gen_rows_table.py + tuner overrides) lists, per nq, the tile
+// shape of the rows and pipe back-ends and which of the two the default routing
+// prefers.
 #include "bwdtrans_impl.cuh"
 
 namespace b200fe
@@ -12,14 +15,89 @@ static int quad_rows_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cu
 {
     switch (nq)
     {
-#define ROWS_CASE(NQ, E, TH)                                                                                 \
+#define ROWS_CASE(NQ, E, TH, R, V)                                                                              \
     case NQ:                                                                                                 \
-        return launch_quad_rows<T, NQ, E, TH>(nelmt, in, out, s);
+        return launch_quad_rows<T, NQ, E, TH, R, V>(nelmt, in, out, s);
+#define PIPE_CASE(NQ, E, TH, R, V)
+#define PREFER(NQ, BE)
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
+#undef PIPE_CASE
+#undef PREFER
     default:
         return B200FE_EUNSUPPORTED;
     }
+}
+
+static int quad_pipe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
+{
+    switch (nq)
+    {
+#define ROWS_CASE(NQ, E, TH, R, V)
+#define PIPE_CASE(NQ, E, TH, R, V)                                                                              \
+    case NQ:                                                                                                 \
+        return launch_quad_pipe<T, NQ, E, TH, R, V>(nelmt, in, out, s);
+#define PREFER(NQ, BE)
+#include B200FE_ROWS_TABLE
+#undef ROWS_CASE
+#undef PIPE_CASE
+#undef PREFER
+    default:
+        return B200FE_EUNSUPPORTED;
+    }
+}
+
+// what the table offers for this nq: bit 0 rows, bit 1 pipe; *preferred = default routing
+static int quad_table_lookup(unsigned nq, Backend *preferred)
+{
+    int have   = 0;
+    *preferred = Backend::Generic;
+    switch (nq)
+    {
+#define ROWS_CASE(NQ, E, TH, R, V)                                                                              \
+    case NQ:                                                                                                 \
+        have |= 1;                                                                                           \
+        break;
+#define PIPE_CASE(NQ, E, TH, R, V)
+#define PREFER(NQ, BE)
+#include B200FE_ROWS_TABLE
+#undef ROWS_CASE
+#undef PIPE_CASE
+#undef PREFER
+    default:
+        break;
+    }
+    switch (nq)
+    {
+#define ROWS_CASE(NQ, E, TH, R, V)
+#define PIPE_CASE(NQ, E, TH, R, V)                                                                              \
+    case NQ:                                                                                                 \
+        have |= 2;                                                                                           \
+        break;
+#define PREFER(NQ, BE)
+#include B200FE_ROWS_TABLE
+#undef ROWS_CASE
+#undef PIPE_CASE
+#undef PREFER
+    default:
+        break;
+    }
+    switch (nq)
+    {
+#define ROWS_CASE(NQ, E, TH, R, V)
+#define PIPE_CASE(NQ, E, TH, R, V)
+#define PREFER(NQ, BE)                                                                                       \
+    case NQ:                                                                                                 \
+        *preferred = Backend::BE;                                                                            \
+        break;
+#include B200FE_ROWS_TABLE
+#undef ROWS_CASE
+#undef PIPE_CASE
+#undef PREFER
+    default:
+        break;
+    }
+    return have;
 }
 
 // registers hold nm^2 + nm values per thread
@@ -48,10 +126,12 @@ static int quad_tpe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cud
 }
 
 template <>
-int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsigned nq0, unsigned nq1,
-                         unsigned nelmt, const T *b0, const T *b1, const T *in, T *out, cudaStream_t stream)
+int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsigned nq0, unsigned nq1, unsigned nelmt,
+                        const T *b0, const T *b1, const T *in, T *out, cudaStream_t stream)
 {
     const bool regular = (nq0 == nq1) && (nm0 + 1 == nq0) && (nm1 + 1 == nq1) && nq0 >= 2 && nq0 <= 32;
+    Backend preferred  = Backend::Generic;
+    const int have     = regular ? quad_table_lookup(nq0, &preferred) : 0;
     if (be == Backend::Auto)
     {
         if (!regular)
@@ -59,14 +139,21 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
         else if (coa)
             be = nq0 <= kQuadTpeMaxNq ? Backend::Tpe : Backend::Generic;
         else
-            be = Backend::Rows;
+            be = preferred;
+        // the bulk-copy ring needs a 16-byte aligned slab; otherwise take the plain-load twin
+        if (be == Backend::Pipe && (!(have & 2) || !aligned16(in)))
+            be = (have & 1) ? Backend::Rows : Backend::Generic;
+        if (be == Backend::Rows && !(have & 1))
+            be = Backend::Generic;
     }
     if (be == Backend::Generic)
     {
         t_last_backend = "generic";
         return launch_quad_generic<T>(nm0, nm1, nq0, nq1, nelmt, b0, b1, in, out, coa, stream);
     }
-    if (!regular || (be == Backend::Rows && coa) || (be == Backend::Tpe && !coa))
+    if (!regular || ((be == Backend::Rows || be == Backend::Pipe) && coa) || (be == Backend::Tpe && !coa))
+        return B200FE_EUNSUPPORTED;
+    if (be == Backend::Pipe && (!(have & 2) || !aligned16(in)))
         return B200FE_EUNSUPPORTED;
 
     std::lock_guard<std::mutex> lock(g_bank_lock);
@@ -75,8 +162,12 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
     int rc              = fill_basis_bank<T>(g_bank, 2, bases, counts, stream);
     if (rc)
         return rc;
-    rc = (be == Backend::Rows) ? quad_rows_switch(nq0, nelmt, in, out, stream)
-                               : quad_tpe_switch(nq0, nelmt, in, out, stream);
+    if (be == Backend::Rows)
+        rc = quad_rows_switch(nq0, nelmt, in, out, stream);
+    else if (be == Backend::Pipe)
+        rc = quad_pipe_switch(nq0, nelmt, in, out, stream);
+    else
+        rc = quad_tpe_switch(nq0, nelmt, in, out, stream);
     if (rc)
         return rc;
     return release_basis_bank(g_bank, stream);

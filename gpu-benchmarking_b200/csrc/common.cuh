@@ -74,8 +74,8 @@ __device__ __forceinline__ float fmadd(float a, float b, float c)
 // nq <= 32 (2*31*32) and hex nq <= 16 (3*15*16).  `static`: one bank per
 // translation unit, filled by that unit's launcher.
 constexpr int kBasisBankElems = 1984;
-static __constant__ double c_basis_f64[kBasisBankElems];
-static __constant__ float c_basis_f32[kBasisBankElems];
+static __constant__ __align__(16) double c_basis_f64[kBasisBankElems];
+static __constant__ __align__(16) float c_basis_f32[kBasisBankElems];
 
 template <typename T> __device__ __forceinline__ T cbasis(int i);
 template <> __device__ __forceinline__ double cbasis<double>(int i)
@@ -85,6 +85,63 @@ template <> __device__ __forceinline__ double cbasis<double>(int i)
 template <> __device__ __forceinline__ float cbasis<float>(int i)
 {
     return c_basis_f32[i];
+}
+
+// IB consecutive basis values starting at bank slot idx.  When the slot is
+// 16-byte aligned (ALIGNED, decided at compile time by the caller) the values are
+// fetched with 16-byte uniform loads (LDCU.128), 2 doubles / 4 floats at a time.
+template <int IB, bool ALIGNED> __device__ __forceinline__ void cbasis_load(int idx, double (&b)[IB])
+{
+    if (ALIGNED && IB % 2 == 0)
+    {
+        const double2 *v = reinterpret_cast<const double2 *>(c_basis_f64);
+#pragma unroll
+        for (int j = 0; j < IB / 2; ++j)
+        {
+            const double2 t = v[idx / 2 + j];
+            b[2 * j]        = t.x;
+            b[2 * j + 1]    = t.y;
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int j = 0; j < IB; ++j)
+            b[j] = c_basis_f64[idx + j];
+    }
+}
+template <int IB, bool ALIGNED> __device__ __forceinline__ void cbasis_load(int idx, float (&b)[IB])
+{
+    if (ALIGNED && IB % 4 == 0)
+    {
+        const float4 *v = reinterpret_cast<const float4 *>(c_basis_f32);
+#pragma unroll
+        for (int j = 0; j < IB / 4; ++j)
+        {
+            const float4 t = v[idx / 4 + j];
+            b[4 * j]       = t.x;
+            b[4 * j + 1]   = t.y;
+            b[4 * j + 2]   = t.z;
+            b[4 * j + 3]   = t.w;
+        }
+    }
+    else if (ALIGNED && IB % 2 == 0)
+    {
+        const float2 *v = reinterpret_cast<const float2 *>(c_basis_f32);
+#pragma unroll
+        for (int j = 0; j < IB / 2; ++j)
+        {
+            const float2 t = v[idx / 2 + j];
+            b[2 * j]       = t.x;
+            b[2 * j + 1]   = t.y;
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int j = 0; j < IB; ++j)
+            b[j] = c_basis_f32[idx + j];
+    }
 }
 
 template <typename T> inline const void *basis_bank_symbol();

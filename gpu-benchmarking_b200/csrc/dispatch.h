@@ -13,6 +13,7 @@ enum class Backend : int
     Rows    = 1, // element-batched row contractions through shared memory (element-major)
     Tpe     = 2, // thread per element, registers only (interleaved layout)
     Generic = 3, // run-time sizes, any shape
+    Pipe    = 4, // rows + persistent CTAs fed by bulk (TMA) copies through an mbarrier ring
 };
 
 // element-major unless coa; return 0 / cudaError_t / negative B200FE_E*
