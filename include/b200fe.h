@@ -252,8 +252,9 @@ int b200fe_bwdtrans_hex_host_f32(unsigned nq0, unsigned nq1, unsigned nq2, size_
 
 /* ---- tuning / introspection (not part of the reference surface) -----------------
  * Force a back-end for the BwdTrans entry points of the calling process:
- * "auto" (default routing), "rows", "tpe", "generic".  Returns 0 or
- * B200FE_EINVAL for an unknown name.  Used by the tuner and the parity tests to
+ * "auto" (default routing), "rows", "pipe", "tpe", "generic".  Returns 0 or
+ * B200FE_EINVAL for an unknown name; an entry point then returns
+ * B200FE_EUNSUPPORTED where the forced back-end has no instantiation.  Used by the tuner and the parity tests to
  * exercise every back-end through the same C ABI. */
 int b200fe_set_backend(const char *name);
 #if defined(__GNUC__)

@@ -48,7 +48,7 @@ def test_quad_every_nq_bit_exact(G, suf, nq):
         inp = rnd(rng, nelmt * nm * nm, dt)
         want = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp, use_fma=True)
         got = G.run_quad("BwdTransQuadKernel_QP_Shared", suf, nq, nq, nelmt, b0, b1, inp)
-        assert G.fe.last_backend() == "rows"
+        assert G.fe.last_backend() in ("rows", "pipe")
         assert np.array_equal(got, want), (nq, nelmt, G.rel_max(got, want))
         plain = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp, use_fma=False)
         assert G.rel_max(got, plain) < G.TOL[suf]
@@ -139,6 +139,49 @@ def test_generic_backend_handles_unequal_and_non_nm_shapes(G, suf):
     inpc = rnd(rng, 64 * 121, dt)
     gotc = G.run_quad("BwdTransQuadKernel_Coa", suf, 12, 12, 64, b0, b1, inpc)
     assert np.array_equal(gotc, oracle.bwdtrans_quad(12, 12, 64, b0, b1, inpc, coa=True))
+
+
+@pytest.mark.parametrize("suf", ["f64", "f32"])
+@pytest.mark.parametrize("backend", ["rows", "pipe"])
+@pytest.mark.parametrize("nq", [2, 4, 6, 8, 10, 12, 14, 16, 32])
+def test_quad_rows_and_pipe_backends_bit_exact(G, backend, nq, suf):
+    """both tiled back-ends for every tuned nq: many tiles per persistent CTA (the ring wraps), ragged last tile"""
+    dt, nm = G.NP[suf], nq - 1
+    nelmt = 40013 if nq <= 16 else 3001
+    rng = np.random.default_rng(300 + nq)
+    b0, b1 = rnd(rng, nm * nq, dt), rnd(rng, nm * nq, dt)
+    inp = rnd(rng, nelmt * nm * nm, dt)
+    try:
+        G.fe.set_backend(backend)
+        got = G.run_quad("BwdTransQuadKernel_QP_Shared", suf, nq, nq, nelmt, b0, b1, inp)
+        assert G.fe.last_backend() == backend
+    except G.fe.B200feError as e:
+        assert e.code == G.fe.E_UNSUPPORTED and backend == "pipe"
+        pytest.skip(f"no pipe instantiation for quad nq={nq} {suf}")
+    finally:
+        G.fe.set_backend("auto")
+    assert np.array_equal(got, oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp))
+
+
+@pytest.mark.parametrize("suf", ["f64", "f32"])
+@pytest.mark.parametrize("backend", ["rows", "pipe"])
+@pytest.mark.parametrize("nq", [2, 4, 6, 8, 10])
+def test_hex_rows_and_pipe_backends_bit_exact(G, backend, nq, suf):
+    dt, nm = G.NP[suf], nq - 1
+    nelmt = {2: 700001, 4: 90001, 6: 20011, 8: 5003, 10: 3001}[nq]  # > one wave of tiles, ragged tail
+    rng = np.random.default_rng(400 + nq)
+    b = [rnd(rng, nm * nq, dt) for _ in range(3)]
+    inp = rnd(rng, nelmt * nm ** 3, dt)
+    try:
+        G.fe.set_backend(backend)
+        got = G.run_hex("BwdTransHexKernel_QP_Shared", suf, (nq, nq, nq), nelmt, b, inp)
+        assert G.fe.last_backend() == backend
+    except G.fe.B200feError as e:
+        assert e.code == G.fe.E_UNSUPPORTED and backend == "pipe"
+        pytest.skip(f"no pipe instantiation for hex nq={nq} {suf}")
+    finally:
+        G.fe.set_backend("auto")
+    assert np.array_equal(got, oracle.bwdtrans_hex(nq, nq, nq, nelmt, *b, inp))
 
 
 @pytest.mark.parametrize("backend", ["rows", "generic"])
