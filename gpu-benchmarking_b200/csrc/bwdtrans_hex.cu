@@ -20,6 +20,9 @@ static int hex_rows_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cud
         return launch_hex_rows<T, NQ, E, TH, R, V>(nelmt, in, out, s);
 #define PIPE_CASE(NQ, E, TH, R, V)
 #define PREFER(NQ, BE)
+#ifndef MMA_CASE
+#define MMA_CASE(...)
+#endif
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE
@@ -38,6 +41,9 @@ static int hex_pipe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cud
     case NQ:                                                                                                 \
         return launch_hex_pipe<T, NQ, E, TH, R, V>(nelmt, in, out, s);
 #define PREFER(NQ, BE)
+#ifndef MMA_CASE
+#define MMA_CASE(...)
+#endif
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE
@@ -60,6 +66,9 @@ static int hex_table_lookup(unsigned nq, Backend *preferred)
         break;
 #define PIPE_CASE(NQ, E, TH, R, V)
 #define PREFER(NQ, BE)
+#ifndef MMA_CASE
+#define MMA_CASE(...)
+#endif
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE
@@ -75,6 +84,9 @@ static int hex_table_lookup(unsigned nq, Backend *preferred)
         have |= 2;                                                                                           \
         break;
 #define PREFER(NQ, BE)
+#ifndef MMA_CASE
+#define MMA_CASE(...)
+#endif
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE
@@ -90,6 +102,9 @@ static int hex_table_lookup(unsigned nq, Backend *preferred)
     case NQ:                                                                                                 \
         *preferred = Backend::BE;                                                                            \
         break;
+#ifndef MMA_CASE
+#define MMA_CASE(...)
+#endif
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE

@@ -6,6 +6,7 @@
 
 #include "dispatch.h"
 #include "sumfac_generic.cuh"
+#include "sumfac_mma.cuh"
 #include "sumfac_rows.cuh"
 #include "sumfac_tpe.cuh"
 
@@ -99,6 +100,29 @@ int launch_quad_pipe(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
     kernel<<<grid, THREADS, C::SMEM, stream>>>(in, out, nelmt, ntiles, out_vec);
     count_launch();
     t_last_backend = "pipe";
+    return launch_status();
+}
+
+// FP64 tensor-core variant: persistent CTAs of independent warps, one group of G elements per warp at a time
+template <int NQ, int G, int WARPS, int MB0, int NB1>
+int launch_quad_mma(unsigned nelmt, const double *b0, const double *b1, const double *in, double *out,
+                    cudaStream_t stream)
+{
+    using C = QuadMma<NQ, G, WARPS, MB0, NB1>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "warp regions do not fit shared memory");
+    static int occ[64] = {};
+    auto kernel        = bwdtrans_quad_mma_kernel<NQ, G, WARPS, MB0, NB1>;
+    int rc             = opt_in_smem(kernel, C::SMEM);
+    if (rc)
+        return rc;
+    const unsigned ngroups = (nelmt + G - 1) / G;
+    const unsigned need    = (ngroups + WARPS - 1) / WARPS;
+    const unsigned fit     = (unsigned)(sm_count() * ctas_per_sm(kernel, WARPS * 32, C::SMEM, occ));
+    const unsigned grid    = need < fit ? need : fit;
+    const int out_vec      = aligned16(out);
+    kernel<<<grid, WARPS * 32, C::SMEM, stream>>>(b0, b1, in, out, nelmt, ngroups, out_vec);
+    count_launch();
+    t_last_backend = "mma";
     return launch_status();
 }
 

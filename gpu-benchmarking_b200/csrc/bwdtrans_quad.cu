@@ -20,10 +20,12 @@ static int quad_rows_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cu
         return launch_quad_rows<T, NQ, E, TH, R, V>(nelmt, in, out, s);
 #define PIPE_CASE(NQ, E, TH, R, V)
 #define PREFER(NQ, BE)
+#define MMA_CASE(NQ, G, W, MB0, NB1)
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE
 #undef PREFER
+#undef MMA_CASE
     default:
         return B200FE_EUNSUPPORTED;
     }
@@ -38,16 +40,39 @@ static int quad_pipe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cu
     case NQ:                                                                                                 \
         return launch_quad_pipe<T, NQ, E, TH, R, V>(nelmt, in, out, s);
 #define PREFER(NQ, BE)
+#define MMA_CASE(NQ, G, W, MB0, NB1)
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE
 #undef PREFER
+#undef MMA_CASE
     default:
         return B200FE_EUNSUPPORTED;
     }
 }
 
-// what the table offers for this nq: bit 0 rows, bit 1 pipe; *preferred = default routing
+// FP64 tensor-core variant (only the f64 table lists MMA_CASE lines)
+static int quad_mma_switch(unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *in, T *out, cudaStream_t s)
+{
+    switch (nq)
+    {
+#define ROWS_CASE(NQ, E, TH, R, V)
+#define PIPE_CASE(NQ, E, TH, R, V)
+#define PREFER(NQ, BE)
+#define MMA_CASE(NQ, G, W, MB0, NB1)                                                                         \
+    case NQ:                                                                                                 \
+        return launch_quad_mma<NQ, G, W, MB0, NB1>(nelmt, b0, b1, in, out, s);
+#include B200FE_ROWS_TABLE
+#undef ROWS_CASE
+#undef PIPE_CASE
+#undef PREFER
+#undef MMA_CASE
+    default:
+        return B200FE_EUNSUPPORTED;
+    }
+}
+
+// what the table offers for this nq: bit 0 rows, bit 1 pipe, bit 2 mma; *preferred = default routing
 static int quad_table_lookup(unsigned nq, Backend *preferred)
 {
     int have   = 0;
@@ -60,10 +85,12 @@ static int quad_table_lookup(unsigned nq, Backend *preferred)
         break;
 #define PIPE_CASE(NQ, E, TH, R, V)
 #define PREFER(NQ, BE)
+#define MMA_CASE(NQ, G, W, MB0, NB1)
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE
 #undef PREFER
+#undef MMA_CASE
     default:
         break;
     }
@@ -75,10 +102,29 @@ static int quad_table_lookup(unsigned nq, Backend *preferred)
         have |= 2;                                                                                           \
         break;
 #define PREFER(NQ, BE)
+#define MMA_CASE(NQ, G, W, MB0, NB1)
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE
 #undef PREFER
+#undef MMA_CASE
+    default:
+        break;
+    }
+    switch (nq)
+    {
+#define ROWS_CASE(NQ, E, TH, R, V)
+#define PIPE_CASE(NQ, E, TH, R, V)
+#define PREFER(NQ, BE)
+#define MMA_CASE(NQ, G, W, MB0, NB1)                                                                         \
+    case NQ:                                                                                                 \
+        have |= 4;                                                                                           \
+        break;
+#include B200FE_ROWS_TABLE
+#undef ROWS_CASE
+#undef PIPE_CASE
+#undef PREFER
+#undef MMA_CASE
     default:
         break;
     }
@@ -90,10 +136,12 @@ static int quad_table_lookup(unsigned nq, Backend *preferred)
     case NQ:                                                                                                 \
         *preferred = Backend::BE;                                                                            \
         break;
+#define MMA_CASE(NQ, G, W, MB0, NB1)
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE
 #undef PREFER
+#undef MMA_CASE
     default:
         break;
     }
@@ -143,6 +191,8 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
         // the bulk-copy ring needs a 16-byte aligned slab; otherwise take the plain-load twin
         if (be == Backend::Pipe && (!(have & 2) || !aligned16(in)))
             be = (have & 1) ? Backend::Rows : Backend::Generic;
+        if (be == Backend::Mma && !(have & 4))
+            be = (have & 1) ? Backend::Rows : Backend::Generic;
         if (be == Backend::Rows && !(have & 1))
             be = Backend::Generic;
     }
@@ -151,10 +201,13 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
         t_last_backend = "generic";
         return launch_quad_generic<T>(nm0, nm1, nq0, nq1, nelmt, b0, b1, in, out, coa, stream);
     }
-    if (!regular || ((be == Backend::Rows || be == Backend::Pipe) && coa) || (be == Backend::Tpe && !coa))
+    if (!regular || ((be == Backend::Rows || be == Backend::Pipe || be == Backend::Mma) && coa) ||
+        (be == Backend::Tpe && !coa))
         return B200FE_EUNSUPPORTED;
     if (be == Backend::Pipe && (!(have & 2) || !aligned16(in)))
         return B200FE_EUNSUPPORTED;
+    if (be == Backend::Mma) // reads the basis matrices from global memory: no constant bank, no lock
+        return (have & 4) ? quad_mma_switch(nq0, nelmt, b0, b1, in, out, stream) : B200FE_EUNSUPPORTED;
 
     std::lock_guard<std::mutex> lock(g_bank_lock);
     const T *bases[2]   = {b0, b1};

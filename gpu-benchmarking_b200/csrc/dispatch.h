@@ -14,6 +14,7 @@ enum class Backend : int
     Tpe     = 2, // thread per element, registers only (interleaved layout)
     Generic = 3, // run-time sizes, any shape
     Pipe    = 4, // rows + persistent CTAs fed by bulk (TMA) copies through an mbarrier ring
+    Mma     = 5, // FP64 tensor cores (DMMA m8n8k4), one element group per warp, bulk (TMA) fed (quad, even nq)
 };
 
 // element-major unless coa; return 0 / cudaError_t / negative B200FE_E*

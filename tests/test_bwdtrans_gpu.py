@@ -48,7 +48,7 @@ def test_quad_every_nq_bit_exact(G, suf, nq):
         inp = rnd(rng, nelmt * nm * nm, dt)
         want = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp, use_fma=True)
         got = G.run_quad("BwdTransQuadKernel_QP_Shared", suf, nq, nq, nelmt, b0, b1, inp)
-        assert G.fe.last_backend() in ("rows", "pipe")
+        assert G.fe.last_backend() in ("rows", "pipe", "mma")
         assert np.array_equal(got, want), (nq, nelmt, G.rel_max(got, want))
         plain = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp, use_fma=False)
         assert G.rel_max(got, plain) < G.TOL[suf]
@@ -142,10 +142,12 @@ def test_generic_backend_handles_unequal_and_non_nm_shapes(G, suf):
 
 
 @pytest.mark.parametrize("suf", ["f64", "f32"])
-@pytest.mark.parametrize("backend", ["rows", "pipe"])
+@pytest.mark.parametrize("backend", ["rows", "pipe", "mma"])
 @pytest.mark.parametrize("nq", [2, 4, 6, 8, 10, 12, 14, 16, 32])
 def test_quad_rows_and_pipe_backends_bit_exact(G, backend, nq, suf):
-    """both tiled back-ends for every tuned nq: many tiles per persistent CTA (the ring wraps), ragged last tile"""
+    """every tiled back-end for every tuned nq: many tiles per persistent CTA (the ring wraps), ragged last tile.
+    mma (FP64 tensor cores) is held to the same bit-for-bit bar: DMMA m8n8k4 on sm_100 accumulates its four
+    products in k order with fused multiply-adds, i.e. the reference's own summation order."""
     dt, nm = G.NP[suf], nq - 1
     nelmt = 40013 if nq <= 16 else 3001
     rng = np.random.default_rng(300 + nq)
@@ -156,8 +158,8 @@ def test_quad_rows_and_pipe_backends_bit_exact(G, backend, nq, suf):
         got = G.run_quad("BwdTransQuadKernel_QP_Shared", suf, nq, nq, nelmt, b0, b1, inp)
         assert G.fe.last_backend() == backend
     except G.fe.B200feError as e:
-        assert e.code == G.fe.E_UNSUPPORTED and backend == "pipe"
-        pytest.skip(f"no pipe instantiation for quad nq={nq} {suf}")
+        assert e.code == G.fe.E_UNSUPPORTED and backend in ("pipe", "mma")
+        pytest.skip(f"no {backend} instantiation for quad nq={nq} {suf}")
     finally:
         G.fe.set_backend("auto")
     assert np.array_equal(got, oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp))
@@ -317,3 +319,48 @@ def test_unaligned_16_byte_input_still_exact(G):
     G.fe.bwdtrans_quad("BwdTransQuadKernel", "f64", nq, nq, nelmt, d_b0.data_ptr(), d_b1.data_ptr(),
                        big_in.data_ptr() + 8, big_out.data_ptr() + 8)
     assert np.array_equal(G.host(big_out)[1:], oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp))
+
+
+@pytest.mark.parametrize("nq", [8, 12, 14, 16, 32])
+@pytest.mark.parametrize("nelmt,shift", [(1, 0), (3, 1), (64, 1), (1001, 0), (1001, 1)])
+def test_quad_mma_ragged_groups_and_8_byte_aligned_slabs(G, nq, nelmt, shift):
+    """tensor-core back-end: partial last group, fewer groups than warps, and input/output slabs that start
+    8 bytes off a 16-byte boundary (bulk copy of the enclosing window, scalar stores)"""
+    import torch
+    nm = nq - 1
+    rng = np.random.default_rng(500 + nq + nelmt)
+    b0, b1 = rnd(rng, nm * nq, np.float64), rnd(rng, nm * nq, np.float64)
+    inp = rnd(rng, nelmt * nm * nm, np.float64)
+    big_in = torch.full((inp.size + 2,), float("nan"), dtype=torch.float64, device="cuda")
+    big_in[shift:shift + inp.size] = torch.from_numpy(inp).cuda()
+    big_out = torch.full((nelmt * nq * nq + 2,), float("nan"), dtype=torch.float64, device="cuda")
+    d_b0, d_b1 = G.dev(b0), G.dev(b1)
+    try:
+        G.fe.set_backend("mma")
+        G.fe.bwdtrans_quad("BwdTransQuadKernel_QP_Shared", "f64", nq, nq, nelmt, d_b0.data_ptr(), d_b1.data_ptr(),
+                           big_in.data_ptr() + 8 * shift, big_out.data_ptr() + 8 * shift)
+        assert G.fe.last_backend() == "mma"
+    finally:
+        G.fe.set_backend("auto")
+    got = G.host(big_out)
+    assert np.array_equal(got[shift:shift + nelmt * nq * nq], oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp))
+    assert np.isnan(got[:shift]).all() and np.isnan(got[shift + nelmt * nq * nq:]).all()  # nothing written outside
+
+
+def test_quad_mma_non_finite_neighbours_do_not_leak(G):
+    """zero padding of the k dimension must not turn a neighbouring row's Inf/NaN into NaN here"""
+    nq, nm, nelmt = 14, 13, 9
+    rng = np.random.default_rng(77)
+    b0, b1 = rnd(rng, nm * nq, np.float64), rnd(rng, nm * nq, np.float64)
+    inp = rnd(rng, nelmt * nm * nm, np.float64)
+    inp[4 * nm * nm: 5 * nm * nm] = np.inf  # element 4 is poisoned
+    try:
+        G.fe.set_backend("mma")
+        got = G.run_quad("BwdTransQuadKernel_QP_Shared", "f64", nq, nq, nelmt, b0, b1, inp).reshape(nelmt, -1)
+    finally:
+        G.fe.set_backend("auto")
+    want = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp).reshape(nelmt, -1)
+    ok = [e for e in range(nelmt) if e != 4]
+    assert np.isfinite(got[ok]).all()
+    assert np.array_equal(got[ok], want[ok])
+    assert not np.isfinite(got[4]).any()

@@ -67,18 +67,49 @@ def configs(dim, tag, nq):
     return out
 
 
+def mma_smem(nq, g, warps):
+    """QuadMma<NQ, G, WARPS, ..>::SMEM of sumfac_mma.cuh"""
+    nm = nq - 1
+    ks, nt = (nm + 3) // 4, (nq + 7) // 8
+    s = nq + (nq & 1)
+    while s % 16 not in (4, 12):
+        s += 2
+    slot = (g * nm * nm + 5) // 2 * 2
+    return (warps * 8 + 15) // 16 * 16 + 8 * (2 * ks * nt * 32 + warps * (slot + g * nm * s))
+
+
+def mma_configs(nq):
+    """FP64 quad tensor-core back-end: (G elements per warp, warps per CTA, MB0, NB1)"""
+    out = []
+    nt = (nq + 7) // 8
+    for g in (1, 2, 4, 8):
+        for warps in (4, 8):
+            if mma_smem(nq, g, warps) > SMEM_MAX:
+                continue
+            for mb0 in (1, 2, 4):
+                if mb0 * nt > 8 or (mb0 - 1) * 8 >= g * (nq - 1):
+                    continue
+                for nb1 in (1, 2, 4):
+                    if nb1 * nt > 8 or (nb1 - 1) * 8 >= g * nq:
+                        continue
+                    out.append(("mma", g, warps * 32, mb0, nb1))
+    return out
+
+
 DEFAULT = [f"2:{t}:{n}" for t in ("f64", "f32") for n in (2, 4, 6, 8, 10, 12, 14, 16, 32)] + \
           [f"3:{t}:{n}" for t in ("f64", "f32") for n in (2, 4, 6, 8, 10)]
 
 
 def main():
-    cases = sys.argv[1:] or DEFAULT
+    cases = [a for a in sys.argv[1:] if not a.startswith("--")] or DEFAULT
     os.makedirs(BUILD, exist_ok=True)
     names = []
     for case in cases:
         dim, tag, nq = case.split(":")
         dim, nq = int(dim), int(nq)
         cfgs = configs(dim, tag, nq)
+        if "--mma" in sys.argv:
+            cfgs = cfgs[:1] + (mma_configs(nq) if dim == 2 and tag == "f64" and nq % 2 == 0 else [])
         name = f"{dim}_{tag}_{nq}"
         with open(os.path.join(BUILD, f"cfg_{name}.inc"), "w") as f:
             for be, e, th, r, v in cfgs:

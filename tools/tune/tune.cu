@@ -7,6 +7,8 @@
 // Every configuration's output is compared bit for bit with the first one's.
 #include <algorithm>
 #include <cstdio>
+#include <cstring>
+#include <string>
 #include <vector>
 
 #include "../../gpu-benchmarking_b200/csrc/bwdtrans_impl.cuh"
@@ -49,6 +51,20 @@ struct Cfg
     {"pipe", E, TH, R, V, &launch_hex_pipe<T, NQ, E, TH, R, V>, HexPipe<T, NQ, E, TH, R, V>::SMEM,           \
      (const void *)bwdtrans_hex_pipe_kernel<T, NQ, E, TH, R, V>},
 #endif
+// mma (FP64 quads only): E = elements per warp group, TH = 32 * warps, R = MB0, V = NB1
+static const double *g_b0 = nullptr, *g_b1 = nullptr;
+#if TUNE_DIM == 2
+template <int G, int W, int MB0, int NB1> int mma_wrap(unsigned nelmt, const T *in, T *out, cudaStream_t s)
+{
+    if constexpr (sizeof(T) == 8)
+        return launch_quad_mma<NQ, G, W, MB0, NB1>(nelmt, g_b0, g_b1, (const double *)in, (double *)out, s);
+    else
+        return -2;
+}
+#define CFG_mma(E, TH, R, V)                                                                                 \
+    {"mma", E, TH, R, V, &mma_wrap<E, TH / 32, R, V>, QuadMma<NQ, E, TH / 32, R, V>::SMEM,                     \
+     (const void *)bwdtrans_quad_mma_kernel<NQ, E, TH / 32, R, V>},
+#endif
 #define CFG(BE, E, TH, R, V) CFG_##BE(E, TH, R, V)
 
 static Cfg cfgs[] = {
@@ -62,6 +78,20 @@ __global__ void fill_kernel(T *in, size_t n, size_t nmTot)
         const size_t k = i % nmTot, e = i / nmTot;
         in[i]          = (T)sin((double)(k + 1) + 1e-3 * (double)(e % 977)); // element-dependent
     }
+}
+
+// max |a-b| and max |b| (non-negative doubles order like their bit patterns)
+__global__ void maxdiff_kernel(const T *a, const T *b, size_t n, unsigned long long *res)
+{
+    double md = 0, mb = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const double d = fabs((double)a[i] - (double)b[i]);
+        md             = (d > md || d != d) ? (d != d ? 1e300 : d) : md;
+        mb             = fmax(mb, fabs((double)b[i]));
+    }
+    atomicMax(res, (unsigned long long)__double_as_longlong(md));
+    atomicMax(res + 1, (unsigned long long)__double_as_longlong(mb));
 }
 
 __global__ void diff_kernel(const T *a, const T *b, size_t n, unsigned long long *bad)
@@ -94,12 +124,15 @@ int main(int argc, char **argv)
     const char *tname = sizeof(T) == 8 ? "f64" : "f32";
 
     T *d_in, *d_out, *d_ref, *d_basis;
-    unsigned long long *d_bad;
+    unsigned long long *d_bad, *d_md;
     CK(cudaMalloc(&d_in, nelmt * NMTOT * sizeof(T)));
     CK(cudaMalloc(&d_out, nelmt * NQTOT * sizeof(T)));
     CK(cudaMalloc(&d_ref, nelmt * NQTOT * sizeof(T)));
     CK(cudaMalloc(&d_basis, DIM * NM * NQ * sizeof(T)));
     CK(cudaMalloc(&d_bad, sizeof(unsigned long long)));
+    CK(cudaMalloc(&d_md, 2 * sizeof(unsigned long long)));
+    g_b0 = (const double *)d_basis;
+    g_b1 = (const double *)(d_basis + NM * NQ);
     fill_kernel<<<148 * 8, 256>>>(d_in, nelmt * NMTOT, NMTOT);
     std::vector<T> hb(DIM * NM * NQ);
     for (size_t k = 0; k < hb.size(); ++k)
@@ -166,8 +199,26 @@ int main(int argc, char **argv)
             CK(cudaMemcpy(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost));
         }
         const double gbs = 1e-9 * bytes / (ms[0] * 1e-3);
+        char verdict[64] = "ok";
+        if (bad && std::string(c.be) == "mma")
+        {
+            // tensor-core summation order differs: judged by the north_star tolerance (1e-12 of the largest value)
+            unsigned long long h[2] = {0, 0};
+            CK(cudaMemset(d_md, 0, sizeof(h)));
+            maxdiff_kernel<<<148 * 8, 256>>>(d_out, d_ref, nelmt * NQTOT, d_md);
+            CK(cudaMemcpy(h, d_md, sizeof(h), cudaMemcpyDeviceToHost));
+            double md, mb;
+            memcpy(&md, &h[0], 8);
+            memcpy(&mb, &h[1], 8);
+            const double rel = md / (mb > 0 ? mb : 1);
+            std::snprintf(verdict, sizeof(verdict), rel < 1e-12 ? "ok" : "MISMATCH(rel=%.2e)", rel);
+            if (rel < 1e-12)
+                std::fprintf(stderr, "# mma rel err %.3e\n", rel);
+        }
+        else if (bad)
+            std::snprintf(verdict, sizeof(verdict), "MISMATCH");
         std::printf("%d,%s,%d,%s,%d,%d,%d,%d,%zu,%d,%d,%.4f,%.4f,%.1f,%.4f,%s\n", DIM, tname, NQ, c.be, c.E, c.TH, c.R, c.V,
-                    c.smem, occ, fa.numRegs, ms[0], ms[reps / 2], gbs, gbs / peak, bad ? "MISMATCH" : "ok");
+                    c.smem, occ, fa.numRegs, ms[0], ms[reps / 2], gbs, gbs / peak, verdict);
         std::fflush(stdout);
     }
     return 0;
