@@ -257,8 +257,11 @@ def main():
     import torch
     import torch.distributed as dist
 
+    import importlib
+
     import b200fe_loader
     fe = b200fe_loader.load()  # raises if libb200fe.so is missing: no fallback
+    sharding = importlib.import_module("gpu-benchmarking_b200.sharding")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -279,7 +282,9 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
 
     # ---- this rank's shard: elements [rank*NELMT_PER_GPU, (rank+1)*NELMT_PER_GPU) -----------------
-    nelmt = NELMT_PER_GPU
+    e_begin, e_end = sharding.shard_range(NELMT_PER_GPU * world, rank, world)
+    nelmt = e_end - e_begin
+    assert nelmt == NELMT_PER_GPU
     h_b = torch.from_numpy(oracle.gen_basis(NM, NQ))
     h_one = torch.from_numpy(oracle.gen_in(1024, NM ** 3))       # reference generator (oracle port)
     h_in = h_one.view(1024, -1).repeat(nelmt // 1024, 1).reshape(-1).contiguous().pin_memory()
@@ -316,18 +321,13 @@ def main():
     total_ms = t_begin.elapsed_time(t_end)
     kern_ms = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)) / args.steps
     backend = fe.last_backend()
-    if world > 1:
-        t = torch.tensor([total_ms, kern_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, kern_ms = float(t[0]), float(t[1])
+    total_ms, kern_ms = sharding.max_over_ranks([total_ms, kern_ms], device="cuda")
     ms_per_step = total_ms / args.steps
     value = 1e-9 * nelmt * ngpus * NM ** 3 / (ms_per_step * 1e-3)
 
     # ---- result check: global norm (NCCL scalar all-reduce) vs the reference's golden checksum ----
     fe.sumsq("f64", d_out.data_ptr(), d_out.numel(), d_res.data_ptr(), d_scr.data_ptr(), st)
-    if world > 1:
-        dist.all_reduce(d_res, op=dist.ReduceOp.SUM)
-    norm = math.sqrt(float(d_res.item()))
+    norm = sharding.global_norm(float(d_res.item()), device="cuda")  # NCCL all-reduce of one double
     want = GOLDEN_NORM_128 * math.sqrt(nelmt * ngpus / 128)
     norm_ok = abs(norm - want) / want < 6e-10
     el0 = d_out[: NQ ** 3].cpu().numpy()
@@ -355,10 +355,7 @@ def main():
     barrier()
     e2e_full_ms = (time.perf_counter() - t0) * 1e3 / max(2, args.e2e_steps // 2)
     del h_out
-    if world > 1:
-        t = torch.tensor([e2e_ms, e2e_full_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms, e2e_full_ms = float(t[0]), float(t[1])
+    e2e_ms, e2e_full_ms = sharding.max_over_ranks([e2e_ms, e2e_full_ms], device="cuda")
     chunk = max(32, ((24 << 20) // (NM ** 3 * 8)) // 32 * 32)
     nchunk = (nelmt + chunk - 1) // chunk
     e2e = {"value": 1e-9 * nelmt * ngpus * NM ** 3 / (e2e_ms * 1e-3), "unit": "GDoF/s",
