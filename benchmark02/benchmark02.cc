@@ -22,7 +22,7 @@ namespace
 template <typename T> struct Api;
 template <> struct Api<double>
 {
-    static constexpr auto set_data  = b200fe_set_data_f64;
+    static constexpr auto set_data  = b200fe_set_data_hostgen_f64; // benchmark02 initialises on the host
     static constexpr auto set_data2 = b200fe_set_data2_f64;
     static constexpr auto add       = b200fe_add_vector_f64;
     static constexpr auto functor   = b200fe_vector_kernel_add_f64;
@@ -35,7 +35,7 @@ template <> struct Api<double>
 };
 template <> struct Api<float>
 {
-    static constexpr auto set_data  = b200fe_set_data_f32;
+    static constexpr auto set_data  = b200fe_set_data_hostgen_f32;
     static constexpr auto set_data2 = b200fe_set_data2_f32;
     static constexpr auto add       = b200fe_add_vector_f32;
     static constexpr auto functor   = b200fe_vector_kernel_add_f32;

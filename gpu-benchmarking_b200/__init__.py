@@ -127,8 +127,8 @@ def bwdtrans_hex(kernel, suf, nq0, nq1, nq2, nelmt, b0, b1, b2, inp, out, wsp0=0
     _check(name, rc)
 
 
-def set_data(suf, data, n, second=False, stream=0):
-    name = f"b200fe_set_data{'2' if second else ''}_{suf}"
+def set_data(suf, data, n, second=False, stream=0, hostgen=False):
+    name = f"b200fe_set_data{'2' if second else ('_hostgen' if hostgen else '')}_{suf}"
     _check(name, getattr(lib(), name)(_vp(data), _u(n), _vp(stream)))
 
 

@@ -359,11 +359,15 @@ HEX_NOWSP(BwdTransHexKernel_QP_1D_Shared, f32, float, Backend::Auto)
 #define VEC_API(SUF, T)                                                                                      \
     int b200fe_set_data_##SUF(T *data, unsigned n, void *stream)                                             \
     {                                                                                                        \
-        return launch_set_data<T>(data, n, false, (cudaStream_t)stream);                                     \
+        return launch_set_data<T>(data, n, 0, (cudaStream_t)stream);                                         \
     }                                                                                                        \
     int b200fe_set_data2_##SUF(T *data, unsigned n, void *stream)                                            \
     {                                                                                                        \
-        return launch_set_data<T>(data, n, true, (cudaStream_t)stream);                                      \
+        return launch_set_data<T>(data, n, 1, (cudaStream_t)stream);                                         \
+    }                                                                                                        \
+    int b200fe_set_data_hostgen_##SUF(T *data, unsigned n, void *stream)                                     \
+    {                                                                                                        \
+        return launch_set_data<T>(data, n, 2, (cudaStream_t)stream);                                         \
     }                                                                                                        \
     int b200fe_l2norm_vl_##SUF(T *sums, const T *data, unsigned n, unsigned blocks, int vl, void *stream)    \
     {                                                                                                        \

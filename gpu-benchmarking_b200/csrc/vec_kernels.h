@@ -8,7 +8,7 @@ namespace b200fe
 template <typename T>
 int launch_reduce_partials(T *sums, const T *data, unsigned begin, unsigned end, unsigned slots, bool vl, bool square,
                            cudaStream_t s);
-template <typename T> int launch_set_data(T *data, unsigned n, bool second, cudaStream_t s);
+template <typename T> int launch_set_data(T *data, unsigned n, int mode, cudaStream_t s);
 template <typename T> int launch_add_vector(T *x, const T *y, unsigned begin, unsigned end, bool vl, cudaStream_t s);
 template <typename T> int launch_matvec(unsigned N, unsigned M, const T *A, const T *x, T *y, bool vl, cudaStream_t s);
 size_t sumsq_scratch_bytes();

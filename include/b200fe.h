@@ -180,10 +180,16 @@ int b200fe_BwdTransHexKernel_QP_1D_Shared_f32(unsigned nm0, unsigned nm1, unsign
  * (the reference's per-warp atomicAdd order is not) and the cudaMemset calls
  * of the reference's timed region are unnecessary but harmless. */
 
-/* replaces set_data<T>                            benchmark01/benchmark01.cc:171-181 */
+/* replaces set_data<T>                            benchmark01/benchmark01.cc:171-181
+ * data[i] = i%13 + (0.2 + 1e-5*(i%100191)), bit-identical to the reference's device kernel
+ * (nvcc contracts 0.2 + 1e-5*k into one fused multiply-add) */
 int b200fe_set_data_f64(double *data, unsigned n, void *stream);
 int b200fe_set_data_f32(float *data, unsigned n, void *stream);
-/* second generator y[i] = i%8 + (0.4 + 3e-5*(i%100721))   benchmark02/benchmark02.cc:143 */
+/* device-side twins of benchmark02's HOST generators (benchmark02/benchmark02.cc:142-143; g++ rounds every
+ * operation separately): _hostgen is x[i] (same formula as set_data, unfused), set_data2 is
+ * y[i] = i%8 + (0.4 + 3e-5*(i%100721)) */
+int b200fe_set_data_hostgen_f64(double *data, unsigned n, void *stream);
+int b200fe_set_data_hostgen_f32(float *data, unsigned n, void *stream);
 int b200fe_set_data2_f64(double *data, unsigned n, void *stream);
 int b200fe_set_data2_f32(float *data, unsigned n, void *stream);
 /* replaces l2norm_vl<T,vl>: sums[b] = partial sum of data[i]^2   benchmark01.cc:15-77 */

@@ -121,9 +121,10 @@ def bwdtrans_hex(nq0, nq1, nq2, nelmt, b0, b1, b2, inp, coa=False, use_fma=True)
 
 # ---- benchmark01-03 ------------------------------------------------------------
 
-def set_data(n, dtype=np.float64, second=False):
+def set_data(n, dtype=np.float64, second=False, fused=False):
+    """second: benchmark02's y generator; fused: the first generator as the reference's DEVICE kernel rounds it"""
     a = np.empty(int(n), dtype=dtype)
-    fn = "oracle_set_data2" if second else "oracle_set_data"
+    fn = "oracle_set_data2" if second else ("oracle_set_data_fused" if fused else "oracle_set_data")
     getattr(lib(), f"{fn}_{_suf(dtype)}")(_p(a), _z(n))
     return a
 

@@ -279,6 +279,18 @@ void FN(oracle_set_data)(T *data, size_t n)
     }
 }
 
+/* the same statement as nvcc compiles it for the device (benchmark01.cc:178 inside the
+ * __global__ set_data): 0.2 + 1e-5*k is contracted into one fused multiply-add. */
+void FN(oracle_set_data_fused)(T *data, size_t n)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t ii = 0; ii < n; ++ii)
+    {
+        unsigned i = (unsigned)ii;
+        data[ii]   = (T)((double)(i % 13) + fma(0.00001, (double)(i % 100191), 0.2));
+    }
+}
+
 /* y[i] = i%8 + (0.4 + 3e-5*(i%100721)).  benchmark02.cc:143. */
 void FN(oracle_set_data2)(T *data, size_t n)
 {

@@ -123,10 +123,18 @@ B_SIZES = [1024, 2048, 65536, 1048576, 4194304]
 
 @pytest.mark.parametrize("n", B_SIZES)
 def test_b01_norm(golden, n):
-    x = oracle.set_data(n)
-    got = math.sqrt(oracle.sumsq(x))
-    for want in golden["b01"][str(n)]:
-        assert rel(got, want) < PRINT_TOL
+    for fused in (True, False):  # device rounding of benchmark01.cc:178 (FMA-contracted by nvcc) / host rounding
+        x = oracle.set_data(n, fused=fused)
+        got = math.sqrt(oracle.sumsq(x))
+        for want in golden["b01"][str(n)]:
+            assert rel(got, want) < PRINT_TOL
+
+
+def test_b01_fused_generator_differs_from_host_rounding_by_at_most_one_ulp():
+    n = 300000
+    a, b = oracle.set_data(n, fused=True), oracle.set_data(n, fused=False)
+    assert not np.array_equal(a, b)            # the contraction is observable ...
+    assert np.abs(a - b).max() <= np.spacing(np.abs(b).max())  # ... in the last bit only
 
 
 def test_b01_generator_is_bit_exact_integer_modulo():

@@ -29,10 +29,12 @@ def stream():
 def test_set_data_bit_exact(G, suf, n):
     import torch
     dt = G.NP[suf]
-    for second in (False, True):
+    for second, hostgen in ((False, False), (False, True), (True, False)):
         d = torch.empty(n, dtype=torch.float64 if suf == "f64" else torch.float32, device="cuda")
-        G.fe.set_data(suf, d.data_ptr(), n, second=second, stream=stream())
-        assert np.array_equal(G.host(d), oracle.set_data(n, dt, second=second))
+        G.fe.set_data(suf, d.data_ptr(), n, second=second, hostgen=hostgen, stream=stream())
+        # b200fe_set_data == the reference's device kernel (fused), _hostgen/_set_data2 == benchmark02's host loops
+        want = oracle.set_data(n, dt, second=second, fused=not (second or hostgen))
+        assert np.array_equal(G.host(d), want)
 
 
 @pytest.mark.parametrize("suf", ["f64", "f32"])
@@ -80,7 +82,7 @@ def test_b01_golden_norm_and_subrange(G, golden):
     b, e = 12345, 7654321
     G.fe.reduce_sum_sumsq("f64", b, e, sums.data_ptr(), d.data_ptr(), 1024, stream())
     G.fe.reduce_vl("f64", res.data_ptr(), sums.data_ptr(), 1024, True, stream())
-    want = oracle.sumsq(oracle.set_data(n)[b:e])
+    want = oracle.sumsq(oracle.set_data(n, fused=True)[b:e])
     assert abs(float(res.item()) - want) / want < 1e-12
 
 
@@ -105,7 +107,7 @@ def test_b02_golden_norm(G, golden):
     n = 1 << 22
     dx = torch.empty(n, dtype=torch.float64, device="cuda")
     dy = torch.empty(n, dtype=torch.float64, device="cuda")
-    G.fe.set_data("f64", dx.data_ptr(), n, stream=stream())
+    G.fe.set_data("f64", dx.data_ptr(), n, hostgen=True, stream=stream())  # benchmark02 initialises on the host
     G.fe.set_data("f64", dy.data_ptr(), n, second=True, stream=stream())
     for _ in range(40):
         G.fe.add_vector("f64", dx.data_ptr(), dy.data_ptr(), n, True, stream())
