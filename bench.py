@@ -94,7 +94,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.002)
 
     def start(self):
         if self.nv:
@@ -242,6 +242,7 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the per-operator sweep (extra key `sweep`)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--backend", default="auto", help="force a BwdTrans back-end (rows|pipe|mma), for experiments")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -262,6 +263,8 @@ def main():
     import b200fe_loader
     fe = b200fe_loader.load()  # raises if libb200fe.so is missing: no fallback
     sharding = importlib.import_module("gpu-benchmarking_b200.sharding")
+    if args.backend != "auto":
+        fe.set_backend(args.backend)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -319,7 +322,12 @@ def main():
     clocks = sampler.stop()
     launches = fe.launch_count() - launches0
     total_ms = t_begin.elapsed_time(t_end)
-    kern_ms = sum(ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)) / args.steps
+    series = [ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)]
+    log("per-step ms:", " ".join(f"{t:.3f}" for t in series))
+    per_step = sorted(series)
+    kern_ms = sum(per_step) / args.steps
+    step_stats = {"min": per_step[0], "p50": per_step[len(per_step) // 2], "p90": per_step[(9 * len(per_step)) // 10],
+                  "max": per_step[-1]}
     backend = fe.last_backend()
     total_ms, kern_ms = sharding.max_over_ranks([total_ms, kern_ms], device="cuda")
     ms_per_step = total_ms / args.steps
@@ -378,7 +386,8 @@ def main():
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "kernel": f"bwdtrans_hex_{backend}_kernel<double,8>",
-                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": kern_ms}
+                "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_ms": kern_ms,
+                "launch_ms_distribution": step_stats}
 
     if rank != 0:
         if world > 1:

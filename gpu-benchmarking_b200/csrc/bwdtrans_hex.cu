@@ -20,13 +20,12 @@ static int hex_rows_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cud
         return launch_hex_rows<T, NQ, E, TH, R, V>(nelmt, in, out, s);
 #define PIPE_CASE(NQ, E, TH, R, V)
 #define PREFER(NQ, BE)
-#ifndef MMA_CASE
-#define MMA_CASE(...)
-#endif
+#define MMA_CASE(NQ, G, W, MB0, NB1)
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE
 #undef PREFER
+#undef MMA_CASE
     default:
         return B200FE_EUNSUPPORTED;
     }
@@ -41,23 +40,61 @@ static int hex_pipe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cud
     case NQ:                                                                                                 \
         return launch_hex_pipe<T, NQ, E, TH, R, V>(nelmt, in, out, s);
 #define PREFER(NQ, BE)
-#ifndef MMA_CASE
-#define MMA_CASE(...)
-#endif
+#define MMA_CASE(NQ, G, W, MB0, NB1)
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE
 #undef PREFER
+#undef MMA_CASE
     default:
         return B200FE_EUNSUPPORTED;
     }
 }
 
-// what the table offers for this nq: bit 0 rows, bit 1 pipe; *preferred = default routing
+// FP64 tensor-core variant (only the f64 table lists MMA_CASE lines)
+static int hex_mma_switch(unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *b2, const T *in, T *out,
+                          cudaStream_t s)
+{
+    switch (nq)
+    {
+#define ROWS_CASE(NQ, E, TH, R, V)
+#define PIPE_CASE(NQ, E, TH, R, V)
+#define PREFER(NQ, BE)
+#define MMA_CASE(NQ, G, W, MB0, NB1)                                                                         \
+    case NQ:                                                                                                 \
+        return launch_hex_mma<NQ, G, W, MB0, NB1>(nelmt, b0, b1, b2, in, out, s);
+#include B200FE_ROWS_TABLE
+#undef ROWS_CASE
+#undef PIPE_CASE
+#undef PREFER
+#undef MMA_CASE
+    default:
+        return B200FE_EUNSUPPORTED;
+    }
+}
+
+// what the table offers for this nq: bit 0 rows, bit 1 pipe, bit 2 mma; *preferred = default routing
 static int hex_table_lookup(unsigned nq, Backend *preferred)
 {
     int have   = 0;
     *preferred = Backend::Generic;
+    switch (nq)
+    {
+#define ROWS_CASE(NQ, E, TH, R, V)
+#define PIPE_CASE(NQ, E, TH, R, V)
+#define PREFER(NQ, BE)
+#define MMA_CASE(NQ, G, W, MB0, NB1)                                                                         \
+    case NQ:                                                                                                 \
+        have |= 4;                                                                                           \
+        break;
+#include B200FE_ROWS_TABLE
+#undef ROWS_CASE
+#undef PIPE_CASE
+#undef PREFER
+#undef MMA_CASE
+    default:
+        break;
+    }
     switch (nq)
     {
 #define ROWS_CASE(NQ, E, TH, R, V)                                                                              \
@@ -66,13 +103,12 @@ static int hex_table_lookup(unsigned nq, Backend *preferred)
         break;
 #define PIPE_CASE(NQ, E, TH, R, V)
 #define PREFER(NQ, BE)
-#ifndef MMA_CASE
-#define MMA_CASE(...)
-#endif
+#define MMA_CASE(NQ, G, W, MB0, NB1)
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE
 #undef PREFER
+#undef MMA_CASE
     default:
         break;
     }
@@ -84,13 +120,12 @@ static int hex_table_lookup(unsigned nq, Backend *preferred)
         have |= 2;                                                                                           \
         break;
 #define PREFER(NQ, BE)
-#ifndef MMA_CASE
-#define MMA_CASE(...)
-#endif
+#define MMA_CASE(NQ, G, W, MB0, NB1)
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE
 #undef PREFER
+#undef MMA_CASE
     default:
         break;
     }
@@ -102,13 +137,12 @@ static int hex_table_lookup(unsigned nq, Backend *preferred)
     case NQ:                                                                                                 \
         *preferred = Backend::BE;                                                                            \
         break;
-#ifndef MMA_CASE
-#define MMA_CASE(...)
-#endif
+#define MMA_CASE(NQ, G, W, MB0, NB1)
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE
 #undef PREFER
+#undef MMA_CASE
     default:
         break;
     }
@@ -153,6 +187,8 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
         // the bulk-copy ring needs a 16-byte aligned slab; otherwise take the plain-load twin
         if (be == Backend::Pipe && (!(have & 2) || !aligned16(in)))
             be = (have & 1) ? Backend::Rows : Backend::Generic;
+        if (be == Backend::Mma && !(have & 4))
+            be = (have & 1) ? Backend::Rows : Backend::Generic;
         if (be == Backend::Rows && !(have & 1))
             be = Backend::Generic;
     }
@@ -161,10 +197,13 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
         t_last_backend = "generic";
         return launch_hex_generic<T>(nm0, nm1, nm2, nq0, nq1, nq2, nelmt, b0, b1, b2, in, out, coa, stream);
     }
-    if (!regular || ((be == Backend::Rows || be == Backend::Pipe) && coa) || (be == Backend::Tpe && !coa))
+    if (!regular || ((be == Backend::Rows || be == Backend::Pipe || be == Backend::Mma) && coa) ||
+        (be == Backend::Tpe && !coa))
         return B200FE_EUNSUPPORTED;
     if (be == Backend::Pipe && (!(have & 2) || !aligned16(in)))
         return B200FE_EUNSUPPORTED;
+    if (be == Backend::Mma) // reads the basis matrices from global memory: no constant bank, no lock
+        return (have & 4) ? hex_mma_switch(nq0, nelmt, b0, b1, b2, in, out, stream) : B200FE_EUNSUPPORTED;
 
     std::lock_guard<std::mutex> lock(g_bank_lock);
     const T *bases[3]   = {b0, b1, b2};

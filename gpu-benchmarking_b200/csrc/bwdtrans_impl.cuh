@@ -174,6 +174,28 @@ int launch_hex_pipe(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
     return launch_status();
 }
 
+template <int NQ, int G, int WARPS, int MB0, int NB>
+int launch_hex_mma(unsigned nelmt, const double *b0, const double *b1, const double *b2, const double *in, double *out,
+                   cudaStream_t stream)
+{
+    using C = HexMma<NQ, G, WARPS, MB0, NB>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "warp regions do not fit shared memory");
+    static int occ[64] = {};
+    auto kernel        = bwdtrans_hex_mma_kernel<NQ, G, WARPS, MB0, NB>;
+    int rc             = opt_in_smem(kernel, C::SMEM);
+    if (rc)
+        return rc;
+    const unsigned ngroups = (nelmt + G - 1) / G;
+    const unsigned need    = (ngroups + WARPS - 1) / WARPS;
+    const unsigned fit     = (unsigned)(sm_count() * ctas_per_sm(kernel, WARPS * 32, C::SMEM, occ));
+    const unsigned grid    = need < fit ? need : fit;
+    const int out_vec      = aligned16(out);
+    kernel<<<grid, WARPS * 32, C::SMEM, stream>>>(b0, b1, b2, in, out, nelmt, ngroups, out_vec);
+    count_launch();
+    t_last_backend = "mma";
+    return launch_status();
+}
+
 template <typename T, int NQ> int launch_hex_tpe_coa(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
 {
     constexpr int THREADS = 128;

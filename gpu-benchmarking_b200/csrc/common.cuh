@@ -163,7 +163,21 @@ struct BankGuard
     cudaEvent_t done[64] = {};
     cudaStream_t last[64] = {};
     bool used[64]         = {};
+    void *bank[64]        = {}; // global address of this translation unit's constant bank, per device
 };
+
+// One tiny kernel writes the bank through the symbol's global address (constant caches are
+// invalidated at kernel boundaries, so the next kernel on the stream sees the new values).  This
+// replaces three cudaMemcpyToSymbolAsync calls, which cost ~10 us of stream time per operator call --
+// 6-12 % of a 64 Mi-point operator.
+template <typename T>
+__global__ void fill_bank_kernel(T *__restrict__ bank, const T *__restrict__ b0, int n0, const T *__restrict__ b1,
+                                 int n1, const T *__restrict__ b2, int n2)
+{
+    const int n = n0 + n1 + n2;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        bank[i] = i < n0 ? b0[i] : (i < n0 + n1 ? b1[i - n0] : b2[i - n0 - n1]);
+}
 
 template <typename T>
 inline int fill_basis_bank(BankGuard &g, int nb, const T *const *basis, const int *count, cudaStream_t stream)
@@ -174,19 +188,20 @@ inline int fill_basis_bank(BankGuard &g, int nb, const T *const *basis, const in
         return B200FE_EUNSUPPORTED;
     if (g.used[dev] && g.last[dev] != stream)
         B200FE_CUDA_TRY(cudaStreamWaitEvent(stream, g.done[dev], 0));
-    size_t off = 0;
-    for (int b = 0; b < nb; ++b)
+    if (!g.bank[dev])
     {
-        const size_t bytes = (size_t)count[b] * sizeof(T);
         if (std::is_same<T, double>::value)
-            B200FE_CUDA_TRY(cudaMemcpyToSymbolAsync(c_basis_f64, basis[b], bytes, off, cudaMemcpyDeviceToDevice,
-                                                    stream));
+            B200FE_CUDA_TRY(cudaGetSymbolAddress(&g.bank[dev], c_basis_f64));
         else
-            B200FE_CUDA_TRY(cudaMemcpyToSymbolAsync(c_basis_f32, basis[b], bytes, off, cudaMemcpyDeviceToDevice,
-                                                    stream));
-        off += bytes;
+            B200FE_CUDA_TRY(cudaGetSymbolAddress(&g.bank[dev], c_basis_f32));
     }
-    return 0;
+    const int n0 = count[0], n1 = nb > 1 ? count[1] : 0, n2 = nb > 2 ? count[2] : 0;
+    if (n0 + n1 + n2 > kBasisBankElems)
+        return B200FE_EUNSUPPORTED;
+    fill_bank_kernel<T><<<1, 256, 0, stream>>>(static_cast<T *>(g.bank[dev]), basis[0], n0, nb > 1 ? basis[1] : basis[0],
+                                               n1, nb > 2 ? basis[2] : basis[0], n2);
+    count_launch();
+    return launch_status();
 }
 
 inline int release_basis_bank(BankGuard &g, cudaStream_t stream)

@@ -1,11 +1,11 @@
 // sumfac_mma.cuh -- "mma" back-end: FP64 sum-factorisation on the tensor cores
-// (DMMA, mma.sync.m8n8k4.f64) for the large-nq quads, where the contraction is a
-// dense GEMM-shaped problem that the scalar FP64 pipe cannot feed fast enough:
-// per element 2*nq*nm*(nm+nq) flops against 8*(nm^2+nq^2) bytes is 3.4-7.9 flop/B
-// for nq = 14..32, i.e. 22-51 TFLOP/s at the HBM roofline, while DFMA with a
-// constant-bank operand tops out near 27 TFLOP/s on B200 (profiles/r01_ubench_fp_pipe.txt)
-// and DMMA sustains 37 TFLOP/s from registers with 1/8 of the issue slots
-// (profiles/r01_ubench_dmma.txt).
+// (DMMA, mma.sync.m8n8k4.f64 = SASS DMMA.8x8x4) for the cases where the contraction is
+// a dense GEMM-shaped problem that the scalar FP64 pipe cannot feed fast enough.  Quad:
+// per element 2*nq*nm*(nm+nq) flops against 8*(nm^2+nq^2) bytes is 2.9-7.9 flop/B for
+// nq = 12..32, i.e. 19-51 TFLOP/s at the HBM roofline, while DFMA with a constant-bank
+// operand tops out near 27 TFLOP/s on B200 (profiles/r01_ubench_fp_pipe.txt) and DMMA
+// sustains 37 TFLOP/s from registers with 1/8 of the issue slots
+// (profiles/r01_ubench_dmma.txt).  Hex: nq = 8 fills the 8x8x4 tile exactly.
 //
 // Work unit: one WARP owns a group of G consecutive elements from load to store;
 // warps never synchronise with each other (only __syncwarp), so their load /
@@ -14,19 +14,21 @@
 //   load   the group's contiguous slab in[e0 .. e0+G) is fetched by ONE bulk
 //          tensor-memory-accelerator copy (cp.async.bulk, completion on the warp's
 //          own mbarrier).  The copy of the next group is issued as soon as direction
-//          0 has consumed the slot, so it lands while direction 1 computes.
-//   dir 0  mid[(e,q)][i] = sum_p in[(e,q)][p] * B0[p][i]
-//          A = data rows (M = flattened (e,q), K = p), B = basis fragments.
-//   dir 1  out[e][j][i]  = sum_q B1[q][j] * mid[e][q][i]
-//          A = transposed basis fragments (M = j, K = q), B = mid (N = flattened
-//          (e,i)); each lane ends up with out[e][j][i..i+1]: one 16-byte store.
+//          0 has consumed the slot, so it lands while the later directions compute.
+//   dir 0  mid[(e,..,q)][i] = sum_p in[(e,..,q)][p] * B0[p][i]
+//          A = data rows (M = all rows of the group, flattened), B = basis fragments.
+//   dir 1+ out[..][j][..]   = sum_q B1[q][j] * mid[..][q][..]
+//          A = transposed basis fragments (M = j, K = q), B = the intermediate
+//          (N = everything else, flattened); each lane ends up with two outputs
+//          adjacent in i: one 16-byte store (streaming, to global, in the last direction).
 //
 // Padding of M/N/K up to the 8x8x4 tile is done with zeros in the basis
 // fragments and with clamped / zero-selected data loads, never by touching
-// memory outside the group.  The summation order inside a k = 4 step is the
-// hardware's, so results agree with the reference to rounding (<= 1e-12
-// relative, tests/test_bwdtrans_gpu.py), not bit for bit; the rows / pipe
-// back-ends remain the bit-exact ones.
+// memory outside the group.  DMMA.8x8x4 on sm_100 accumulates its four products
+// in k order with fused multiply-adds, which is the reference's own summation
+// order, so this back-end too is bit-identical to the reference kernels
+// (tests/test_bwdtrans_gpu.py, tests/test_reference_kernels_gpu.py compare with
+// array_equal); the documented bar, should hardware ever differ, is 1e-12.
 #pragma once
 
 #include "sumfac_rows.cuh"
@@ -51,28 +53,371 @@ constexpr int mma_mid_stride(int nq)
     return s;
 }
 
-template <int NQ, int G, int WARPS, int MB0, int NB1> struct QuadMma
+// ---- the two pass shapes ------------------------------------------------------------------
+//
+// pass_data_rows: A = data.  nrows rows of NM values, row r at src + r*NM (contiguous rows: the raw
+// element-major slab), contracted with the basis fragments fragB[ks][nt]; output (row, i) to
+// dst + row*DS + i (shared memory).  MB m-tiles (8 rows each) share every B fragment.
+template <int NQ, int DS, int MB>
+__device__ __forceinline__ void mma_pass_data_rows(const double *__restrict__ src, const double *__restrict__ fragB,
+                                                   double *__restrict__ dst, int nrows, int lane)
 {
-    static constexpr int NM    = NQ - 1;
-    static constexpr int NM2   = NM * NM;
-    static constexpr int NQ2   = NQ * NQ;
-    static constexpr int KS    = (NM + 3) / 4;     // k steps (K = nm in both directions)
-    static constexpr int NT0   = (NQ + 7) / 8;     // direction 0: n tiles over i
-    static constexpr int MT1   = (NQ + 7) / 8;     // direction 1: m tiles over j
-    static constexpr int ROWS0 = G * NM;           // direction 0: M = flattened (e, q)
-    static constexpr int MT0   = (ROWS0 + 7) / 8;
-    static constexpr int COLS1 = G * NQ;           // direction 1: N = flattened (e, i)
-    static constexpr int NT1   = (COLS1 + 7) / 8;
-    static constexpr int S     = mma_mid_stride(NQ);
-    static constexpr int SLOT  = (G * NM2 + 1 + 3 + 1) / 2 * 2; // +1: 8-byte window offset, +3: k over-read of the last row
-    static constexpr int MID   = G * NM * S;
-    static constexpr int WARP_D = SLOT + MID;      // doubles per warp (even)
-    static constexpr int FRAG0 = KS * NT0 * 32;
-    static constexpr int FRAG1 = MT1 * KS * 32;
-    static constexpr int BAR_BYTES = (WARPS * 8 + 15) / 16 * 16;
-    static constexpr size_t SMEM = BAR_BYTES + (size_t)(FRAG0 + FRAG1 + WARPS * WARP_D) * sizeof(double);
-    static_assert(NQ % 2 == 0, "the mma back-end pairs outputs along i");
-};
+    constexpr int NM = NQ - 1, KS = (NM + 3) / 4, NT = (NQ + 7) / 8;
+    const int r = lane >> 2, c = lane & 3;
+#pragma unroll 1
+    for (int mt = 0; mt * 8 < nrows; mt += MB)
+    {
+        double acc[MB][NT][2];
+        const double *ap[MB];
+#pragma unroll
+        for (int m = 0; m < MB; ++m)
+        {
+            const int row = (mt + m) * 8 + r;
+            ap[m]         = src + (row < nrows ? row : nrows - 1) * NM + c;
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+                acc[m][n][0] = acc[m][n][1] = 0.0;
+        }
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+        {
+            double a[MB], b[NT];
+#pragma unroll
+            for (int m = 0; m < MB; ++m)
+            {
+                a[m] = ap[m][4 * ks]; // may over-read up to 3 values past the row: still inside the slot
+                if (4 * ks + 3 >= NM && 4 * ks + c >= NM)
+                    a[m] = 0.0; // k padding: whatever lies there (next row, Inf, NaN) must not contribute
+            }
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+                b[n] = fragB[(ks * NT + n) * 32 + lane];
+#pragma unroll
+            for (int m = 0; m < MB; ++m)
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+                    dmma884(acc[m][n], a[m], b[n]);
+        }
+#pragma unroll
+        for (int m = 0; m < MB; ++m)
+        {
+            const int row = (mt + m) * 8 + r;
+            if (row < nrows)
+            {
+                double *mp = dst + row * DS + 2 * c;
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+                    if (8 * n + 2 * c < NQ)
+                        *reinterpret_cast<double2 *>(mp + 8 * n) = make_double2(acc[m][n][0], acc[m][n][1]);
+            }
+        }
+    }
+}
+
+// pass_basis_rows: A = transposed basis fragments fragA[mt][ks] (M = the NQ new points, K = NM).  The
+// data is the B operand: column n of ncols decomposes as (g, w) = (n / W, n % W) and its K values lie
+// STRIDE apart: src + (g*NM + k)*STRIDE + w.  Output (m, n) goes to dst + g*DG + m*DM + w, i.e. each
+// lane holds two values adjacent in w: one 16-byte store, to shared memory or (streaming) to global.
+template <int NQ, int W, int STRIDE, int DG, int DM, int NB, bool TO_GLOBAL>
+__device__ __forceinline__ void mma_pass_basis_rows(const double *__restrict__ src, const double *__restrict__ fragA,
+                                                    double *__restrict__ dst, int ncols, bool vec, int lane)
+{
+    constexpr int NM = NQ - 1, KS = (NM + 3) / 4, MT = (NQ + 7) / 8;
+    static_assert(W % 2 == 0, "outputs are paired along w");
+    const int r = lane >> 2, c = lane & 3;
+#pragma unroll 1
+    for (int nt = 0; nt * 8 < ncols; nt += NB)
+    {
+        double acc[MT][NB][2];
+        const double *bp[NB];
+#pragma unroll
+        for (int t = 0; t < NB; ++t)
+        {
+            const int n  = (nt + t) * 8 + r;
+            const int nc = n < ncols ? n : ncols - 1;
+            const int g = nc / W, w = nc - g * W;
+            bp[t] = src + (g * NM + c) * STRIDE + w;
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+                acc[m][t][0] = acc[m][t][1] = 0.0;
+        }
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+        {
+            double a[MT], b[NB];
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+                a[m] = fragA[(m * KS + ks) * 32 + lane];
+#pragma unroll
+            for (int t = 0; t < NB; ++t)
+            {
+                if (4 * ks + 3 < NM)
+                    b[t] = bp[t][4 * ks * STRIDE];
+                else
+                    b[t] = (4 * ks + c < NM) ? bp[t][4 * ks * STRIDE] : 0.0; // rows >= nm do not exist
+            }
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int t = 0; t < NB; ++t)
+                    dmma884(acc[m][t], a[m], b[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < NB; ++t)
+        {
+            const int n = (nt + t) * 8 + 2 * c;
+            if (n < ncols)
+            {
+                const int g = n / W, w = n - g * W;
+                double *op = dst + (size_t)g * DG + w;
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                {
+                    const int j = 8 * m + r;
+                    if (j < NQ)
+                    {
+                        if (!TO_GLOBAL)
+                            *reinterpret_cast<double2 *>(op + j * DM) = make_double2(acc[m][t][0], acc[m][t][1]);
+                        else if (vec)
+                            st_stream(reinterpret_cast<double2 *>(op + j * DM), make_double2(acc[m][t][0], acc[m][t][1]));
+                        else
+                        {
+                            st_stream(op + j * DM, acc[m][t][0]);
+                            st_stream(op + j * DM + 1, acc[m][t][1]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- fully unrolled twins for a FULL group (compile-time row / column counts) ------------------
+// Every tile index is a compile-time constant, so all shared-memory offsets become immediates of
+// one per-lane base register and no index arithmetic is left in the instruction stream: per element
+// the generic loops issue ~15 instructions per DMMA (hex nq = 8), these ~3.
+// The blocks are software pipelined by hand: the operand loads of block b+1 are issued before the
+// DMMAs of block b, its stores after them.  dmma884_ordered keeps the issue order written here --
+// all first k steps of a block's independent accumulators, then all second ones -- so that no DMMA
+// waits for the one issued just before it (ptxas otherwise schedules each accumulator's dependent
+// chain back to back).
+__device__ __forceinline__ void dmma884_ordered(double (&c)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1])
+                 : "d"(a), "d"(b));
+}
+
+template <int NQ, int DS, int MB, int NROWS>
+__device__ __forceinline__ void mma_pass_data_rows_full(const double *__restrict__ src,
+                                                        const double *__restrict__ fragB, double *__restrict__ dst,
+                                                        int lane)
+{
+    constexpr int NM = NQ - 1, KS = (NM + 3) / 4, NT = (NQ + 7) / 8, MT = (NROWS + 7) / 8;
+    constexpr int NBLK = (MT + MB - 1) / MB;
+    const int r = lane >> 2, c = lane & 3;
+    const double *abase = src + r * NM + c;   // row (8*mt + r), column c
+    double *dbase       = dst + r * DS + 2 * c;
+    const bool kpad     = c >= NM - 4 * (KS - 1); // this lane's column of the last k step is padding
+
+    double b[KS][NT]; // the basis fragments are the same for every block: loaded once per pass
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+            b[ks][n] = fragB[(ks * NT + n) * 32 + lane];
+
+    double a[2][MB][KS];
+    auto load_block = [&](int blk, double (&dstA)[MB][KS]) {
+#pragma unroll
+        for (int m = 0; m < MB; ++m)
+            if (blk * MB + m < MT)
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks)
+                {
+                    // rows >= NROWS of the last tile read whatever follows the slab inside this warp's
+                    // region: rows are independent and those outputs are never stored
+                    dstA[m][ks] = abase[(blk * MB + m) * 8 * NM + 4 * ks];
+                    if (4 * ks + 3 >= NM && kpad)
+                        dstA[m][ks] = 0.0; // k padding must not contribute whatever lies there
+                }
+    };
+    load_block(0, a[0]);
+#pragma unroll
+    for (int blk = 0; blk < NBLK; ++blk)
+    {
+        if (blk + 1 < NBLK)
+            load_block(blk + 1, a[(blk + 1) & 1]);
+        double acc[MB][NT][2];
+#pragma unroll
+        for (int m = 0; m < MB; ++m)
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+                acc[m][n][0] = acc[m][n][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int m = 0; m < MB; ++m)
+                if (blk * MB + m < MT)
+#pragma unroll
+                    for (int n = 0; n < NT; ++n)
+                        dmma884_ordered(acc[m][n], a[blk & 1][m][ks], b[ks][n]);
+#pragma unroll
+        for (int m = 0; m < MB; ++m)
+            if (blk * MB + m < MT)
+            {
+                const int mt     = blk * MB + m;
+                const bool whole = mt * 8 + 8 <= NROWS;
+                if (whole || r < NROWS - mt * 8)
+                {
+#pragma unroll
+                    for (int n = 0; n < NT; ++n)
+                        if (8 * n + 8 <= NQ || 8 * n + 2 * c < NQ)
+                            *reinterpret_cast<double2 *>(dbase + mt * 8 * DS + 8 * n) =
+                                make_double2(acc[m][n][0], acc[m][n][1]);
+                }
+            }
+    }
+}
+
+// needs NCOLS % 8 == 0.  A tile of 8 columns may straddle two groups when W % 8 != 0: the lanes past
+// the group boundary then add one compile-time constant to their address (a predicated add per tile).
+template <int NQ, int W, int STRIDE, int DG, int DM, int NB, bool TO_GLOBAL, bool VEC, int NCOLS>
+__device__ __forceinline__ void mma_pass_basis_rows_full(const double *__restrict__ src,
+                                                         const double *__restrict__ fragA, double *__restrict__ dst,
+                                                         int lane)
+{
+    constexpr int NM = NQ - 1, KS = (NM + 3) / 4, MT = (NQ + 7) / 8, NTT = NCOLS / 8;
+    constexpr int NBLK = (NTT + NB - 1) / NB;
+    static_assert(W % 2 == 0 && NCOLS % 8 == 0, "whole tiles, outputs paired along w");
+    const int r = lane >> 2, c = lane & 3;
+    const double *bbase = src + c * STRIDE + r;    // k row c, column r of tile 0
+    double *dbase       = dst + r * DM + 2 * c;    // output row r, column pair c
+    const bool kpad     = c >= NM - 4 * (KS - 1);
+
+    double a[MT][KS]; // transposed basis fragments: loaded once per pass
+#pragma unroll
+    for (int m = 0; m < MT; ++m)
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+            a[m][ks] = fragA[(m * KS + ks) * 32 + lane];
+
+    double b[2][NB][KS];
+    auto load_block = [&](int blk, double (&dstB)[NB][KS]) {
+#pragma unroll
+        for (int t = 0; t < NB; ++t)
+            if (blk * NB + t < NTT)
+            {
+                const int g = ((blk * NB + t) * 8) / W, w0 = ((blk * NB + t) * 8) % W;
+                // columns w0 + r >= W belong to the next group: its rows start NM*STRIDE later
+                const double *bb = (w0 + 8 > W && r >= W - w0) ? bbase + (NM * STRIDE - W) : bbase;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks)
+                {
+                    if (4 * ks + 3 < NM)
+                        dstB[t][ks] = bb[(g * NM + 4 * ks) * STRIDE + w0];
+                    else
+                        dstB[t][ks] = kpad ? 0.0 : bb[(g * NM + 4 * ks) * STRIDE + w0]; // rows >= nm do not exist
+                }
+            }
+    };
+    load_block(0, b[0]);
+#pragma unroll
+    for (int blk = 0; blk < NBLK; ++blk)
+    {
+        if (blk + 1 < NBLK)
+            load_block(blk + 1, b[(blk + 1) & 1]);
+        double acc[MT][NB][2];
+#pragma unroll
+        for (int m = 0; m < MT; ++m)
+#pragma unroll
+            for (int t = 0; t < NB; ++t)
+                acc[m][t][0] = acc[m][t][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int m = 0; m < MT; ++m)
+#pragma unroll
+                for (int t = 0; t < NB; ++t)
+                    if (blk * NB + t < NTT)
+                        dmma884_ordered(acc[m][t], a[m][ks], b[blk & 1][t][ks]);
+#pragma unroll
+        for (int t = 0; t < NB; ++t)
+            if (blk * NB + t < NTT)
+            {
+                const int g = ((blk * NB + t) * 8) / W, w0 = ((blk * NB + t) * 8) % W;
+                double *db = (w0 + 8 > W && 2 * c >= W - w0) ? dbase + (DG - W) : dbase;
+#pragma unroll
+                for (int m = 0; m < MT; ++m)
+                    if (8 * m + 8 <= NQ || 8 * m + r < NQ)
+                    {
+                        double *op = db + (size_t)g * DG + w0 + 8 * m * DM;
+                        if (!TO_GLOBAL)
+                            *reinterpret_cast<double2 *>(op) = make_double2(acc[m][t][0], acc[m][t][1]);
+                        else if (VEC)
+                            st_stream(reinterpret_cast<double2 *>(op), make_double2(acc[m][t][0], acc[m][t][1]));
+                        else
+                        {
+                            st_stream(op, acc[m][t][0]);
+                            st_stream(op + 1, acc[m][t][1]);
+                        }
+                    }
+            }
+    }
+}
+
+// dispatch: unrolled twin for a full group where the shape allows it, generic loops otherwise
+template <int NQ, int DS, int MB, int NROWS>
+__device__ __forceinline__ void mma_dir_data(const double *__restrict__ src, const double *__restrict__ fragB,
+                                             double *__restrict__ dst, int nrows, int lane)
+{
+    if (nrows == NROWS)
+        mma_pass_data_rows_full<NQ, DS, MB, NROWS>(src, fragB, dst, lane);
+    else
+        mma_pass_data_rows<NQ, DS, MB>(src, fragB, dst, nrows, lane);
+}
+template <int NQ, int W, int STRIDE, int DG, int DM, int NB, bool TO_GLOBAL, int NCOLS>
+__device__ __forceinline__ void mma_dir_basis(const double *__restrict__ src, const double *__restrict__ fragA,
+                                              double *__restrict__ dst, int ncols, bool vec, int lane)
+{
+    if constexpr (NCOLS % 8 == 0)
+    {
+        if (ncols == NCOLS)
+        {
+            if (vec)
+                mma_pass_basis_rows_full<NQ, W, STRIDE, DG, DM, NB, TO_GLOBAL, true, NCOLS>(src, fragA, dst, lane);
+            else
+                mma_pass_basis_rows_full<NQ, W, STRIDE, DG, DM, NB, TO_GLOBAL, false, NCOLS>(src, fragA, dst, lane);
+            return;
+        }
+    }
+    mma_pass_basis_rows<NQ, W, STRIDE, DG, DM, NB, TO_GLOBAL>(src, fragA, dst, ncols, vec, lane);
+}
+
+// basis matrix B[p*NQ + i] -> B-operand fragments [ks][nt][lane] (K = p, N = i), zero padded
+template <int NQ, int THREADS>
+__device__ __forceinline__ void mma_fill_fragB(double *__restrict__ frag, const double *__restrict__ basis)
+{
+    constexpr int NM = NQ - 1, KS = (NM + 3) / 4, NT = (NQ + 7) / 8;
+    for (int idx = threadIdx.x; idx < KS * NT * 32; idx += THREADS)
+    {
+        const int l = idx & 31, t = idx >> 5, nt = t % NT, ks = t / NT;
+        const int p = 4 * ks + (l & 3), i = 8 * nt + (l >> 2);
+        frag[idx]   = (p < NM && i < NQ) ? basis[p * NQ + i] : 0.0;
+    }
+}
+// basis matrix B[q*NQ + j] -> A-operand fragments of its transpose [mt][ks][lane] (M = j, K = q)
+template <int NQ, int THREADS>
+__device__ __forceinline__ void mma_fill_fragA(double *__restrict__ frag, const double *__restrict__ basis)
+{
+    constexpr int NM = NQ - 1, KS = (NM + 3) / 4, MT = (NQ + 7) / 8;
+    for (int idx = threadIdx.x; idx < MT * KS * 32; idx += THREADS)
+    {
+        const int l = idx & 31, t = idx >> 5, ks = t % KS, mt = t / KS;
+        const int j = 8 * mt + (l >> 2), q = 4 * ks + (l & 3);
+        frag[idx]   = (j < NQ && q < NM) ? basis[q * NQ + j] : 0.0;
+    }
+}
 
 // Fetch group gn into the warp's slot.  Returns true when the data arrives through the
 // mbarrier (bulk copy of the enclosing 16-byte aligned window), false when it was copied
@@ -107,6 +452,25 @@ __device__ __forceinline__ bool mma_fetch_group(double *slot, uint64_t *bar, con
     return false;
 }
 
+// ============================== quad ==========================================
+
+template <int NQ, int G, int WARPS, int MB0, int NB1> struct QuadMma
+{
+    static constexpr int NM    = NQ - 1;
+    static constexpr int NM2   = NM * NM;
+    static constexpr int NQ2   = NQ * NQ;
+    static constexpr int KS    = (NM + 3) / 4;     // k steps (K = nm in both directions)
+    static constexpr int NT    = (NQ + 7) / 8;     // tiles over the nq new points of a direction
+    static constexpr int S     = mma_mid_stride(NQ);
+    static constexpr int SLOT  = (G * NM2 + 1 + 3 + 1) / 2 * 2; // +1: 8-byte window offset, +3: k over-read of the last row
+    static constexpr int MID   = G * NM * S;
+    static constexpr int WARP_D = SLOT + MID;      // doubles per warp (even)
+    static constexpr int FRAG  = KS * NT * 32;
+    static constexpr int BAR_BYTES = (WARPS * 8 + 15) / 16 * 16;
+    static constexpr size_t SMEM = BAR_BYTES + (size_t)(2 * FRAG + WARPS * WARP_D) * sizeof(double);
+    static_assert(NQ % 2 == 0, "the mma back-end pairs outputs along i");
+};
+
 template <int NQ, int G, int WARPS, int MB0, int NB1>
 __global__ void __launch_bounds__(WARPS * 32)
     bwdtrans_quad_mma_kernel(const double *__restrict__ basis0, const double *__restrict__ basis1,
@@ -114,42 +478,34 @@ __global__ void __launch_bounds__(WARPS * 32)
                              int out_vec)
 {
     using C = QuadMma<NQ, G, WARPS, MB0, NB1>;
-    constexpr int NM = C::NM, KS = C::KS, NT0 = C::NT0, MT1 = C::MT1, S = C::S;
+    constexpr int NM = C::NM, S = C::S;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
     double *frag0  = reinterpret_cast<double *>(smem_raw + C::BAR_BYTES);
-    double *frag1  = frag0 + C::FRAG0;
+    double *frag1  = frag0 + C::FRAG;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = lane >> 2, c = lane & 3;
-    double *slot = frag1 + C::FRAG1 + warp * C::WARP_D;
-    double *mid  = slot + C::SLOT;
+    double *slot  = frag1 + C::FRAG + warp * C::WARP_D;
+    double *mid   = slot + C::SLOT;
+    uint64_t *bar = bars + warp;
 
-    // basis matrices in fragment order, zero padded to the tile grid
-    for (int idx = threadIdx.x; idx < C::FRAG0; idx += WARPS * 32)
-    {
-        const int l = idx & 31, t = idx >> 5, nt = t % NT0, ks = t / NT0;
-        const int p = 4 * ks + (l & 3), i = 8 * nt + (l >> 2);
-        frag0[idx]  = (p < NM && i < NQ) ? basis0[p * NQ + i] : 0.0;
-    }
-    for (int idx = threadIdx.x; idx < C::FRAG1; idx += WARPS * 32)
-    {
-        const int l = idx & 31, t = idx >> 5, ks = t % KS, mt = t / KS;
-        const int j = 8 * mt + (l >> 2), q = 4 * ks + (l & 3);
-        frag1[idx]  = (j < NQ && q < NM) ? basis1[q * NQ + j] : 0.0;
-    }
+    mma_fill_fragB<NQ, WARPS * 32>(frag0, basis0);
+    mma_fill_fragA<NQ, WARPS * 32>(frag1, basis1);
     if (lane == 0)
     {
-        mbar_init(&bars[warp], 1);
+        mbar_init(bar, 1);
         mbar_fence_init();
     }
     __syncthreads();
 
+    // One input slot per warp: the next group's copy is issued as soon as direction 0 has drained it and
+    // lands under direction 1.  (A two-slot ring was measured: the extra shared memory costs more resident
+    // warps than the deeper prefetch gains -- profiles/r01_tune_mma.csv vs r01_tune_mma_2slot.csv.)
     const unsigned nw = gridDim.x * WARPS;
     unsigned g        = blockIdx.x * WARPS + warp;
-    unsigned phase    = 0;
-    bool by_barrier   = false;
+    unsigned parity   = 0;
+    bool by_bar       = false; // the slot is filled through the mbarrier (else it was copied with plain loads)
     if (g < ngroups)
-        by_barrier = mma_fetch_group<G, C::NM2>(slot, &bars[warp], in, g, nelmt, lane);
+        by_bar = mma_fetch_group<G, C::NM2>(slot, bar, in, g, nelmt, lane);
 
     for (; g < ngroups; g += nw)
     {
@@ -157,140 +513,114 @@ __global__ void __launch_bounds__(WARPS * 32)
         const int ne    = (nelmt - e0 < (size_t)G) ? (int)(nelmt - e0) : G;
         const double *s_in =
             slot + ((reinterpret_cast<uintptr_t>(in + e0 * C::NM2) & 15u) >> 3); // window offset of this group
-        if (by_barrier)
+        if (by_bar)
         {
-            mbar_wait(&bars[warp], phase);
-            phase ^= 1u;
+            mbar_wait(bar, parity);
+            parity ^= 1u; // the phase advances only when the fill went through the barrier
         }
-
-        // ---- direction 0: mid[(e,q)][i] ----------------------------------------------------
-        const int nrows = ne * NM;
-#pragma unroll 1
-        for (int mt = 0; mt < C::MT0; mt += MB0)
-        {
-            if (mt * 8 >= nrows)
-                break;
-            double acc[MB0][NT0][2];
-            const double *ap[MB0];
-#pragma unroll
-            for (int m = 0; m < MB0; ++m)
-            {
-                const int row = (mt + m) * 8 + r;
-                ap[m]         = s_in + (row < nrows ? row : nrows - 1) * NM + c;
-#pragma unroll
-                for (int n = 0; n < NT0; ++n)
-                    acc[m][n][0] = acc[m][n][1] = 0.0;
-            }
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks)
-            {
-                double a[MB0], b[NT0];
-#pragma unroll
-                for (int m = 0; m < MB0; ++m)
-                {
-                    a[m] = ap[m][4 * ks]; // over-reads at most 3 values past the row: still inside the slot
-                    if (4 * ks + 3 >= NM && 4 * ks + c >= NM)
-                        a[m] = 0.0;
-                }
-#pragma unroll
-                for (int n = 0; n < NT0; ++n)
-                    b[n] = frag0[(ks * NT0 + n) * 32 + lane];
-#pragma unroll
-                for (int m = 0; m < MB0; ++m)
-#pragma unroll
-                    for (int n = 0; n < NT0; ++n)
-                        dmma884(acc[m][n], a[m], b[n]);
-            }
-#pragma unroll
-            for (int m = 0; m < MB0; ++m)
-            {
-                const int row = (mt + m) * 8 + r;
-                if (row < nrows)
-                {
-                    double *mp = mid + row * S + 2 * c;
-#pragma unroll
-                    for (int n = 0; n < NT0; ++n)
-                        if (8 * n + 2 * c < NQ)
-                            *reinterpret_cast<double2 *>(mp + 8 * n) = make_double2(acc[m][n][0], acc[m][n][1]);
-                }
-            }
-        }
+        // direction 0: mid[(e,q)][i] = sum_p in[(e,q)][p] B0[p][i]
+        mma_dir_data<NQ, S, MB0, G * NM>(s_in, frag0, mid, ne * NM, lane);
         __syncwarp();
-
         // the slot is drained: start fetching this warp's next group under direction 1
         if (g + nw < ngroups)
-            by_barrier = mma_fetch_group<G, C::NM2>(slot, &bars[warp], in, g + nw, nelmt, lane);
-
-        // ---- direction 1: out[e][j][i] -----------------------------------------------------
-        const int ncols = ne * NQ;
-        double *gout    = out + e0 * C::NQ2;
-#pragma unroll 1
-        for (int nt = 0; nt < C::NT1; nt += NB1)
-        {
-            if (nt * 8 >= ncols)
-                break;
-            double acc[MT1][NB1][2];
-            const double *bp[NB1];
-#pragma unroll
-            for (int t = 0; t < NB1; ++t)
-            {
-                const int n  = (nt + t) * 8 + r;
-                const int nc = n < ncols ? n : ncols - 1;
-                const int e = nc / NQ, i = nc - e * NQ;
-                bp[t] = mid + (e * NM + c) * S + i;
-#pragma unroll
-                for (int m = 0; m < MT1; ++m)
-                    acc[m][t][0] = acc[m][t][1] = 0.0;
-            }
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks)
-            {
-                double a[MT1], b[NB1];
-#pragma unroll
-                for (int m = 0; m < MT1; ++m)
-                    a[m] = frag1[(m * KS + ks) * 32 + lane];
-#pragma unroll
-                for (int t = 0; t < NB1; ++t)
-                {
-                    if (4 * ks + 3 < NM)
-                        b[t] = bp[t][4 * ks * S];
-                    else
-                        b[t] = (4 * ks + c < NM) ? bp[t][4 * ks * S] : 0.0; // predicated: rows >= nm do not exist
-                }
-#pragma unroll
-                for (int m = 0; m < MT1; ++m)
-#pragma unroll
-                    for (int t = 0; t < NB1; ++t)
-                        dmma884(acc[m][t], a[m], b[t]);
-            }
-#pragma unroll
-            for (int t = 0; t < NB1; ++t)
-            {
-                const int n = (nt + t) * 8 + 2 * c;
-                if (n < ncols)
-                {
-                    const int e = n / NQ, i = n - e * NQ;
-                    double *op = gout + (size_t)e * C::NQ2 + i;
-#pragma unroll
-                    for (int m = 0; m < MT1; ++m)
-                    {
-                        const int j = 8 * m + r;
-                        if (j < NQ)
-                        {
-                            if (out_vec)
-                                st_stream(reinterpret_cast<double2 *>(op + j * NQ),
-                                          make_double2(acc[m][t][0], acc[m][t][1]));
-                            else
-                            {
-                                st_stream(op + j * NQ, acc[m][t][0]);
-                                st_stream(op + j * NQ + 1, acc[m][t][1]);
-                            }
-                        }
-                    }
-                }
-            }
-        }
+            by_bar = mma_fetch_group<G, C::NM2>(slot, bar, in, g + nw, nelmt, lane);
+        // direction 1: out[e][j][i] = sum_q B1[q][j] mid[e][q][i]
+        mma_dir_basis<NQ, NQ, S, C::NQ2, NQ, NB1, true, G * NQ>(mid, frag1, out + e0 * C::NQ2, ne * NQ, out_vec != 0,
+                                                               lane);
         __syncwarp(); // mid is rewritten by the next group's direction 0
+    }
+}
+
+// ============================== hex ===========================================
+
+// stride of the (e, r) rows of the second intermediate: >= nq^2, even, == 4 or 12 (mod 16)
+constexpr int mma_s2_stride(int nq)
+{
+    int s = nq * nq;
+    while (s % 16 != 4 && s % 16 != 12)
+        s += 2;
+    return s;
+}
+
+template <int NQ, int G, int WARPS, int MB0, int NB> struct HexMma
+{
+    static constexpr int NM   = NQ - 1;
+    static constexpr int NM2  = NM * NM;
+    static constexpr int NM3  = NM2 * NM;
+    static constexpr int NQ2  = NQ * NQ;
+    static constexpr int NQ3  = NQ2 * NQ;
+    static constexpr int KS   = (NM + 3) / 4;
+    static constexpr int NT   = (NQ + 7) / 8;
+    static constexpr int S1   = mma_mid_stride(NQ); // s1[(e,r,q)][i]
+    static constexpr int S2   = mma_s2_stride(NQ);  // s2[(e,r)][j*nq + i]
+    static constexpr int SLOT = (G * NM3 + 1 + 3 + 1) / 2 * 2;
+    static constexpr int MID1 = G * NM2 * S1;
+    static constexpr int MID2 = G * NM * S2;
+    static constexpr int WARP_D = SLOT + MID1 + MID2;
+    static constexpr int FRAG = KS * NT * 32;
+    static constexpr int BAR_BYTES = (WARPS * 8 + 15) / 16 * 16;
+    static constexpr size_t SMEM = BAR_BYTES + (size_t)(3 * FRAG + WARPS * WARP_D) * sizeof(double);
+    static_assert(NQ % 2 == 0, "the mma back-end pairs outputs along i");
+};
+
+template <int NQ, int G, int WARPS, int MB0, int NB>
+__global__ void __launch_bounds__(WARPS * 32)
+    bwdtrans_hex_mma_kernel(const double *__restrict__ basis0, const double *__restrict__ basis1,
+                            const double *__restrict__ basis2, const double *__restrict__ in, double *__restrict__ out,
+                            unsigned nelmt, unsigned ngroups, int out_vec)
+{
+    using C = HexMma<NQ, G, WARPS, MB0, NB>;
+    constexpr int NM = C::NM;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+    double *frag0  = reinterpret_cast<double *>(smem_raw + C::BAR_BYTES);
+    double *frag1  = frag0 + C::FRAG;
+    double *frag2  = frag1 + C::FRAG;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *slot  = frag2 + C::FRAG + warp * C::WARP_D;
+    double *s1    = slot + C::SLOT;
+    double *s2    = s1 + C::MID1;
+    uint64_t *bar = bars + warp;
+
+    mma_fill_fragB<NQ, WARPS * 32>(frag0, basis0);
+    mma_fill_fragA<NQ, WARPS * 32>(frag1, basis1);
+    mma_fill_fragA<NQ, WARPS * 32>(frag2, basis2);
+    if (lane == 0)
+    {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const unsigned nw = gridDim.x * WARPS;
+    unsigned g        = blockIdx.x * WARPS + warp;
+    unsigned parity   = 0;
+    bool by_bar       = false;
+    if (g < ngroups)
+        by_bar = mma_fetch_group<G, C::NM3>(slot, bar, in, g, nelmt, lane);
+
+    for (; g < ngroups; g += nw)
+    {
+        const size_t e0 = (size_t)g * G;
+        const int ne    = (nelmt - e0 < (size_t)G) ? (int)(nelmt - e0) : G;
+        const double *s_in = slot + ((reinterpret_cast<uintptr_t>(in + e0 * C::NM3) & 15u) >> 3);
+        if (by_bar)
+        {
+            mbar_wait(bar, parity);
+            parity ^= 1u;
+        }
+        // direction 0: s1[(e,r,q)][i] = sum_p in[(e,r,q)][p] B0[p][i]
+        mma_dir_data<NQ, C::S1, MB0, G * C::NM2>(s_in, frag0, s1, ne * C::NM2, lane);
+        __syncwarp();
+        if (g + nw < ngroups)
+            by_bar = mma_fetch_group<G, C::NM3>(slot, bar, in, g + nw, nelmt, lane);
+        // direction 1: s2[(e,r)][j][i] = sum_q B1[q][j] s1[(e,r)][q][i]
+        mma_dir_basis<NQ, NQ, C::S1, C::S2, NQ, NB, false, G * NM * NQ>(s1, frag1, s2, ne * NM * NQ, true, lane);
+        __syncwarp();
+        // direction 2: out[e][k][(j,i)] = sum_r B2[r][k] s2[e][r][(j,i)]
+        mma_dir_basis<NQ, C::NQ2, C::S2, C::NQ3, C::NQ2, NB, true, G * C::NQ2>(s2, frag2, out + e0 * C::NQ3,
+                                                                              ne * C::NQ2, out_vec != 0, lane);
+        __syncwarp(); // s1 / s2 are rewritten by the next group
     }
 }
 

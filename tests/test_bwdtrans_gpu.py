@@ -166,7 +166,7 @@ def test_quad_rows_and_pipe_backends_bit_exact(G, backend, nq, suf):
 
 
 @pytest.mark.parametrize("suf", ["f64", "f32"])
-@pytest.mark.parametrize("backend", ["rows", "pipe"])
+@pytest.mark.parametrize("backend", ["rows", "pipe", "mma"])
 @pytest.mark.parametrize("nq", [2, 4, 6, 8, 10])
 def test_hex_rows_and_pipe_backends_bit_exact(G, backend, nq, suf):
     dt, nm = G.NP[suf], nq - 1
@@ -179,8 +179,8 @@ def test_hex_rows_and_pipe_backends_bit_exact(G, backend, nq, suf):
         got = G.run_hex("BwdTransHexKernel_QP_Shared", suf, (nq, nq, nq), nelmt, b, inp)
         assert G.fe.last_backend() == backend
     except G.fe.B200feError as e:
-        assert e.code == G.fe.E_UNSUPPORTED and backend == "pipe"
-        pytest.skip(f"no pipe instantiation for hex nq={nq} {suf}")
+        assert e.code == G.fe.E_UNSUPPORTED and backend in ("pipe", "mma")
+        pytest.skip(f"no {backend} instantiation for hex nq={nq} {suf}")
     finally:
         G.fe.set_backend("auto")
     assert np.array_equal(got, oracle.bwdtrans_hex(nq, nq, nq, nelmt, *b, inp))
@@ -364,3 +364,27 @@ def test_quad_mma_non_finite_neighbours_do_not_leak(G):
     assert np.isfinite(got[ok]).all()
     assert np.array_equal(got[ok], want[ok])
     assert not np.isfinite(got[4]).any()
+
+
+@pytest.mark.parametrize("nq", [6, 8])
+@pytest.mark.parametrize("nelmt,shift", [(1, 0), (3, 1), (33, 1), (1001, 0)])
+def test_hex_mma_ragged_groups_and_8_byte_aligned_slabs(G, nq, nelmt, shift):
+    import torch
+    nm = nq - 1
+    rng = np.random.default_rng(600 + nq + nelmt)
+    b = [rnd(rng, nm * nq, np.float64) for _ in range(3)]
+    inp = rnd(rng, nelmt * nm ** 3, np.float64)
+    big_in = torch.full((inp.size + 2,), float("nan"), dtype=torch.float64, device="cuda")
+    big_in[shift:shift + inp.size] = torch.from_numpy(inp).cuda()
+    big_out = torch.full((nelmt * nq ** 3 + 2,), float("nan"), dtype=torch.float64, device="cuda")
+    d_b = [G.dev(x) for x in b]
+    try:
+        G.fe.set_backend("mma")
+        G.fe.bwdtrans_hex("BwdTransHexKernel_QP_Shared", "f64", nq, nq, nq, nelmt, d_b[0].data_ptr(), d_b[1].data_ptr(),
+                          d_b[2].data_ptr(), big_in.data_ptr() + 8 * shift, big_out.data_ptr() + 8 * shift)
+        assert G.fe.last_backend() == "mma"
+    finally:
+        G.fe.set_backend("auto")
+    got = G.host(big_out)
+    assert np.array_equal(got[shift:shift + nelmt * nq ** 3], oracle.bwdtrans_hex(nq, nq, nq, nelmt, *b, inp))
+    assert np.isnan(got[:shift]).all() and np.isnan(got[shift + nelmt * nq ** 3:]).all()

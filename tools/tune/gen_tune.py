@@ -78,19 +78,33 @@ def mma_smem(nq, g, warps):
     return (warps * 8 + 15) // 16 * 16 + 8 * (2 * ks * nt * 32 + warps * (slot + g * nm * s))
 
 
-def mma_configs(nq):
-    """FP64 quad tensor-core back-end: (G elements per warp, warps per CTA, MB0, NB1)"""
+def mma_smem3(nq, g, warps):
+    """HexMma<NQ, G, WARPS, ..>::SMEM of sumfac_mma.cuh"""
+    nm = nq - 1
+    ks, nt = (nm + 3) // 4, (nq + 7) // 8
+    s1 = nq + (nq & 1)
+    while s1 % 16 not in (4, 12):
+        s1 += 2
+    s2 = nq * nq
+    while s2 % 16 not in (4, 12):
+        s2 += 2
+    slot = (g * nm ** 3 + 5) // 2 * 2
+    return (warps * 8 + 15) // 16 * 16 + 8 * (3 * ks * nt * 32 + warps * (slot + g * nm * nm * s1 + g * nm * s2))
+
+
+def mma_configs(nq, dim=2):
+    """FP64 tensor-core back-end: (G elements per warp, warps per CTA, MB0, NB1)"""
     out = []
     nt = (nq + 7) // 8
     for g in (1, 2, 4, 8):
         for warps in (4, 8):
-            if mma_smem(nq, g, warps) > SMEM_MAX:
+            if (mma_smem(nq, g, warps) if dim == 2 else mma_smem3(nq, g, warps)) > SMEM_MAX:
                 continue
             for mb0 in (1, 2, 4):
-                if mb0 * nt > 8 or (mb0 - 1) * 8 >= g * (nq - 1):
+                if mb0 * nt > 8 or (mb0 - 1) * 8 >= g * (nq - 1) ** (dim - 1):
                     continue
                 for nb1 in (1, 2, 4):
-                    if nb1 * nt > 8 or (nb1 - 1) * 8 >= g * nq:
+                    if nb1 * nt > 8 or (nb1 - 1) * 8 >= g * nq * (nq - 1) ** (dim - 2):
                         continue
                     out.append(("mma", g, warps * 32, mb0, nb1))
     return out
@@ -109,7 +123,7 @@ def main():
         dim, nq = int(dim), int(nq)
         cfgs = configs(dim, tag, nq)
         if "--mma" in sys.argv:
-            cfgs = cfgs[:1] + (mma_configs(nq) if dim == 2 and tag == "f64" and nq % 2 == 0 else [])
+            cfgs = cfgs[:1] + (mma_configs(nq, dim) if tag == "f64" and nq % 2 == 0 else [])
         name = f"{dim}_{tag}_{nq}"
         with open(os.path.join(BUILD, f"cfg_{name}.inc"), "w") as f:
             for be, e, th, r, v in cfgs:

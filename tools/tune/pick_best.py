@@ -45,7 +45,8 @@ for dim in (2, 3):
                 if entry[k + "_frac"] >= merged.get(k + "_frac", 0):
                     merged[k], merged[k + "_frac"] = v, entry[k + "_frac"]
             fr = {b: merged.get(b + "_frac", 0) for b in ("rows", "pipe", "mma") if b in merged}
-            merged["prefer"] = max(fr, key=fr.get).capitalize() if fr else "Rows"
+            if not merged.get("prefer_locked"):  # a hand-set preference (see "why") survives re-tuning
+                merged["prefer"] = max(fr, key=fr.get).capitalize() if fr else "Rows"
             over[f"{dim}:{dt}:{nq}"] = merged
             print(f"{dim}:{dt}:{nq:<5d} {cells[0]:34s} {cells[1]:34s} {cells[2]:34s} -> {merged['prefer']}")
 if "--write" in sys.argv:

@@ -52,7 +52,19 @@ struct Cfg
      (const void *)bwdtrans_hex_pipe_kernel<T, NQ, E, TH, R, V>},
 #endif
 // mma (FP64 quads only): E = elements per warp group, TH = 32 * warps, R = MB0, V = NB1
-static const double *g_b0 = nullptr, *g_b1 = nullptr;
+static const double *g_b0 = nullptr, *g_b1 = nullptr, *g_b2 = nullptr;
+#if TUNE_DIM == 3
+template <int G, int W, int MB0, int NB> int mma_wrap(unsigned nelmt, const T *in, T *out, cudaStream_t s)
+{
+    if constexpr (sizeof(T) == 8)
+        return launch_hex_mma<NQ, G, W, MB0, NB>(nelmt, g_b0, g_b1, g_b2, (const double *)in, (double *)out, s);
+    else
+        return -2;
+}
+#define CFG_mma(E, TH, R, V)                                                                                 \
+    {"mma", E, TH, R, V, &mma_wrap<E, TH / 32, R, V>, HexMma<NQ, E, TH / 32, R, V>::SMEM,                      \
+     (const void *)bwdtrans_hex_mma_kernel<NQ, E, TH / 32, R, V>},
+#endif
 #if TUNE_DIM == 2
 template <int G, int W, int MB0, int NB1> int mma_wrap(unsigned nelmt, const T *in, T *out, cudaStream_t s)
 {
@@ -118,7 +130,8 @@ int main(int argc, char **argv)
 {
     const double peak = argc > 1 ? atof(argv[1]) : 6546.9;
     const int reps    = argc > 2 ? atoi(argv[2]) : 9;
-    size_t nelmt      = ((size_t)1 << 26) / NQTOT / 32 * 32;
+    const int mult    = argc > 3 ? atoi(argv[3]) : 1; // workload = mult * 64 Mi quadrature points
+    size_t nelmt      = (size_t)mult * (((size_t)1 << 26) / NQTOT / 32 * 32);
     if (nelmt < 32)
         nelmt = 32;
     const char *tname = sizeof(T) == 8 ? "f64" : "f32";
@@ -133,6 +146,7 @@ int main(int argc, char **argv)
     CK(cudaMalloc(&d_md, 2 * sizeof(unsigned long long)));
     g_b0 = (const double *)d_basis;
     g_b1 = (const double *)(d_basis + NM * NQ);
+    g_b2 = (const double *)(d_basis + (DIM - 1) * NM * NQ);
     fill_kernel<<<148 * 8, 256>>>(d_in, nelmt * NMTOT, NMTOT);
     std::vector<T> hb(DIM * NM * NQ);
     for (size_t k = 0; k < hb.size(); ++k)
@@ -184,6 +198,15 @@ int main(int argc, char **argv)
             cudaEventRecord(e1);
             cudaEventSynchronize(e1);
             cudaEventElapsedTime(&ms[r], e0, e1);
+        }
+        if (reps >= 100) // sustained-load view: does the configuration hold its rate once the power cap bites?
+        {
+            double first = 0, last = 0;
+            for (int r = 0; r < 10; ++r)
+                first += ms[r] / 10, last += ms[reps - 1 - r] / 10;
+            std::fprintf(stderr, "# sustained %s E=%d TH=%d R=%d V=%d: first10 %.4f ms, last10 %.4f ms (%.3f -> %.3f of peak)\n",
+                         c.be, c.E, c.TH, c.R, c.V, first, last, 1e-9 * bytes / (first * 1e-3) / peak,
+                         1e-9 * bytes / (last * 1e-3) / peak);
         }
         std::sort(ms.begin(), ms.end());
         unsigned long long bad = 0;
