@@ -236,7 +236,7 @@ def sweep(fe, torch, oracle, peak, reps=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-sweep", action="store_true", help="skip the per-operator sweep (extra key `sweep`)")
@@ -379,9 +379,9 @@ def main():
     bytes_per_launch = nelmt * alg_bytes_per_elem(3, NQ, 8)
     achieved = 1e-9 * bytes_per_launch / (kern_ms * 1e-3)
     traffic = None
-    try:
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
         with open(os.path.join(ROOT, "profiles", "dram_traffic.json")) as f:
-            traffic = json.load(f).get("hex8_f64_bytes_per_launch")
+            traffic = json.load(f).get(f"hex8_f64_{backend}", {}).get("bytes_per_launch")
     except Exception:
         pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
