@@ -7,6 +7,7 @@
 #include "dispatch.h"
 #include "sumfac_generic.cuh"
 #include "sumfac_mma.cuh"
+#include "sumfac_mma32.cuh"
 #include "sumfac_rows.cuh"
 #include "sumfac_tpe.cuh"
 
@@ -120,6 +121,28 @@ int launch_quad_mma(unsigned nelmt, const double *b0, const double *b1, const do
     const unsigned fit     = (unsigned)(sm_count() * ctas_per_sm(kernel, WARPS * 32, C::SMEM, occ));
     const unsigned grid    = need < fit ? need : fit;
     const int out_vec      = aligned16(out);
+    kernel<<<grid, WARPS * 32, C::SMEM, stream>>>(b0, b1, in, out, nelmt, ngroups, out_vec);
+    count_launch();
+    t_last_backend = "mma";
+    return launch_status();
+}
+
+// FP32 twin: 3xTF32 split on the warp-level tensor-core path
+template <int NQ, int G, int WARPS, int MB0, int NB1>
+int launch_quad_mma(unsigned nelmt, const float *b0, const float *b1, const float *in, float *out, cudaStream_t stream)
+{
+    using C = QuadMma32<NQ, G, WARPS, MB0, NB1>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "warp regions do not fit shared memory");
+    static int occ[64] = {};
+    auto kernel        = bwdtrans_quad_mma32_kernel<NQ, G, WARPS, MB0, NB1>;
+    int rc             = opt_in_smem(kernel, C::SMEM);
+    if (rc)
+        return rc;
+    const unsigned ngroups = (nelmt + G - 1) / G;
+    const unsigned need    = (ngroups + WARPS - 1) / WARPS;
+    const unsigned fit     = (unsigned)(sm_count() * ctas_per_sm(kernel, WARPS * 32, C::SMEM, occ));
+    const unsigned grid    = need < fit ? need : fit;
+    const int out_vec      = (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
     kernel<<<grid, WARPS * 32, C::SMEM, stream>>>(b0, b1, in, out, nelmt, ngroups, out_vec);
     count_launch();
     t_last_backend = "mma";

@@ -48,3 +48,14 @@ def run_hex(kernel, suf, nq, nelmt, b, inp, nm=None):
                     d_in.data_ptr(), d_out.data_ptr(), wsp0=d_w0.data_ptr(), wsp1=d_w1.data_ptr(),
                     stream=torch.cuda.current_stream().cuda_stream, nm=nm)
     return host(d_out)
+
+
+def assert_parity(got, want, suf, what=""):
+    """Bit for bit with the oracle / the reference kernels -- every back-end accumulates in the reference's own
+    order with fused multiply-adds -- except the FP32 tensor-core back-end (3xTF32 split), which agrees to
+    rounding and is held to north_star's FP32 tolerance."""
+    if suf == "f32" and fe.last_backend() == "mma":
+        err = rel_max(got, want)
+        assert err < TOL["f32"], (what, "mma f32", err)
+    else:
+        assert np.array_equal(got, want), (what, fe.last_backend(), rel_max(got, want))

@@ -49,7 +49,7 @@ def test_quad_every_nq_bit_exact(G, suf, nq):
         want = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp, use_fma=True)
         got = G.run_quad("BwdTransQuadKernel_QP_Shared", suf, nq, nq, nelmt, b0, b1, inp)
         assert G.fe.last_backend() in ("rows", "pipe", "mma")
-        assert np.array_equal(got, want), (nq, nelmt, G.rel_max(got, want))
+        G.assert_parity(got, want, suf, (nq, nelmt))
         plain = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp, use_fma=False)
         assert G.rel_max(got, plain) < G.TOL[suf]
 
@@ -78,7 +78,7 @@ def test_quad_all_element_major_entry_points(G, suf, kernel, nq):
     b0, b1 = rnd(rng, nm * nq, dt), rnd(rng, nm * nq, dt)
     inp = rnd(rng, nelmt * nm * nm, dt)
     want = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp)
-    assert np.array_equal(G.run_quad(kernel, suf, nq, nq, nelmt, b0, b1, inp), want)
+    G.assert_parity(G.run_quad(kernel, suf, nq, nq, nelmt, b0, b1, inp), want, suf, (kernel, nq))
 
 
 @pytest.mark.parametrize("suf", ["f64", "f32"])
@@ -146,8 +146,9 @@ def test_generic_backend_handles_unequal_and_non_nm_shapes(G, suf):
 @pytest.mark.parametrize("nq", [2, 4, 6, 8, 10, 12, 14, 16, 32])
 def test_quad_rows_and_pipe_backends_bit_exact(G, backend, nq, suf):
     """every tiled back-end for every tuned nq: many tiles per persistent CTA (the ring wraps), ragged last tile.
-    mma (FP64 tensor cores) is held to the same bit-for-bit bar: DMMA m8n8k4 on sm_100 accumulates its four
-    products in k order with fused multiply-adds, i.e. the reference's own summation order."""
+    mma on FP64 (DMMA m8n8k4) is held to the same bit-for-bit bar: on sm_100 it accumulates its four products
+    in k order with fused multiply-adds, i.e. the reference's own summation order.  mma on FP32 is the 3xTF32
+    split: 1e-5 relative (G.assert_parity)."""
     dt, nm = G.NP[suf], nq - 1
     nelmt = 40013 if nq <= 16 else 3001
     rng = np.random.default_rng(300 + nq)
@@ -162,7 +163,7 @@ def test_quad_rows_and_pipe_backends_bit_exact(G, backend, nq, suf):
         pytest.skip(f"no {backend} instantiation for quad nq={nq} {suf}")
     finally:
         G.fe.set_backend("auto")
-    assert np.array_equal(got, oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp))
+    G.assert_parity(got, oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp), suf, (backend, nq))
 
 
 @pytest.mark.parametrize("suf", ["f64", "f32"])
@@ -388,3 +389,32 @@ def test_hex_mma_ragged_groups_and_8_byte_aligned_slabs(G, nq, nelmt, shift):
     got = G.host(big_out)
     assert np.array_equal(got[shift:shift + nelmt * nq ** 3], oracle.bwdtrans_hex(nq, nq, nq, nelmt, *b, inp))
     assert np.isnan(got[:shift]).all() and np.isnan(got[shift + nelmt * nq ** 3:]).all()
+
+
+@pytest.mark.parametrize("nq", [16, 32])
+@pytest.mark.parametrize("nelmt,shift", [(1, 0), (5, 1), (5, 3), (64, 2), (1001, 1)])
+def test_quad_mma_f32_accuracy_ragged_groups_and_4_byte_aligned_slabs(G, nq, nelmt, shift):
+    """FP32 tensor-core back-end (3xTF32): error budget, partial last group, slabs at any 4-byte offset"""
+    import torch
+    nm = nq - 1
+    rng = np.random.default_rng(700 + nq + nelmt)
+    b0, b1 = rnd(rng, nm * nq, np.float32), rnd(rng, nm * nq, np.float32)
+    inp = rnd(rng, nelmt * nm * nm, np.float32)
+    big_in = torch.full((inp.size + 4,), float("nan"), dtype=torch.float32, device="cuda")
+    big_in[shift:shift + inp.size] = torch.from_numpy(inp).cuda()
+    big_out = torch.full((nelmt * nq * nq + 4,), float("nan"), dtype=torch.float32, device="cuda")
+    d_b0, d_b1 = G.dev(b0), G.dev(b1)
+    try:
+        G.fe.set_backend("mma")
+        G.fe.bwdtrans_quad("BwdTransQuadKernel_QP_Shared", "f32", nq, nq, nelmt, d_b0.data_ptr(), d_b1.data_ptr(),
+                           big_in.data_ptr() + 4 * shift, big_out.data_ptr() + 4 * shift)
+        assert G.fe.last_backend() == "mma"
+    finally:
+        G.fe.set_backend("auto")
+    got = G.host(big_out)
+    want = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp)
+    exact = oracle.bwdtrans_quad(nq, nq, nelmt, b0.astype(np.float64), b1.astype(np.float64), inp.astype(np.float64))
+    body = got[shift:shift + nelmt * nq * nq]
+    assert G.rel_max(body, want) < 1e-5                       # vs the reference's FP32 arithmetic: north_star bar
+    assert G.rel_max(body, exact) < 2 * max(G.rel_max(want, exact), 1e-6)  # vs exact: no worse than ~2x the FFMA chain
+    assert np.isnan(got[:shift]).all() and np.isnan(got[shift + nelmt * nq * nq:]).all()

