@@ -5,7 +5,7 @@ HOSTCXX := $(shell [ -x /usr/bin/g++ ] && echo /usr/bin/g++ || echo g++)
 CUDA    ?= /usr/local/cuda
 CXXFLAGS := -O3 -std=c++17 -fopenmp -march=x86-64-v3 -Wall -I$(CUDA)/include
 LIBDIR  := gpu-benchmarking_b200
-LDFLAGS := -L$(LIBDIR) -lb200fe -L$(CUDA)/lib64 -lcudart -lcublas -Wl,-rpath,'$$ORIGIN/../../$(LIBDIR)' -Wl,-rpath,$(CUDA)/lib64
+LDFLAGS := -L$(LIBDIR) -lb200fe -L$(CUDA)/lib64 -lcudart -lcublas -lnccl -lpthread -Wl,-rpath,'$$ORIGIN/../../$(LIBDIR)' -Wl,-rpath,$(CUDA)/lib64
 BENCH   := 01 02 03 04 05
 DRIVERS := $(foreach b,$(BENCH),benchmark$(b)/build/benchmark$(b))
 HDRS    := $(wildcard utils/*.h) include/b200fe.h

@@ -22,6 +22,7 @@
 #include "../utils/bench_common.h"
 #include "../utils/cpu_reference.h"
 #include "../utils/cublas_compare.h"
+#include "../utils/multi_gpu.h"
 
 using namespace bench;
 
@@ -185,6 +186,108 @@ void run_test(const unsigned nelmt, const unsigned nq0, const unsigned nq1, cons
     std::cout << " | host threads " << host_threads() << std::endl << std::flush;
 }
 
+// B200FE_NGPUS > 1: the element range is sharded over the GPUs (one host thread each); the six Cuda columns
+// report whole-job throughput (slowest GPU), the norm is all-reduced with NCCL.  Host / cuBLAS columns: 0.
+template <typename T> void run_test_multi(MultiGpu &mg, const unsigned nelmt, const unsigned nq0, const unsigned nq1)
+{
+    const unsigned nm0 = nq0 - 1u, nm1 = nq1 - 1u;
+    const size_t nmTot = (size_t)nm0 * nm1, nqTot = (size_t)nq0 * nq1;
+    const unsigned reps = (unsigned)env_long("B200FE_REPS", 40);
+    constexpr int kCols = 11;
+    double secs[kCols], sumsq[kCols];
+    std::fill(secs, secs + kCols, std::numeric_limits<double>::infinity());
+    std::fill(sumsq, sumsq + kCols, 0.0);
+    bool all32 = true; // the interleaved layout needs every shard to hold whole groups of 32
+    for (int r = 0; r < mg.size(); ++r)
+    {
+        size_t b, e;
+        shard_range(nelmt, r, mg.size(), 32, &b, &e);
+        all32 = all32 && ((e - b) % 32u == 0);
+    }
+
+    mg.run([&](int rank) {
+        size_t e_begin, e_end;
+        shard_range(nelmt, rank, mg.size(), 32, &e_begin, &e_end);
+        const unsigned n = (unsigned)(e_end - e_begin);
+        // every element carries the same modes, so a shard's input does not depend on its position
+        std::vector<T> h_in(n * nmTot), h_in_coa(n * nmTot), h_b0((size_t)nm0 * nq0), h_b1((size_t)nm1 * nq1);
+        for (size_t e = 0; e < n; ++e)
+            for (size_t k = 0; k < nmTot; ++k)
+            {
+                const T v = std::sin((T)(k + 1u));
+                h_in[e * nmTot + k] = v;
+                if (n % 32u == 0)
+                    h_in_coa[cpuref::at(cpuref::Layout::Interleaved, e, k, nmTot)] = v;
+            }
+        for (size_t k = 0; k < h_b0.size(); ++k)
+            h_b0[k] = std::cos((T)k);
+        for (size_t k = 0; k < h_b1.size(); ++k)
+            h_b1[k] = std::cos((T)k);
+        DeviceArray<T> d_in(n * nmTot), d_in_coa(n * nmTot), d_out(n * nqTot), d_b0(h_b0.size()), d_b1(h_b1.size()),
+            d_wsp((size_t)n * nq0 * nm1);
+        if (n)
+        {
+            d_in.upload(h_in);
+            d_in_coa.upload(h_in_coa);
+        }
+        d_b0.upload(h_b0);
+        d_b1.upload(h_b1);
+        Checksum<T> checksum;
+
+        using A = Api<T>;
+        auto with_wsp = [&](auto fn, const T *in) {
+            FE_OK(fn(nm0, nm1, (unsigned)nmTot, nq0, nq1, n, d_b0.get(), d_b1.get(), in, d_wsp.get(), d_out.get(),
+                     nullptr));
+        };
+        auto no_wsp = [&](auto fn) {
+            FE_OK(fn(nm0, nm1, (unsigned)nmTot, nq0, nq1, n, d_b0.get(), d_b1.get(), d_in.get(), d_out.get(), nullptr));
+        };
+        auto column = [&](int col, auto &&launch) {
+            if (n)
+                d_out.zero();
+            const double t = mg.time_min(rank, reps, [&] {
+                if (n)
+                    launch();
+            });
+            checksum.launch(d_out.get(), n ? d_out.size() : 0);
+            const double total = mg.allreduce_sum(rank, checksum.result.get()); // NCCL: one double
+            if (rank == 0)
+            {
+                secs[col]  = t;
+                sumsq[col] = total;
+            }
+        };
+        column(5, [&] { with_wsp(A::uncoa, d_in.get()); });
+        if (all32)
+            column(6, [&] { with_wsp(A::coa, d_in_coa.get()); });
+        column(7, [&] { with_wsp(A::qp, d_in.get()); });
+        column(8, [&] { no_wsp(A::qpsh); });
+        column(9, [&] { with_wsp(A::q1d, d_in.get()); });
+        column(10, [&] { no_wsp(A::q1dsh); });
+    });
+
+    std::cout << std::setprecision(10);
+    std::cout << "nelmt " << nelmt
+              << " Case: Kokkos (Uncoales) Kokkos (Coales) Kokkos (QP)   Kokkos (QP/Shared) cuBLAS          Cuda "
+                 "(Uncoales) Cuda (Coales)    Cuda (QP)      Cuda (QP/Shared)  Cuda (QP-1D)   Cuda (QP-1D/Shared)"
+              << std::endl;
+    std::cout << "nelmt " << nelmt << " norm:";
+    for (int c = 0; c < kCols; ++c)
+        std::cout << (c ? "     " : " ") << std::sqrt(sumsq[c]);
+    std::cout << std::endl;
+    const double dof = 1.0e-9 * (double)nelmt * (double)nmTot;
+    std::cout << "nelmt " << nelmt << " DOF/s:";
+    for (int c = 0; c < kCols; ++c)
+        std::cout << (c ? "     " : " ") << dof / secs[c];
+    std::cout << std::endl;
+    const double gb = 1.0e-9 * (double)nelmt * (double)sizeof(T) * (double)(nmTot + nqTot);
+    std::cout << "info " << nelmt << " " << Api<T>::name << " gpus " << mg.size() << " aggregate HBM% of "
+              << mg.size() << " x " << hbm_peak_gbs() << " GB/s, columns 6-11:";
+    for (int c = 5; c < kCols; ++c)
+        std::cout << " " << std::setprecision(4) << 100.0 * gb / secs[c] / (hbm_peak_gbs() * mg.size());
+    std::cout << std::endl << std::flush;
+}
+
 } // namespace
 
 int main(int argc, char **argv)
@@ -211,6 +314,20 @@ int main(int argc, char **argv)
         for (unsigned size = 2 << 6; size < 2 << 20; size <<= 1)
             sizes.push_back(size);
     const std::string dtype = env_str("B200FE_DTYPE", "double");
+    const int ngpus = (int)env_long("B200FE_NGPUS", 1);
+    if (ngpus > 1)
+    {
+        MultiGpu mg(ngpus);
+        std::cout << "info sharded over " << ngpus << " GPUs, NCCL scalar all-reduce of the norm only" << std::endl;
+        for (unsigned size : sizes)
+        {
+            if (dtype != "float")
+                run_test_multi<double>(mg, size, nq0, nq1);
+            if (dtype == "float" || dtype == "both")
+                run_test_multi<float>(mg, size, nq0, nq1);
+        }
+        return 0;
+    }
     for (unsigned size : sizes)
     {
         if (dtype != "float")

@@ -182,6 +182,8 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
             be = Backend::Generic;
         else if (coa)
             be = nq0 <= kHexTpeMaxNq ? Backend::Tpe : Backend::Generic;
+        else if (nq0 == 2)
+            be = Backend::Nm1;
         else
             be = preferred;
         // the bulk-copy ring needs a 16-byte aligned slab; otherwise take the plain-load twin
@@ -197,11 +199,13 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
         t_last_backend = "generic";
         return launch_hex_generic<T>(nm0, nm1, nm2, nq0, nq1, nq2, nelmt, b0, b1, b2, in, out, coa, stream);
     }
-    if (!regular || ((be == Backend::Rows || be == Backend::Pipe || be == Backend::Mma) && coa) ||
+    if (!regular || ((be == Backend::Rows || be == Backend::Pipe || be == Backend::Mma || be == Backend::Nm1) && coa) ||
         (be == Backend::Tpe && !coa))
         return B200FE_EUNSUPPORTED;
     if (be == Backend::Pipe && (!(have & 2) || !aligned16(in)))
         return B200FE_EUNSUPPORTED;
+    if (be == Backend::Nm1)
+        return (nq0 == 2 && !coa) ? launch_nm1<T, 3>(nelmt, b0, b1, b2, in, out, stream) : B200FE_EUNSUPPORTED;
     if (be == Backend::Mma) // reads the basis matrices from global memory: no constant bank, no lock
         return (have & 4) ? hex_mma_switch(nq0, nelmt, b0, b1, b2, in, out, stream) : B200FE_EUNSUPPORTED;
 

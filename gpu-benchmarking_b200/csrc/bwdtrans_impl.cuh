@@ -8,6 +8,7 @@
 #include "sumfac_generic.cuh"
 #include "sumfac_mma.cuh"
 #include "sumfac_mma32.cuh"
+#include "sumfac_nm1.cuh"
 #include "sumfac_rows.cuh"
 #include "sumfac_tpe.cuh"
 

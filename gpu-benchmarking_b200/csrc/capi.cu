@@ -283,6 +283,8 @@ int b200fe_set_backend(const char *name)
         g_forced_backend = (int)Backend::Pipe;
     else if (!strcmp(name, "mma"))
         g_forced_backend = (int)Backend::Mma;
+    else if (!strcmp(name, "nm1"))
+        g_forced_backend = (int)Backend::Nm1;
     else if (!strcmp(name, "tpe"))
         g_forced_backend = (int)Backend::Tpe;
     else if (!strcmp(name, "generic"))

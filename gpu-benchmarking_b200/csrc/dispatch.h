@@ -14,6 +14,7 @@ enum class Backend : int
     Tpe     = 2, // thread per element, registers only (interleaved layout)
     Generic = 3, // run-time sizes, any shape
     Pipe    = 4, // rows + persistent CTAs fed by bulk (TMA) copies through an mbarrier ring
+    Nm1     = 6, // nq = 2: scaled broadcast, one thread per 16-byte output chunk, no basis staging
     Mma     = 5, // FP64 tensor cores (DMMA m8n8k4), one element group per warp, bulk (TMA) fed (quad, even nq)
 };
 

@@ -305,17 +305,23 @@ __global__ void __launch_bounds__(256)
                 const unsigned nv = N / W;
                 const V *av       = reinterpret_cast<const V *>(a);
                 const V *xv       = reinterpret_cast<const V *>(x);
-                V acc0 = vzero<V>(), acc1 = vzero<V>();
+                // four independent 16-byte loads of A in flight per thread (the row is streamed exactly once)
+                V acc0 = vzero<V>(), acc1 = vzero<V>(), acc2 = vzero<V>(), acc3 = vzero<V>();
                 unsigned t = lane;
-                for (; t + LANES < nv; t += 2 * LANES)
+                for (; t + 3 * LANES < nv; t += 4 * LANES)
                 {
                     const V a0 = ld_stream(av + t), a1 = ld_stream(av + t + LANES);
+                    const V a2 = ld_stream(av + t + 2 * LANES), a3 = ld_stream(av + t + 3 * LANES);
                     dot_acc(acc0, a0, __ldg(xv + t));
                     dot_acc(acc1, a1, __ldg(xv + t + LANES));
+                    dot_acc(acc2, a2, __ldg(xv + t + 2 * LANES));
+                    dot_acc(acc3, a3, __ldg(xv + t + 3 * LANES));
                 }
                 for (; t < nv; t += LANES)
                     dot_acc(acc0, ld_stream(av + t), __ldg(xv + t));
                 add_acc(acc0, acc1);
+                add_acc(acc2, acc3);
+                add_acc(acc0, acc2);
                 v = hsum(acc0);
             }
             else

@@ -48,7 +48,7 @@ def test_quad_every_nq_bit_exact(G, suf, nq):
         inp = rnd(rng, nelmt * nm * nm, dt)
         want = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp, use_fma=True)
         got = G.run_quad("BwdTransQuadKernel_QP_Shared", suf, nq, nq, nelmt, b0, b1, inp)
-        assert G.fe.last_backend() in ("rows", "pipe", "mma")
+        assert G.fe.last_backend() in ("rows", "pipe", "mma", "nm1")
         G.assert_parity(got, want, suf, (nq, nelmt))
         plain = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp, use_fma=False)
         assert G.rel_max(got, plain) < G.TOL[suf]
@@ -418,3 +418,35 @@ def test_quad_mma_f32_accuracy_ragged_groups_and_4_byte_aligned_slabs(G, nq, nel
     assert G.rel_max(body, want) < 1e-5                       # vs the reference's FP32 arithmetic: north_star bar
     assert G.rel_max(body, exact) < 2 * max(G.rel_max(want, exact), 1e-6)  # vs exact: no worse than ~2x the FFMA chain
     assert np.isnan(got[:shift]).all() and np.isnan(got[shift + nelmt * nq * nq:]).all()
+
+
+@pytest.mark.parametrize("suf", ["f64", "f32"])
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("nelmt,shift", [(1, 0), (33, 1), (100003, 0), (100003, 1)])
+def test_nq2_broadcast_kernel_bit_exact_including_signed_zeros(G, suf, dim, nelmt, shift):
+    """nq = 2 routes to the nm1 back-end; zeros of either sign and misaligned output slabs"""
+    import torch
+    dt = G.NP[suf]
+    tdt = torch.float64 if suf == "f64" else torch.float32
+    rng = np.random.default_rng(800 + nelmt)
+    b = [rnd(rng, 2, dt) for _ in range(3)]
+    b[1][0] = -0.0
+    inp = rnd(rng, nelmt, dt)
+    inp[::7] = 0.0
+    inp[3::11] = -0.0
+    nout = 2 ** dim
+    big_out = torch.full((nelmt * nout + 4,), float("nan"), dtype=tdt, device="cuda")
+    d_b, d_in = [G.dev(x) for x in b], G.dev(inp)
+    isz = big_out.element_size()
+    if dim == 2:
+        G.fe.bwdtrans_quad("BwdTransQuadKernel_QP", suf, 2, 2, nelmt, d_b[0].data_ptr(), d_b[1].data_ptr(),
+                           d_in.data_ptr(), big_out.data_ptr() + isz * shift)
+        want = oracle.bwdtrans_quad(2, 2, nelmt, b[0], b[1], inp)
+    else:
+        G.fe.bwdtrans_hex("BwdTransHexKernel_QP", suf, 2, 2, 2, nelmt, d_b[0].data_ptr(), d_b[1].data_ptr(),
+                          d_b[2].data_ptr(), d_in.data_ptr(), big_out.data_ptr() + isz * shift)
+        want = oracle.bwdtrans_hex(2, 2, 2, nelmt, b[0], b[1], b[2], inp)
+    assert G.fe.last_backend() == "nm1"
+    got = G.host(big_out)[shift:shift + nelmt * nout]
+    assert np.array_equal(got, want)
+    assert np.array_equal(np.signbit(got), np.signbit(want))

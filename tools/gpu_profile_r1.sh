@@ -14,13 +14,10 @@ python bench.py --steps 5 --warmup 3 --no-sweep --no-cpu > gpurun_out/plain_benc
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench.csv \
     python bench.py --steps 5 --warmup 3 --no-sweep --no-cpu > gpurun_out/ncu_bench.log 2>&1
 echo "launch list rc=$?"
-B200FE_NELMT=262144 prof hex8_f64 bwdtrans_hex_ benchmark05/build/benchmark05 8 8 8
-B200FE_NELMT=131072 B200FE_DTYPE=float prof hex8_f32 bwdtrans_hex_ benchmark05/build/benchmark05 8 8 8
+B200FE_NELMT=262144 prof hex8_f64_mma bwdtrans_hex_ benchmark05/build/benchmark05 8 8 8
+B200FE_NELMT=262144 prof quad16_f64_mma bwdtrans_quad_ benchmark04/build/benchmark04 16 16
+B200FE_NELMT=65536 prof quad32_f64_mma bwdtrans_quad_ benchmark04/build/benchmark04 32 32
+B200FE_NELMT=65536 B200FE_DTYPE=float prof quad32_f32_mma bwdtrans_quad_ benchmark04/build/benchmark04 32 32
 B200FE_NELMT=67104 prof hex10_f64 bwdtrans_hex_ benchmark05/build/benchmark05 10 10 10
-B200FE_NELMT=4194304 prof quad4_f64 bwdtrans_quad_ benchmark04/build/benchmark04 4 4
-B200FE_NELMT=342368 prof quad14_f64 bwdtrans_quad_ benchmark04/build/benchmark04 14 14
-B200FE_NELMT=262144 prof quad16_f64 bwdtrans_quad_ benchmark04/build/benchmark04 16 16
-B200FE_NELMT=262144 B200FE_DTYPE=float prof quad16_f32 bwdtrans_quad_ benchmark04/build/benchmark04 16 16
-B200FE_NELMT=65536 prof quad32_f64 bwdtrans_quad_ benchmark04/build/benchmark04 32 32
-B200FE_NELMT=65536 B200FE_DTYPE=float prof quad32_f32 bwdtrans_quad_ benchmark04/build/benchmark04 32 32
+B200FE_NELMT=67104 B200FE_DTYPE=float prof hex10_f32 bwdtrans_hex_ benchmark05/build/benchmark05 10 10 10
 ls -la gpurun_out

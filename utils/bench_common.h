@@ -166,12 +166,22 @@ template <typename T> struct Checksum
 {
     DeviceArray<double> result{1};
     DeviceArray<unsigned char> scratch{b200fe_sumsq_scratch_bytes()};
-    double operator()(const T *x, size_t n)
+    // leaves sum(x^2) in *result.get() (device), for the multi-GPU all-reduce
+    void launch(const T *x, size_t n)
     {
+        if (n == 0)
+        {
+            CUDA_OK(cudaMemset(result.get(), 0, sizeof(double)));
+            return;
+        }
         if constexpr (std::is_same<T, double>::value)
             FE_OK(b200fe_sumsq_f64(x, n, result.get(), scratch.get(), nullptr));
         else
             FE_OK(b200fe_sumsq_f32(x, n, result.get(), scratch.get(), nullptr));
+    }
+    double operator()(const T *x, size_t n)
+    {
+        launch(x, n);
         double h = 0.0;
         CUDA_OK(cudaMemcpy(&h, result.get(), sizeof(double), cudaMemcpyDeviceToHost));
         return h;
