@@ -182,8 +182,6 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
             be = Backend::Generic;
         else if (coa)
             be = nq0 <= kHexTpeMaxNq ? Backend::Tpe : Backend::Generic;
-        else if (nq0 == 2)
-            be = Backend::Nm1;
         else
             be = preferred;
         // the bulk-copy ring needs a 16-byte aligned slab; otherwise take the plain-load twin

@@ -424,7 +424,8 @@ def test_quad_mma_f32_accuracy_ragged_groups_and_4_byte_aligned_slabs(G, nq, nel
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("nelmt,shift", [(1, 0), (33, 1), (100003, 0), (100003, 1)])
 def test_nq2_broadcast_kernel_bit_exact_including_signed_zeros(G, suf, dim, nelmt, shift):
-    """nq = 2 routes to the nm1 back-end; zeros of either sign and misaligned output slabs"""
+    """the nm1 back-end (default for quad FP32 nq = 2, forced here for the rest): zeros of either sign and
+    misaligned output slabs"""
     import torch
     dt = G.NP[suf]
     tdt = torch.float64 if suf == "f64" else torch.float32
@@ -438,15 +439,20 @@ def test_nq2_broadcast_kernel_bit_exact_including_signed_zeros(G, suf, dim, nelm
     big_out = torch.full((nelmt * nout + 4,), float("nan"), dtype=tdt, device="cuda")
     d_b, d_in = [G.dev(x) for x in b], G.dev(inp)
     isz = big_out.element_size()
-    if dim == 2:
-        G.fe.bwdtrans_quad("BwdTransQuadKernel_QP", suf, 2, 2, nelmt, d_b[0].data_ptr(), d_b[1].data_ptr(),
-                           d_in.data_ptr(), big_out.data_ptr() + isz * shift)
-        want = oracle.bwdtrans_quad(2, 2, nelmt, b[0], b[1], inp)
-    else:
-        G.fe.bwdtrans_hex("BwdTransHexKernel_QP", suf, 2, 2, 2, nelmt, d_b[0].data_ptr(), d_b[1].data_ptr(),
-                          d_b[2].data_ptr(), d_in.data_ptr(), big_out.data_ptr() + isz * shift)
-        want = oracle.bwdtrans_hex(2, 2, 2, nelmt, b[0], b[1], b[2], inp)
-    assert G.fe.last_backend() == "nm1"
+    try:
+        if not (dim == 2 and suf == "f32"):
+            G.fe.set_backend("nm1")
+        if dim == 2:
+            G.fe.bwdtrans_quad("BwdTransQuadKernel_QP", suf, 2, 2, nelmt, d_b[0].data_ptr(), d_b[1].data_ptr(),
+                               d_in.data_ptr(), big_out.data_ptr() + isz * shift)
+            want = oracle.bwdtrans_quad(2, 2, nelmt, b[0], b[1], inp)
+        else:
+            G.fe.bwdtrans_hex("BwdTransHexKernel_QP", suf, 2, 2, 2, nelmt, d_b[0].data_ptr(), d_b[1].data_ptr(),
+                              d_b[2].data_ptr(), d_in.data_ptr(), big_out.data_ptr() + isz * shift)
+            want = oracle.bwdtrans_hex(2, 2, 2, nelmt, b[0], b[1], b[2], inp)
+        assert G.fe.last_backend() == "nm1"
+    finally:
+        G.fe.set_backend("auto")
     got = G.host(big_out)[shift:shift + nelmt * nout]
     assert np.array_equal(got, want)
     assert np.array_equal(np.signbit(got), np.signbit(want))
