@@ -335,6 +335,33 @@ def main():
 
     # ---- result check: global norm (NCCL scalar all-reduce) vs the reference's golden checksum ----
     fe.sumsq("f64", d_out.data_ptr(), d_out.numel(), d_res.data_ptr(), d_scr.data_ptr(), st)
+    # the same partial sum from the fused operator + checksum entry point (no second pass over `out`)
+    d_res2 = torch.zeros(1, dtype=torch.float64, device="cuda")
+    fe.bwdtrans_sumsq("f64", (NQ, NQ, NQ), nelmt, [d_b.data_ptr()] * 3, d_in.data_ptr(), d_out.data_ptr(),
+                      d_res2.data_ptr(), d_scr.data_ptr(), st)
+    fused_ok = abs(float(d_res2.item()) - float(d_res.item())) <= 1e-12 * float(d_res.item())
+
+    def timed(fn, reps=20):
+        fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def two_pass():
+        step()
+        fe.sumsq("f64", d_out.data_ptr(), d_out.numel(), d_res.data_ptr(), d_scr.data_ptr(), st)
+
+    def one_pass():
+        fe.bwdtrans_sumsq("f64", (NQ, NQ, NQ), nelmt, [d_b.data_ptr()] * 3, d_in.data_ptr(), d_out.data_ptr(),
+                          d_res2.data_ptr(), d_scr.data_ptr(), st)
+
+    fused = {"operator_then_checksum_ms": timed(two_pass), "fused_ms": timed(one_pass),
+             "what": "operator + sum(out^2) as the reference does after every variant (benchmark05.cc:1270-1273): "
+                     "two passes (checksum re-reads out) vs b200fe_bwdtrans_hex_sumsq_f64 (epilogue of the DMMA kernel)"}
     norm = sharding.global_norm(float(d_res.item()), device="cuda")  # NCCL all-reduce of one double
     want = GOLDEN_NORM_128 * math.sqrt(nelmt * ngpus / 128)
     norm_ok = abs(norm - want) / want < 6e-10
@@ -409,7 +436,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(ngpus),
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "backend": backend, "norm": norm, "norm_ok": bool(norm_ok and elem_ok), "impl": "b200",
+        "backend": backend, "fused_checksum": fused, "norm": norm, "norm_ok": bool(norm_ok and elem_ok and fused_ok), "impl": "b200",
         "lib": fe.version(),
     }
     if sw is not None:
@@ -418,7 +445,7 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0 if (norm_ok and elem_ok) else 1
+    return 0 if (norm_ok and elem_ok and fused_ok) else 1
 
 
 if __name__ == "__main__":

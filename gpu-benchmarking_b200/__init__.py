@@ -171,6 +171,19 @@ def sumsq(suf, x, n, result, scratch, stream=0):
     _check(name, getattr(lib(), name)(_vp(x), ctypes.c_size_t(int(n)), _vp(result), _vp(scratch), _vp(stream)))
 
 
+def bwdtrans_sumsq(suf, nq, nelmt, bases, inp, out, sumsq, scratch, stream=0):
+    """operator + checksum in one call; nq: tuple of 2 or 3; all addresses are DEVICE pointers"""
+    if len(nq) == 2:
+        name = f"b200fe_bwdtrans_quad_sumsq_{suf}"
+        rc = getattr(lib(), name)(_u(nq[0]), _u(nq[1]), _u(nelmt), _vp(bases[0]), _vp(bases[1]), _vp(inp), _vp(out),
+                                  _vp(sumsq), _vp(scratch), _vp(stream))
+    else:
+        name = f"b200fe_bwdtrans_hex_sumsq_{suf}"
+        rc = getattr(lib(), name)(_u(nq[0]), _u(nq[1]), _u(nq[2]), _u(nelmt), _vp(bases[0]), _vp(bases[1]),
+                                  _vp(bases[2]), _vp(inp), _vp(out), _vp(sumsq), _vp(scratch), _vp(stream))
+    _check(name, rc)
+
+
 def bwdtrans_host(suf, nq, nelmt, bases_host, in_host, out_host=0):
     """host-buffer operator; nq: tuple of 2 or 3; addresses are HOST pointers.  Returns sum(out^2)."""
     res = ctypes.c_double(0.0)

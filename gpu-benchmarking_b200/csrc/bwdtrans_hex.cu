@@ -53,7 +53,7 @@ static int hex_pipe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cud
 
 // FP64 tensor-core variant (only the f64 table lists MMA_CASE lines)
 static int hex_mma_switch(unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *b2, const T *in, T *out,
-                          cudaStream_t s)
+                          cudaStream_t s, double *partials, unsigned *npartials)
 {
     switch (nq)
     {
@@ -62,7 +62,7 @@ static int hex_mma_switch(unsigned nq, unsigned nelmt, const T *b0, const T *b1,
 #define PREFER(NQ, BE)
 #define MMA_CASE(NQ, G, W, MB0, NB1)                                                                         \
     case NQ:                                                                                                 \
-        return launch_hex_mma<NQ, G, W, MB0, NB1>(nelmt, b0, b1, b2, in, out, s);
+        return launch_hex_mma<NQ, G, W, MB0, NB1>(nelmt, b0, b1, b2, in, out, s, partials, npartials);
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE
@@ -171,8 +171,11 @@ static int hex_tpe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cuda
 
 template <>
 int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsigned nm2, unsigned nq0, unsigned nq1, unsigned nq2, unsigned nelmt,
-                        const T *b0, const T *b1, const T *b2, const T *in, T *out, cudaStream_t stream)
+                        const T *b0, const T *b1, const T *b2, const T *in, T *out, cudaStream_t stream,
+                        double *partials, unsigned *npartials)
 {
+    if (npartials)
+        *npartials = 0;
     const bool regular = (nq0 == nq1) && (nq1 == nq2) && (nm0 + 1 == nq0) && (nm1 + 1 == nq1) && (nm2 + 1 == nq2) && nq0 >= 2 && nq0 <= 16;
     Backend preferred  = Backend::Generic;
     const int have     = regular ? hex_table_lookup(nq0, &preferred) : 0;
@@ -205,7 +208,7 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
     if (be == Backend::Nm1)
         return (nq0 == 2 && !coa) ? launch_nm1<T, 3>(nelmt, b0, b1, b2, in, out, stream) : B200FE_EUNSUPPORTED;
     if (be == Backend::Mma) // reads the basis matrices from global memory: no constant bank, no lock
-        return (have & 4) ? hex_mma_switch(nq0, nelmt, b0, b1, b2, in, out, stream) : B200FE_EUNSUPPORTED;
+        return (have & 4) ? hex_mma_switch(nq0, nelmt, b0, b1, b2, in, out, stream, partials, npartials) : B200FE_EUNSUPPORTED;
 
     std::lock_guard<std::mutex> lock(g_bank_lock);
     const T *bases[3]   = {b0, b1, b2};

@@ -108,13 +108,16 @@ int launch_quad_pipe(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
 // FP64 tensor-core variant: persistent CTAs of independent warps, one group of G elements per warp at a time
 template <int NQ, int G, int WARPS, int MB0, int NB1>
 int launch_quad_mma(unsigned nelmt, const double *b0, const double *b1, const double *in, double *out,
-                    cudaStream_t stream)
+                    cudaStream_t stream, double *partials = nullptr, unsigned *npartials = nullptr)
 {
     using C = QuadMma<NQ, G, WARPS, MB0, NB1>;
     static_assert(C::SMEM <= (size_t)kSmemMax, "warp regions do not fit shared memory");
     static int occ[64] = {};
-    auto kernel        = bwdtrans_quad_mma_kernel<NQ, G, WARPS, MB0, NB1>;
+    auto kernel        = bwdtrans_quad_mma_kernel<NQ, G, WARPS, MB0, NB1, false>;
+    auto kernel_ss     = bwdtrans_quad_mma_kernel<NQ, G, WARPS, MB0, NB1, true>; // + fused checksum partials
     int rc             = opt_in_smem(kernel, C::SMEM);
+    if (!rc && partials)
+        rc = opt_in_smem(kernel_ss, C::SMEM);
     if (rc)
         return rc;
     const unsigned ngroups = (nelmt + G - 1) / G;
@@ -122,7 +125,13 @@ int launch_quad_mma(unsigned nelmt, const double *b0, const double *b1, const do
     const unsigned fit     = (unsigned)(sm_count() * ctas_per_sm(kernel, WARPS * 32, C::SMEM, occ));
     const unsigned grid    = need < fit ? need : fit;
     const int out_vec      = aligned16(out);
-    kernel<<<grid, WARPS * 32, C::SMEM, stream>>>(b0, b1, in, out, nelmt, ngroups, out_vec);
+    if (partials && grid * WARPS <= kFusedPartialsMax)
+    {
+        kernel_ss<<<grid, WARPS * 32, C::SMEM, stream>>>(b0, b1, in, out, nelmt, ngroups, out_vec, partials);
+        *npartials = grid * WARPS;
+    }
+    else
+        kernel<<<grid, WARPS * 32, C::SMEM, stream>>>(b0, b1, in, out, nelmt, ngroups, out_vec, nullptr);
     count_launch();
     t_last_backend = "mma";
     return launch_status();
@@ -130,13 +139,17 @@ int launch_quad_mma(unsigned nelmt, const double *b0, const double *b1, const do
 
 // FP32 twin: 3xTF32 split on the warp-level tensor-core path
 template <int NQ, int G, int WARPS, int MB0, int NB1>
-int launch_quad_mma(unsigned nelmt, const float *b0, const float *b1, const float *in, float *out, cudaStream_t stream)
+int launch_quad_mma(unsigned nelmt, const float *b0, const float *b1, const float *in, float *out, cudaStream_t stream,
+                    double *partials = nullptr, unsigned *npartials = nullptr)
 {
     using C = QuadMma32<NQ, G, WARPS, MB0, NB1>;
     static_assert(C::SMEM <= (size_t)kSmemMax, "warp regions do not fit shared memory");
     static int occ[64] = {};
-    auto kernel        = bwdtrans_quad_mma32_kernel<NQ, G, WARPS, MB0, NB1>;
+    auto kernel        = bwdtrans_quad_mma32_kernel<NQ, G, WARPS, MB0, NB1, false>;
+    auto kernel_ss     = bwdtrans_quad_mma32_kernel<NQ, G, WARPS, MB0, NB1, true>;
     int rc             = opt_in_smem(kernel, C::SMEM);
+    if (!rc && partials)
+        rc = opt_in_smem(kernel_ss, C::SMEM);
     if (rc)
         return rc;
     const unsigned ngroups = (nelmt + G - 1) / G;
@@ -144,7 +157,13 @@ int launch_quad_mma(unsigned nelmt, const float *b0, const float *b1, const floa
     const unsigned fit     = (unsigned)(sm_count() * ctas_per_sm(kernel, WARPS * 32, C::SMEM, occ));
     const unsigned grid    = need < fit ? need : fit;
     const int out_vec      = (reinterpret_cast<uintptr_t>(out) & 7u) == 0;
-    kernel<<<grid, WARPS * 32, C::SMEM, stream>>>(b0, b1, in, out, nelmt, ngroups, out_vec);
+    if (partials && grid * WARPS <= kFusedPartialsMax)
+    {
+        kernel_ss<<<grid, WARPS * 32, C::SMEM, stream>>>(b0, b1, in, out, nelmt, ngroups, out_vec, partials);
+        *npartials = grid * WARPS;
+    }
+    else
+        kernel<<<grid, WARPS * 32, C::SMEM, stream>>>(b0, b1, in, out, nelmt, ngroups, out_vec, nullptr);
     count_launch();
     t_last_backend = "mma";
     return launch_status();
@@ -200,13 +219,16 @@ int launch_hex_pipe(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
 
 template <int NQ, int G, int WARPS, int MB0, int NB>
 int launch_hex_mma(unsigned nelmt, const double *b0, const double *b1, const double *b2, const double *in, double *out,
-                   cudaStream_t stream)
+                   cudaStream_t stream, double *partials = nullptr, unsigned *npartials = nullptr)
 {
     using C = HexMma<NQ, G, WARPS, MB0, NB>;
     static_assert(C::SMEM <= (size_t)kSmemMax, "warp regions do not fit shared memory");
     static int occ[64] = {};
-    auto kernel        = bwdtrans_hex_mma_kernel<NQ, G, WARPS, MB0, NB>;
+    auto kernel        = bwdtrans_hex_mma_kernel<NQ, G, WARPS, MB0, NB, false>;
+    auto kernel_ss     = bwdtrans_hex_mma_kernel<NQ, G, WARPS, MB0, NB, true>;
     int rc             = opt_in_smem(kernel, C::SMEM);
+    if (!rc && partials)
+        rc = opt_in_smem(kernel_ss, C::SMEM);
     if (rc)
         return rc;
     const unsigned ngroups = (nelmt + G - 1) / G;
@@ -214,7 +236,13 @@ int launch_hex_mma(unsigned nelmt, const double *b0, const double *b1, const dou
     const unsigned fit     = (unsigned)(sm_count() * ctas_per_sm(kernel, WARPS * 32, C::SMEM, occ));
     const unsigned grid    = need < fit ? need : fit;
     const int out_vec      = aligned16(out);
-    kernel<<<grid, WARPS * 32, C::SMEM, stream>>>(b0, b1, b2, in, out, nelmt, ngroups, out_vec);
+    if (partials && grid * WARPS <= kFusedPartialsMax)
+    {
+        kernel_ss<<<grid, WARPS * 32, C::SMEM, stream>>>(b0, b1, b2, in, out, nelmt, ngroups, out_vec, partials);
+        *npartials = grid * WARPS;
+    }
+    else
+        kernel<<<grid, WARPS * 32, C::SMEM, stream>>>(b0, b1, b2, in, out, nelmt, ngroups, out_vec, nullptr);
     count_launch();
     t_last_backend = "mma";
     return launch_status();

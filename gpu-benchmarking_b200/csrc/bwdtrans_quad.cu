@@ -52,7 +52,8 @@ static int quad_pipe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cu
 }
 
 // FP64 tensor-core variant (only the f64 table lists MMA_CASE lines)
-static int quad_mma_switch(unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *in, T *out, cudaStream_t s)
+static int quad_mma_switch(unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *in, T *out, cudaStream_t s,
+                           double *partials, unsigned *npartials)
 {
     switch (nq)
     {
@@ -61,7 +62,7 @@ static int quad_mma_switch(unsigned nq, unsigned nelmt, const T *b0, const T *b1
 #define PREFER(NQ, BE)
 #define MMA_CASE(NQ, G, W, MB0, NB1)                                                                         \
     case NQ:                                                                                                 \
-        return launch_quad_mma<NQ, G, W, MB0, NB1>(nelmt, b0, b1, in, out, s);
+        return launch_quad_mma<NQ, G, W, MB0, NB1>(nelmt, b0, b1, in, out, s, partials, npartials);
 #include B200FE_ROWS_TABLE
 #undef ROWS_CASE
 #undef PIPE_CASE
@@ -175,8 +176,11 @@ static int quad_tpe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cud
 
 template <>
 int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsigned nq0, unsigned nq1, unsigned nelmt,
-                        const T *b0, const T *b1, const T *in, T *out, cudaStream_t stream)
+                        const T *b0, const T *b1, const T *in, T *out, cudaStream_t stream, double *partials,
+                        unsigned *npartials)
 {
+    if (npartials)
+        *npartials = 0;
     const bool regular = (nq0 == nq1) && (nm0 + 1 == nq0) && (nm1 + 1 == nq1) && nq0 >= 2 && nq0 <= 32;
     Backend preferred  = Backend::Generic;
     const int have     = regular ? quad_table_lookup(nq0, &preferred) : 0;
@@ -211,7 +215,7 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
     if (be == Backend::Nm1)
         return (nq0 == 2 && !coa) ? launch_nm1<T, 2>(nelmt, b0, b1, b1, in, out, stream) : B200FE_EUNSUPPORTED;
     if (be == Backend::Mma) // reads the basis matrices from global memory: no constant bank, no lock
-        return (have & 4) ? quad_mma_switch(nq0, nelmt, b0, b1, in, out, stream) : B200FE_EUNSUPPORTED;
+        return (have & 4) ? quad_mma_switch(nq0, nelmt, b0, b1, in, out, stream, partials, npartials) : B200FE_EUNSUPPORTED;
 
     std::lock_guard<std::mutex> lock(g_bank_lock);
     const T *bases[2]   = {b0, b1};

@@ -233,6 +233,56 @@ static int host_pipeline(int dim, const unsigned *nq, size_t nelmt, const T *con
     return B200FE_OK;
 }
 
+// ---- operator + checksum in one call -------------------------------------
+// The reference follows every operator with thrust::transform_reduce over `out`
+// (benchmark04.cc:920-923), re-reading as many bytes as the operator wrote.  Where the back-end
+// that runs keeps the outputs in registers at the end (mma), sum(out^2) is accumulated there and
+// only one partial per warp is written; elsewhere this is the operator followed by the checksum
+// kernels.  Either way the combination order is fixed: deterministic.
+template <typename T>
+static int quad_sumsq_entry(unsigned nq0, unsigned nq1, unsigned nelmt, const T *b0, const T *b1, const T *in, T *out,
+                            double *sumsq, void *scratch, void *stream)
+{
+    if (!sumsq || !scratch || nq0 < 2 || nq1 < 2)
+        return B200FE_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nelmt == 0)
+        return (int)cudaMemsetAsync(sumsq, 0, sizeof(double), st);
+    if (!b0 || !b1 || !in || !out)
+        return B200FE_EINVAL;
+    if (misaligned(b0) || misaligned(b1) || misaligned(in) || misaligned(out))
+        return B200FE_EALIGN;
+    unsigned np = 0;
+    int rc = run_bwdtrans_quad<T>(pick(Backend::Auto), false, nq0 - 1, nq1 - 1, nq0, nq1, nelmt, b0, b1, in, out, st,
+                                  (double *)scratch, &np);
+    if (rc)
+        return rc;
+    return np ? launch_sum_final((const double *)scratch, np, sumsq, st)
+              : launch_sumsq<T>(out, (size_t)nelmt * nq0 * nq1, sumsq, scratch, false, st);
+}
+
+template <typename T>
+static int hex_sumsq_entry(unsigned nq0, unsigned nq1, unsigned nq2, unsigned nelmt, const T *b0, const T *b1,
+                           const T *b2, const T *in, T *out, double *sumsq, void *scratch, void *stream)
+{
+    if (!sumsq || !scratch || nq0 < 2 || nq1 < 2 || nq2 < 2)
+        return B200FE_EINVAL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nelmt == 0)
+        return (int)cudaMemsetAsync(sumsq, 0, sizeof(double), st);
+    if (!b0 || !b1 || !b2 || !in || !out)
+        return B200FE_EINVAL;
+    if (misaligned(b0) || misaligned(b1) || misaligned(b2) || misaligned(in) || misaligned(out))
+        return B200FE_EALIGN;
+    unsigned np = 0;
+    int rc = run_bwdtrans_hex<T>(pick(Backend::Auto), false, nq0 - 1, nq1 - 1, nq2 - 1, nq0, nq1, nq2, nelmt, b0, b1, b2,
+                                 in, out, st, (double *)scratch, &np);
+    if (rc)
+        return rc;
+    return np ? launch_sum_final((const double *)scratch, np, sumsq, st)
+              : launch_sumsq<T>(out, (size_t)nelmt * nq0 * nq1 * nq2, sumsq, scratch, false, st);
+}
+
 } // namespace b200fe
 
 using namespace b200fe;
@@ -409,6 +459,24 @@ size_t b200fe_sumsq_scratch_bytes(void)
 {
     return sumsq_scratch_bytes();
 }
+
+// ---- operator + checksum in one call: entry templates above ------------------
+#define FUSED_API(SUF, T)                                                                                    \
+    int b200fe_bwdtrans_quad_sumsq_##SUF(unsigned nq0, unsigned nq1, unsigned nelmt, const T *basis0,        \
+                                         const T *basis1, const T *in, T *out, double *sumsq, void *scratch, \
+                                         void *stream)                                                       \
+    {                                                                                                        \
+        return quad_sumsq_entry<T>(nq0, nq1, nelmt, basis0, basis1, in, out, sumsq, scratch, stream);        \
+    }                                                                                                        \
+    int b200fe_bwdtrans_hex_sumsq_##SUF(unsigned nq0, unsigned nq1, unsigned nq2, unsigned nelmt,            \
+                                        const T *basis0, const T *basis1, const T *basis2, const T *in,      \
+                                        T *out, double *sumsq, void *scratch, void *stream)                  \
+    {                                                                                                        \
+        return hex_sumsq_entry<T>(nq0, nq1, nq2, nelmt, basis0, basis1, basis2, in, out, sumsq, scratch,     \
+                                  stream);                                                                   \
+    }
+FUSED_API(f64, double)
+FUSED_API(f32, float)
 
 // ---- host-buffer operator ---------------------------------------------------------------
 #define HOST_API(SUF, T)                                                                                     \

@@ -34,6 +34,8 @@ inline int launch_status()
 }
 
 constexpr int kSmemMax = 227 * 1024; // opt-in dynamic shared memory per CTA on sm_100
+// fused operator + checksum: one partial per resident warp of the persistent grid (148 SMs x 64 warps at most)
+constexpr unsigned kFusedPartialsMax = 16384;
 
 // ---- 16-byte vector types ----------------------------------------------------
 template <typename T> struct Vec16;

@@ -21,10 +21,14 @@ enum class Backend : int
 // element-major unless coa; return 0 / cudaError_t / negative B200FE_E*
 template <typename T>
 int run_bwdtrans_quad(Backend be, bool coa, unsigned nm0, unsigned nm1, unsigned nq0, unsigned nq1, unsigned nelmt,
-                      const T *b0, const T *b1, const T *in, T *out, cudaStream_t stream);
+                      const T *b0, const T *b1, const T *in, T *out, cudaStream_t stream, double *partials = nullptr,
+                      unsigned *npartials = nullptr);
 template <typename T>
 int run_bwdtrans_hex(Backend be, bool coa, unsigned nm0, unsigned nm1, unsigned nm2, unsigned nq0, unsigned nq1,
                      unsigned nq2, unsigned nelmt, const T *b0, const T *b1, const T *b2, const T *in, T *out,
-                     cudaStream_t stream);
+                     cudaStream_t stream, double *partials = nullptr, unsigned *npartials = nullptr);
+// partials/npartials: fused checksum.  When the back-end that runs can fuse sum(out^2) into its
+// epilogue it writes *npartials (> 0) per-warp partial sums to partials[]; otherwise *npartials stays 0 and the
+// caller reduces `out` itself.
 
 } // namespace b200fe

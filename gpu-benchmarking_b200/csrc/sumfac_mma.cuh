@@ -118,9 +118,9 @@ __device__ __forceinline__ void mma_pass_data_rows(const double *__restrict__ sr
 // data is the B operand: column n of ncols decomposes as (g, w) = (n / W, n % W) and its K values lie
 // STRIDE apart: src + (g*NM + k)*STRIDE + w.  Output (m, n) goes to dst + g*DG + m*DM + w, i.e. each
 // lane holds two values adjacent in w: one 16-byte store, to shared memory or (streaming) to global.
-template <int NQ, int W, int STRIDE, int DG, int DM, int NB, bool TO_GLOBAL>
+template <int NQ, int W, int STRIDE, int DG, int DM, int NB, bool TO_GLOBAL, bool SUMSQ = false>
 __device__ __forceinline__ void mma_pass_basis_rows(const double *__restrict__ src, const double *__restrict__ fragA,
-                                                    double *__restrict__ dst, int ncols, bool vec, int lane)
+                                                    double *__restrict__ dst, int ncols, bool vec, int lane, double &ss)
 {
     constexpr int NM = NQ - 1, KS = (NM + 3) / 4, MT = (NQ + 7) / 8;
     static_assert(W % 2 == 0, "outputs are paired along w");
@@ -176,6 +176,8 @@ __device__ __forceinline__ void mma_pass_basis_rows(const double *__restrict__ s
                     const int j = 8 * m + r;
                     if (j < NQ)
                     {
+                        if (SUMSQ) // fused checksum: this lane's share of sum(out^2), fixed order
+                            ss = fmadd(acc[m][t][1], acc[m][t][1], fmadd(acc[m][t][0], acc[m][t][0], ss));
                         if (!TO_GLOBAL)
                             *reinterpret_cast<double2 *>(op + j * DM) = make_double2(acc[m][t][0], acc[m][t][1]);
                         else if (vec)
@@ -282,10 +284,10 @@ __device__ __forceinline__ void mma_pass_data_rows_full(const double *__restrict
 
 // needs NCOLS % 8 == 0.  A tile of 8 columns may straddle two groups when W % 8 != 0: the lanes past
 // the group boundary then add one compile-time constant to their address (a predicated add per tile).
-template <int NQ, int W, int STRIDE, int DG, int DM, int NB, bool TO_GLOBAL, bool VEC, int NCOLS>
+template <int NQ, int W, int STRIDE, int DG, int DM, int NB, bool TO_GLOBAL, bool VEC, int NCOLS, bool SUMSQ = false>
 __device__ __forceinline__ void mma_pass_basis_rows_full(const double *__restrict__ src,
                                                          const double *__restrict__ fragA, double *__restrict__ dst,
-                                                         int lane)
+                                                         int lane, double &ss)
 {
     constexpr int NM = NQ - 1, KS = (NM + 3) / 4, MT = (NQ + 7) / 8, NTT = NCOLS / 8;
     constexpr int NBLK = (NTT + NB - 1) / NB;
@@ -352,6 +354,8 @@ __device__ __forceinline__ void mma_pass_basis_rows_full(const double *__restric
                     if (8 * m + 8 <= NQ || 8 * m + r < NQ)
                     {
                         double *op = db + (size_t)g * DG + w0 + 8 * m * DM;
+                        if (SUMSQ)
+                            ss = fmadd(acc[m][t][1], acc[m][t][1], fmadd(acc[m][t][0], acc[m][t][0], ss));
                         if (!TO_GLOBAL)
                             *reinterpret_cast<double2 *>(op) = make_double2(acc[m][t][0], acc[m][t][1]);
                         else if (VEC)
@@ -376,22 +380,34 @@ __device__ __forceinline__ void mma_dir_data(const double *__restrict__ src, con
     else
         mma_pass_data_rows<NQ, DS, MB>(src, fragB, dst, nrows, lane);
 }
-template <int NQ, int W, int STRIDE, int DG, int DM, int NB, bool TO_GLOBAL, int NCOLS>
+template <int NQ, int W, int STRIDE, int DG, int DM, int NB, bool TO_GLOBAL, int NCOLS, bool SUMSQ = false>
 __device__ __forceinline__ void mma_dir_basis(const double *__restrict__ src, const double *__restrict__ fragA,
-                                              double *__restrict__ dst, int ncols, bool vec, int lane)
+                                              double *__restrict__ dst, int ncols, bool vec, int lane, double &ss)
 {
     if constexpr (NCOLS % 8 == 0)
     {
         if (ncols == NCOLS)
         {
             if (vec)
-                mma_pass_basis_rows_full<NQ, W, STRIDE, DG, DM, NB, TO_GLOBAL, true, NCOLS>(src, fragA, dst, lane);
+                mma_pass_basis_rows_full<NQ, W, STRIDE, DG, DM, NB, TO_GLOBAL, true, NCOLS, SUMSQ>(src, fragA, dst, lane,
+                                                                                                ss);
             else
-                mma_pass_basis_rows_full<NQ, W, STRIDE, DG, DM, NB, TO_GLOBAL, false, NCOLS>(src, fragA, dst, lane);
+                mma_pass_basis_rows_full<NQ, W, STRIDE, DG, DM, NB, TO_GLOBAL, false, NCOLS, SUMSQ>(src, fragA, dst, lane,
+                                                                                                 ss);
             return;
         }
     }
-    mma_pass_basis_rows<NQ, W, STRIDE, DG, DM, NB, TO_GLOBAL>(src, fragA, dst, ncols, vec, lane);
+    mma_pass_basis_rows<NQ, W, STRIDE, DG, DM, NB, TO_GLOBAL, SUMSQ>(src, fragA, dst, ncols, vec, lane, ss);
+}
+
+// this warp's share of the fused checksum -> partials[global warp index] (xor-shuffle: fixed order)
+__device__ __forceinline__ void mma_store_partial(double ss, double *__restrict__ partials, int warp_global, int lane)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0)
+        partials[warp_global] = ss;
 }
 
 // basis matrix B[p*NQ + i] -> B-operand fragments [ks][nt][lane] (K = p, N = i), zero padded
@@ -471,11 +487,13 @@ template <int NQ, int G, int WARPS, int MB0, int NB1> struct QuadMma
     static_assert(NQ % 2 == 0, "the mma back-end pairs outputs along i");
 };
 
-template <int NQ, int G, int WARPS, int MB0, int NB1>
+// SUMSQ: also leave sum(out^2) of this warp's elements in partials[blockIdx.x * WARPS + warp] (SURVEY.md 8f-2:
+// the checksum that follows every operator in the reference, fused into its epilogue instead of re-reading out)
+template <int NQ, int G, int WARPS, int MB0, int NB1, bool SUMSQ = false>
 __global__ void __launch_bounds__(WARPS * 32)
     bwdtrans_quad_mma_kernel(const double *__restrict__ basis0, const double *__restrict__ basis1,
                              const double *__restrict__ in, double *__restrict__ out, unsigned nelmt, unsigned ngroups,
-                             int out_vec)
+                             int out_vec, double *__restrict__ partials)
 {
     using C = QuadMma<NQ, G, WARPS, MB0, NB1>;
     constexpr int NM = C::NM, S = C::S;
@@ -503,6 +521,7 @@ __global__ void __launch_bounds__(WARPS * 32)
     const unsigned nw = gridDim.x * WARPS;
     unsigned g        = blockIdx.x * WARPS + warp;
     unsigned parity   = 0;
+    double ss         = 0.0;   // fused checksum (SUMSQ)
     bool by_bar       = false; // the slot is filled through the mbarrier (else it was copied with plain loads)
     if (g < ngroups)
         by_bar = mma_fetch_group<G, C::NM2>(slot, bar, in, g, nelmt, lane);
@@ -525,10 +544,12 @@ __global__ void __launch_bounds__(WARPS * 32)
         if (g + nw < ngroups)
             by_bar = mma_fetch_group<G, C::NM2>(slot, bar, in, g + nw, nelmt, lane);
         // direction 1: out[e][j][i] = sum_q B1[q][j] mid[e][q][i]
-        mma_dir_basis<NQ, NQ, S, C::NQ2, NQ, NB1, true, G * NQ>(mid, frag1, out + e0 * C::NQ2, ne * NQ, out_vec != 0,
-                                                               lane);
+        mma_dir_basis<NQ, NQ, S, C::NQ2, NQ, NB1, true, G * NQ, SUMSQ>(mid, frag1, out + e0 * C::NQ2, ne * NQ,
+                                                                      out_vec != 0, lane, ss);
         __syncwarp(); // mid is rewritten by the next group's direction 0
     }
+    if (SUMSQ)
+        mma_store_partial(ss, partials, blockIdx.x * WARPS + warp, lane);
 }
 
 // ============================== hex ===========================================
@@ -563,11 +584,11 @@ template <int NQ, int G, int WARPS, int MB0, int NB> struct HexMma
     static_assert(NQ % 2 == 0, "the mma back-end pairs outputs along i");
 };
 
-template <int NQ, int G, int WARPS, int MB0, int NB>
+template <int NQ, int G, int WARPS, int MB0, int NB, bool SUMSQ = false>
 __global__ void __launch_bounds__(WARPS * 32)
     bwdtrans_hex_mma_kernel(const double *__restrict__ basis0, const double *__restrict__ basis1,
                             const double *__restrict__ basis2, const double *__restrict__ in, double *__restrict__ out,
-                            unsigned nelmt, unsigned ngroups, int out_vec)
+                            unsigned nelmt, unsigned ngroups, int out_vec, double *__restrict__ partials)
 {
     using C = HexMma<NQ, G, WARPS, MB0, NB>;
     constexpr int NM = C::NM;
@@ -595,6 +616,7 @@ __global__ void __launch_bounds__(WARPS * 32)
     const unsigned nw = gridDim.x * WARPS;
     unsigned g        = blockIdx.x * WARPS + warp;
     unsigned parity   = 0;
+    double ss         = 0.0;
     bool by_bar       = false;
     if (g < ngroups)
         by_bar = mma_fetch_group<G, C::NM3>(slot, bar, in, g, nelmt, lane);
@@ -615,13 +637,15 @@ __global__ void __launch_bounds__(WARPS * 32)
         if (g + nw < ngroups)
             by_bar = mma_fetch_group<G, C::NM3>(slot, bar, in, g + nw, nelmt, lane);
         // direction 1: s2[(e,r)][j][i] = sum_q B1[q][j] s1[(e,r)][q][i]
-        mma_dir_basis<NQ, NQ, C::S1, C::S2, NQ, NB, false, G * NM * NQ>(s1, frag1, s2, ne * NM * NQ, true, lane);
+        mma_dir_basis<NQ, NQ, C::S1, C::S2, NQ, NB, false, G * NM * NQ>(s1, frag1, s2, ne * NM * NQ, true, lane, ss);
         __syncwarp();
         // direction 2: out[e][k][(j,i)] = sum_r B2[r][k] s2[e][r][(j,i)]
-        mma_dir_basis<NQ, C::NQ2, C::S2, C::NQ3, C::NQ2, NB, true, G * C::NQ2>(s2, frag2, out + e0 * C::NQ3,
-                                                                              ne * C::NQ2, out_vec != 0, lane);
+        mma_dir_basis<NQ, C::NQ2, C::S2, C::NQ3, C::NQ2, NB, true, G * C::NQ2, SUMSQ>(
+            s2, frag2, out + e0 * C::NQ3, ne * C::NQ2, out_vec != 0, lane, ss);
         __syncwarp(); // s1 / s2 are rewritten by the next group
     }
+    if (SUMSQ)
+        mma_store_partial(ss, partials, blockIdx.x * WARPS + warp, lane);
 }
 
 } // namespace b200fe

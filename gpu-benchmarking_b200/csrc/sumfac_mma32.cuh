@@ -110,11 +110,11 @@ __device__ __forceinline__ bool mma32_fetch_group(float *slot, uint64_t *bar, co
     return false;
 }
 
-template <int NQ, int G, int WARPS, int MB0, int NB1>
+template <int NQ, int G, int WARPS, int MB0, int NB1, bool SUMSQ = false>
 __global__ void __launch_bounds__(WARPS * 32)
     bwdtrans_quad_mma32_kernel(const float *__restrict__ basis0, const float *__restrict__ basis1,
                                const float *__restrict__ in, float *__restrict__ out, unsigned nelmt, unsigned ngroups,
-                               int out_vec)
+                               int out_vec, double *__restrict__ partials)
 {
     using C = QuadMma32<NQ, G, WARPS, MB0, NB1>;
     constexpr int NM = C::NM, KS = C::KS, NT0 = C::NT0, MT1 = C::MT1, MT0 = C::MT0, NT1 = C::NT1, S = C::S;
@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(WARPS * 32)
     const unsigned nw = gridDim.x * WARPS;
     unsigned grp      = blockIdx.x * WARPS + warp;
     unsigned parity   = 0;
+    double ss         = 0.0; // fused checksum (SUMSQ), accumulated in double like b200fe_sumsq_f32
     bool by_bar       = false;
     if (grp < ngroups)
         by_bar = mma32_fetch_group<G, C::NM2>(slot, bar, in, grp, nelmt, lane);
@@ -313,6 +314,11 @@ __global__ void __launch_bounds__(WARPS * 32)
                                     const int j = 16 * m + g + 8 * h;
                                     if (j < NQ)
                                     {
+                                        if (SUMSQ)
+                                        {
+                                            const double a0 = acc[m][n][2 * h], a1 = acc[m][n][2 * h + 1];
+                                            ss = fmadd(a1, a1, fmadd(a0, a0, ss));
+                                        }
                                         if (out_vec)
                                             st_stream(reinterpret_cast<float2 *>(op + j * NQ),
                                                       make_float2(acc[m][n][2 * h], acc[m][n][2 * h + 1]));
@@ -329,6 +335,8 @@ __global__ void __launch_bounds__(WARPS * 32)
         }
         __syncwarp(); // mid is rewritten by the next group's direction 0
     }
+    if (SUMSQ)
+        mma_store_partial(ss, partials, blockIdx.x * WARPS + warp, lane);
 }
 
 } // namespace b200fe

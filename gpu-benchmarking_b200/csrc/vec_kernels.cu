@@ -508,7 +508,15 @@ template <typename T> int launch_matvec(unsigned N, unsigned M, const T *A, cons
 
 size_t sumsq_scratch_bytes()
 {
-    return (size_t)kSumsqBlocks * sizeof(double);
+    // partials of the stand-alone checksum, or of the fused operator + checksum (one per resident warp)
+    return (size_t)(kSumsqBlocks > (int)kFusedPartialsMax ? kSumsqBlocks : (int)kFusedPartialsMax) * sizeof(double);
+}
+
+int launch_sum_final(const double *part, unsigned n, double *result, cudaStream_t s)
+{
+    sum_final_kernel<<<1, kRedThreads, 0, s>>>(part, n, result, 0);
+    count_launch();
+    return launch_status();
 }
 
 template <typename T> int launch_sumsq(const T *x, size_t n, double *result, void *scratch, bool accumulate, cudaStream_t s)

@@ -12,5 +12,7 @@ template <typename T> int launch_set_data(T *data, unsigned n, int mode, cudaStr
 template <typename T> int launch_add_vector(T *x, const T *y, unsigned begin, unsigned end, bool vl, cudaStream_t s);
 template <typename T> int launch_matvec(unsigned N, unsigned M, const T *A, const T *x, T *y, bool vl, cudaStream_t s);
 size_t sumsq_scratch_bytes();
+// *result = sum of part[0..n) in a fixed order (second stage of every deterministic reduction)
+int launch_sum_final(const double *part, unsigned n, double *result, cudaStream_t s);
 template <typename T> int launch_sumsq(const T *x, size_t n, double *result, void *scratch, bool accumulate, cudaStream_t s);
 } // namespace b200fe

@@ -233,6 +233,29 @@ size_t b200fe_sumsq_scratch_bytes(void);
 int b200fe_sumsq_f64(const double *x, size_t n, double *result, void *scratch, void *stream);
 int b200fe_sumsq_f32(const float *x, size_t n, double *result, void *scratch, void *stream);
 
+/* ---- operator + checksum in one call (extension) ---------
+ * out = BwdTrans(in) (element-major) AND *sumsq (device, double) = sum out^2, i.e. the
+ * operator launch plus the thrust::transform_reduce that follows it in the reference
+ * (benchmark04.cc:912-923) as one call.  Where the back-end that runs holds the outputs in
+ * registers at the end (the tensor-core back-ends) the sum is accumulated in its epilogue and
+ * `out` is not read again; elsewhere the checksum kernels run after the operator.  The
+ * combination order is fixed (deterministic); it differs from b200fe_sumsq_*'s, so the two
+ * agree to rounding (1e-12 relative), not bit for bit.  scratch: >= b200fe_sumsq_scratch_bytes()
+ * bytes of device memory.  The partial sum is what a multi-GPU caller all-reduces (NCCL, one
+ * double). */
+int b200fe_bwdtrans_quad_sumsq_f64(unsigned nq0, unsigned nq1, unsigned nelmt, const double *basis0,
+                                   const double *basis1, const double *in, double *out, double *sumsq,
+                                   void *scratch, void *stream);
+int b200fe_bwdtrans_quad_sumsq_f32(unsigned nq0, unsigned nq1, unsigned nelmt, const float *basis0,
+                                   const float *basis1, const float *in, float *out, double *sumsq,
+                                   void *scratch, void *stream);
+int b200fe_bwdtrans_hex_sumsq_f64(unsigned nq0, unsigned nq1, unsigned nq2, unsigned nelmt, const double *basis0,
+                                  const double *basis1, const double *basis2, const double *in, double *out,
+                                  double *sumsq, void *scratch, void *stream);
+int b200fe_bwdtrans_hex_sumsq_f32(unsigned nq0, unsigned nq1, unsigned nq2, unsigned nelmt, const float *basis0,
+                                  const float *basis1, const float *basis2, const float *in, float *out,
+                                  double *sumsq, void *scratch, void *stream);
+
 /* ---- host-buffer operator (end-to-end path) --------------------------------------
  * Whole-operator call on HOST arrays, as an application holding its field on
  * the CPU would issue it: the element range is cut into chunks that are

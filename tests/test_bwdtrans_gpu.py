@@ -456,3 +456,40 @@ def test_nq2_broadcast_kernel_bit_exact_including_signed_zeros(G, suf, dim, nelm
     got = G.host(big_out)[shift:shift + nelmt * nout]
     assert np.array_equal(got, want)
     assert np.array_equal(np.signbit(got), np.signbit(want))
+
+
+@pytest.mark.parametrize("suf", ["f64", "f32"])
+@pytest.mark.parametrize("dim,nq", [(2, 4), (2, 8), (2, 14), (2, 16), (2, 32), (3, 4), (3, 8), (3, 10)])
+@pytest.mark.parametrize("nelmt", [1, 37, 20011])
+def test_fused_operator_and_checksum(G, suf, dim, nq, nelmt):
+    """b200fe_bwdtrans_*_sumsq: same `out` as the plain entry point, sum(out^2) within 1e-12 of the oracle's,
+    identical bits run to run; covers the fused (mma) and the two-pass (rows / pipe) routes"""
+    import torch
+    dt, nm = G.NP[suf], nq - 1
+    tdt = torch.float64 if suf == "f64" else torch.float32
+    if dim == 2 and nq == 32:
+        nelmt = min(nelmt, 3001)
+    rng = np.random.default_rng(900 + nq + nelmt)
+    b = [rnd(rng, nm * nq, dt) for _ in range(dim)]
+    inp = rnd(rng, nelmt * nm ** dim, dt)
+    d_b, d_in = [G.dev(x) for x in b], G.dev(inp)
+    st = torch.cuda.current_stream().cuda_stream
+    scratch = torch.empty(G.fe.sumsq_scratch_bytes(), dtype=torch.uint8, device="cuda")
+    results = []
+    for _ in range(2):
+        d_out = torch.full((nelmt * nq ** dim,), float("nan"), dtype=tdt, device="cuda")
+        ss = torch.full((1,), float("nan"), dtype=torch.float64, device="cuda")
+        G.fe.bwdtrans_sumsq(suf, (nq,) * dim, nelmt, [x.data_ptr() for x in d_b], d_in.data_ptr(), d_out.data_ptr(),
+                            ss.data_ptr(), scratch.data_ptr(), st)
+        results.append((G.host(d_out), float(ss.item())))
+    backend = G.fe.last_backend()
+    if dim == 2:
+        plain = G.run_quad("BwdTransQuadKernel_QP_Shared", suf, nq, nq, nelmt, b[0], b[1], inp)
+    else:
+        plain = G.run_hex("BwdTransHexKernel_QP_Shared", suf, (nq,) * 3, nelmt, b, inp)
+    assert G.fe.last_backend() == backend
+    assert np.array_equal(results[0][0], plain)                 # the fused kernel stores exactly what the plain one does
+    want = oracle.sumsq(plain)
+    assert abs(results[0][1] - want) / want < 1e-12, (backend, results[0][1], want)
+    assert results[0][1] == results[1][1]                       # deterministic
+    assert np.array_equal(results[0][0], results[1][0])
