@@ -52,17 +52,66 @@ template <int NM, int NQ, int SIZE> constexpr int unrolled_ib()
     return 1;
 }
 
+// IB accumulators of one row.  FP32 with an even IB packs adjacent outputs into 64-bit registers and
+// updates them with the packed FMA of sm_100 (fma.rn.f32x2 -> SASS FFMA2 R, R.F32 (scalar broadcast),
+// UR.F32x2 (basis pair straight from the constant bank), R.F32x2): two IEEE fused multiply-adds per
+// instruction, bit-identical to two FFMAs, at half the issue slots -- the FP32 rows kernels are
+// issue-bound (profiles/r01_ncu_hex10_f32.txt: 83 % of the issue slots, 60 % of them FFMA).
+template <typename T, int IB, bool PACKED = (sizeof(T) == 4 && IB % 2 == 0)> struct RowAcc
+{
+    T t[IB];
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int j = 0; j < IB; ++j)
+            t[j] = T(0);
+    }
+    __device__ __forceinline__ void fma(T a, const T (&b)[IB])
+    {
+#pragma unroll
+        for (int j = 0; j < IB; ++j)
+            t[j] = fmadd(a, b[j], t[j]);
+    }
+    __device__ __forceinline__ T get(int j) const { return t[j]; }
+};
+template <int IB> struct RowAcc<float, IB, true>
+{
+    unsigned long long t[IB / 2];
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int j = 0; j < IB / 2; ++j)
+            t[j] = 0ull; // (+0.0f, +0.0f)
+    }
+    __device__ __forceinline__ void fma(float a, const float (&b)[IB])
+    {
+        unsigned long long aa;
+        asm("mov.b64 %0, {%1, %1};" : "=l"(aa) : "f"(a));
+#pragma unroll
+        for (int j = 0; j < IB / 2; ++j)
+        {
+            unsigned long long bb;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(bb) : "f"(b[2 * j]), "f"(b[2 * j + 1]));
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(t[j]) : "l"(aa), "l"(bb));
+        }
+    }
+    __device__ __forceinline__ float get(int j) const
+    {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(t[j / 2]));
+        return (j & 1) ? hi : lo;
+    }
+};
+
 template <typename T, int NM, int NQ, int BOFF, int OSTRIDE, int R, int IB, bool TO_GLOBAL>
 __device__ __forceinline__ void contract_block(const T (&a)[R][NM], T *const (&dst)[R], const bool (&ok)[R], int ib)
 {
     constexpr int W       = 16 / (int)sizeof(T);
     constexpr bool ALIGNED = (NQ % W == 0) && (BOFF % W == 0) && (IB % W == 0 || IB % 2 == 0);
-    T t[R][IB];
+    RowAcc<T, IB> t[R];
 #pragma unroll
     for (int k = 0; k < R; ++k)
-#pragma unroll
-        for (int j = 0; j < IB; ++j)
-            t[k][j] = T(0);
+        t[k].zero();
 #pragma unroll
     for (int p = 0; p < NM; ++p)
     {
@@ -70,9 +119,7 @@ __device__ __forceinline__ void contract_block(const T (&a)[R][NM], T *const (&d
         cbasis_load<IB, ALIGNED>(BOFF + p * NQ + ib, b);
 #pragma unroll
         for (int k = 0; k < R; ++k)
-#pragma unroll
-            for (int j = 0; j < IB; ++j)
-                t[k][j] = fmadd(a[k][p], b[j], t[k][j]);
+            t[k].fma(a[k][p], b);
     }
 #pragma unroll
     for (int k = 0; k < R; ++k)
@@ -82,9 +129,9 @@ __device__ __forceinline__ void contract_block(const T (&a)[R][NM], T *const (&d
             for (int j = 0; j < IB; ++j)
             {
                 if (TO_GLOBAL)
-                    st_stream(dst[k] + (size_t)(ib + j) * OSTRIDE, t[k][j]);
+                    st_stream(dst[k] + (size_t)(ib + j) * OSTRIDE, t[k].get(j));
                 else
-                    dst[k][(ib + j) * OSTRIDE] = t[k][j];
+                    dst[k][(ib + j) * OSTRIDE] = t[k].get(j);
             }
         }
 }
@@ -95,12 +142,10 @@ __device__ __forceinline__ void ploop_block(const T *const (&src)[R], T *const (
 {
     constexpr int W        = 16 / (int)sizeof(T);
     constexpr bool ALIGNED = (NQ % W == 0) && (BOFF % W == 0) && (IB0 % W == 0);
-    T t[R][IB];
+    RowAcc<T, IB> t[R];
 #pragma unroll
     for (int k = 0; k < R; ++k)
-#pragma unroll
-        for (int j = 0; j < IB; ++j)
-            t[k][j] = T(0);
+        t[k].zero();
 #pragma unroll 1
     for (int p = 0; p < NM; ++p)
     {
@@ -112,9 +157,7 @@ __device__ __forceinline__ void ploop_block(const T *const (&src)[R], T *const (
         cbasis_load<IB, ALIGNED>(BOFF + p * NQ + IB0, b);
 #pragma unroll
         for (int k = 0; k < R; ++k)
-#pragma unroll
-            for (int j = 0; j < IB; ++j)
-                t[k][j] = fmadd(a[k], b[j], t[k][j]);
+            t[k].fma(a[k], b);
     }
 #pragma unroll
     for (int k = 0; k < R; ++k)
@@ -124,9 +167,9 @@ __device__ __forceinline__ void ploop_block(const T *const (&src)[R], T *const (
             for (int j = 0; j < IB; ++j)
             {
                 if (TO_GLOBAL)
-                    st_stream(dst[k] + (size_t)(IB0 + j) * OSTRIDE, t[k][j]);
+                    st_stream(dst[k] + (size_t)(IB0 + j) * OSTRIDE, t[k].get(j));
                 else
-                    dst[k][(IB0 + j) * OSTRIDE] = t[k][j];
+                    dst[k][(IB0 + j) * OSTRIDE] = t[k].get(j);
             }
         }
 }
