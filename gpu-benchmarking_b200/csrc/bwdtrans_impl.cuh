@@ -30,6 +30,25 @@ template <typename K> inline int opt_in_smem(K kernel, size_t bytes)
     return 0;
 }
 
+// launch as a programmatic dependent of the kernel before it on the stream (the constant-bank fill): see
+// grid_dependency_wait() in common.cuh
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
+                                    cudaStream_t stream, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = dim3(grid);
+    cfg.blockDim           = dim3(block);
+    cfg.dynamicSmemBytes   = smem;
+    cfg.stream             = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs                                          = attr;
+    cfg.numAttrs                                       = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- quad ---------------------------------------------------------------------
 // resident CTAs per SM of a kernel at its block size / shared memory, cached per device
 template <typename K> inline int ctas_per_sm(K kernel, int threads, size_t smem, int *cache)
@@ -77,7 +96,7 @@ int launch_quad_rows(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
     const unsigned grid = (nelmt + E - 1) / E;
     const int in_vec    = C::IN_VEC_OK && aligned16(in);
     const int out_vec   = C::OUT_VEC_OK && aligned16(out);
-    kernel<<<grid, THREADS, C::SMEM, stream>>>(in, out, nelmt, in_vec, out_vec);
+    B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt, in_vec, out_vec));
     count_launch();
     t_last_backend = "rows";
     return launch_status();
@@ -99,7 +118,7 @@ int launch_quad_pipe(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
     const unsigned fit    = (unsigned)(sm_count() * ctas_per_sm(kernel, THREADS, C::SMEM, occ));
     const unsigned grid   = ntiles < fit ? ntiles : fit;
     const int out_vec     = C::OUT_VEC_OK && aligned16(out);
-    kernel<<<grid, THREADS, C::SMEM, stream>>>(in, out, nelmt, ntiles, out_vec);
+    B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt, ntiles, out_vec));
     count_launch();
     t_last_backend = "pipe";
     return launch_status();
@@ -191,7 +210,7 @@ int launch_hex_rows(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
         return rc;
     const unsigned grid = (nelmt + E - 1) / E;
     const int in_vec    = C::IN_VEC_OK && aligned16(in);
-    kernel<<<grid, THREADS, C::SMEM, stream>>>(in, out, nelmt, in_vec);
+    B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt, in_vec));
     count_launch();
     t_last_backend = "rows";
     return launch_status();
@@ -211,7 +230,7 @@ int launch_hex_pipe(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
     const unsigned ntiles = (nelmt + E - 1) / E;
     const unsigned fit    = (unsigned)(sm_count() * ctas_per_sm(kernel, THREADS, C::SMEM, occ));
     const unsigned grid   = ntiles < fit ? ntiles : fit;
-    kernel<<<grid, THREADS, C::SMEM, stream>>>(in, out, nelmt, ntiles);
+    B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt, ntiles));
     count_launch();
     t_last_backend = "pipe";
     return launch_status();
