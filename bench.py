@@ -51,6 +51,19 @@ def hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def gen_basis(nm, nq, dtype="float64"):
+    """B[k] = cos((T)k), k = p*nq + i -- the reference's synthetic basis (benchmark05.cc:1216-1236)"""
+    import numpy as np
+    return np.cos(np.arange(nm * nq, dtype=dtype)).astype(dtype)
+
+
+def gen_in(nelmt, nmtot, dtype="float64"):
+    """in[e][k] = sin((T)(k+1)) for every element (benchmark05.cc:1195-1215), element-major"""
+    import numpy as np
+    one = np.sin(np.arange(1, nmtot + 1, dtype=dtype)).astype(dtype)
+    return np.tile(one, nelmt)
+
+
 def alg_bytes_per_elem(dim, nq, size):
     return size * ((nq - 1) ** dim + nq ** dim)
 
@@ -192,7 +205,7 @@ def workload_config(ngpus):
     }
 
 
-def sweep(fe, torch, oracle, peak, reps=5):
+def sweep(fe, torch, peak, reps=5):
     """GDoF/s and HBM-roofline fraction for every operator/nq of configs[2]/[3] at ~64 Mi quadrature points"""
     import numpy as np
     out = []
@@ -203,8 +216,8 @@ def sweep(fe, torch, oracle, peak, reps=5):
             for nq in nqs:
                 nm = nq - 1
                 nelmt = max(32, ((1 << 26) // nq ** dim) // 32 * 32)
-                b = torch.from_numpy(oracle.gen_basis(nm, nq, npdt)).cuda()
-                one = torch.from_numpy(oracle.gen_in(32, nm ** dim, npdt)).cuda()
+                b = torch.from_numpy(gen_basis(nm, nq, npdt)).cuda()
+                one = torch.from_numpy(gen_in(32, nm ** dim, npdt)).cuda()
                 d_in = one.view(32, -1).repeat(nelmt // 32, 1).reshape(-1).contiguous()
                 d_out = torch.empty(nelmt * nq ** dim, dtype=tdt, device="cuda")
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * reps)]
@@ -280,7 +293,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    import oracle  # checker + CPU baseline only
+    import oracle  # the checker of the result (and, below, the timed CPU baseline); never on the GPU path
     peak, peak_src = hbm_peak()
     st = torch.cuda.current_stream().cuda_stream
 
@@ -288,8 +301,8 @@ def main():
     e_begin, e_end = sharding.shard_range(NELMT_PER_GPU * world, rank, world)
     nelmt = e_end - e_begin
     assert nelmt == NELMT_PER_GPU
-    h_b = torch.from_numpy(oracle.gen_basis(NM, NQ))
-    h_one = torch.from_numpy(oracle.gen_in(1024, NM ** 3))       # reference generator (oracle port)
+    h_b = torch.from_numpy(gen_basis(NM, NQ))
+    h_one = torch.from_numpy(gen_in(1024, NM ** 3))              # the reference's synthetic input
     h_in = h_one.view(1024, -1).repeat(nelmt // 1024, 1).reshape(-1).contiguous().pin_memory()
     d_b = h_b.cuda()
     d_in = h_in.cuda()
@@ -429,7 +442,7 @@ def main():
     if ngpus == 1 and not args.no_sweep:
         del d_in, d_out
         torch.cuda.empty_cache()
-        sw = sweep(fe, torch, oracle, peak)
+        sw = sweep(fe, torch, peak)
 
     line = {
         "metric": METRIC, "value": value, "unit": "GDoF/s", "n_gpus": ngpus, "steps": args.steps,
