@@ -171,6 +171,21 @@ def sumsq(suf, x, n, result, scratch, stream=0):
     _check(name, getattr(lib(), name)(_vp(x), ctypes.c_size_t(int(n)), _vp(result), _vp(scratch), _vp(stream)))
 
 
+def iproduct(suf, nq, nelmt, bases, inp, out, weights=0, stream=0):
+    """IProductWRTBase; nq: tuple of 2 or 3 (equal entries); DEVICE pointers; weights may be 0 (none)"""
+    nm = [n - 1 for n in nq]
+    if len(nq) == 2:
+        name = f"b200fe_IProductWRTBaseQuad_{suf}"
+        rc = getattr(lib(), name)(_u(nm[0]), _u(nm[1]), _u(nq[0]), _u(nq[1]), _u(nelmt), _vp(bases[0]), _vp(bases[1]),
+                                  _vp(weights), _vp(inp), _vp(out), _vp(stream))
+    else:
+        name = f"b200fe_IProductWRTBaseHex_{suf}"
+        rc = getattr(lib(), name)(_u(nm[0]), _u(nm[1]), _u(nm[2]), _u(nq[0]), _u(nq[1]), _u(nq[2]), _u(nelmt),
+                                  _vp(bases[0]), _vp(bases[1]), _vp(bases[2]), _vp(weights), _vp(inp), _vp(out),
+                                  _vp(stream))
+    _check(name, rc)
+
+
 def bwdtrans_sumsq(suf, nq, nelmt, bases, inp, out, sumsq, scratch, stream=0):
     """operator + checksum in one call; nq: tuple of 2 or 3; all addresses are DEVICE pointers"""
     if len(nq) == 2:

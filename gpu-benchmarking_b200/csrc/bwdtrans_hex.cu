@@ -227,4 +227,41 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
     return release_basis_bank(g_bank, stream);
 }
 
+// ---- IProductWRTBase ---------------------------------------------------------------
+static int hex_iprod_switch(unsigned nq, unsigned nelmt, const T *in, const T *w, T *out, cudaStream_t s)
+{
+    switch (nq)
+    {
+#define ROWS_CASE(NQ, E, TH, R, V)                                                                              \
+    case NQ:                                                                                                 \
+        return launch_hex_iprod<T, NQ, E, TH, R>(nelmt, in, w, out, s);
+#define PIPE_CASE(NQ, E, TH, R, V)
+#define PREFER(NQ, BE)
+#define MMA_CASE(NQ, G, W, MB0, NB1)
+#include B200FE_ROWS_TABLE
+#undef ROWS_CASE
+#undef PIPE_CASE
+#undef PREFER
+#undef MMA_CASE
+    default:
+        return B200FE_EUNSUPPORTED;
+    }
+}
+
+template <>
+int run_iproduct_hex<T>(unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *b2, const T *w, const T *in, T *out,
+                         cudaStream_t stream)
+{
+    std::lock_guard<std::mutex> lock(g_bank_lock);
+    const T *bases[3]   = {b0, b1, b2};
+    const int counts[3] = {(int)((nq - 1) * nq), (int)((nq - 1) * nq), (int)((nq - 1) * nq)};
+    int rc = fill_basis_bank<T>(g_bank, 3, bases, counts, stream, (int)nq - 1, (int)nq); // transposed
+    if (rc)
+        return rc;
+    rc = hex_iprod_switch(nq, nelmt, in, w, out, stream);
+    if (rc)
+        return rc;
+    return release_basis_bank(g_bank, stream);
+}
+
 } // namespace b200fe

@@ -6,6 +6,7 @@
 
 #include "dispatch.h"
 #include "sumfac_generic.cuh"
+#include "sumfac_iprod.cuh"
 #include "sumfac_mma.cuh"
 #include "sumfac_mma32.cuh"
 #include "sumfac_nm1.cuh"
@@ -185,6 +186,60 @@ int launch_quad_mma(unsigned nelmt, const float *b0, const float *b1, const floa
         kernel<<<grid, WARPS * 32, C::SMEM, stream>>>(b0, b1, in, out, nelmt, ngroups, out_vec, nullptr);
     count_launch();
     t_last_backend = "mma";
+    return launch_status();
+}
+
+// ---- IProductWRTBase: the BwdTrans tile shape of the same nq, elements per CTA cut so the padded tiles fit ----
+template <typename Shape> constexpr bool iprod_fits()
+{
+    return Shape::SMEM <= 96 * 1024;
+}
+template <typename T, int NQ, int E> constexpr int quad_iprod_e()
+{
+    if constexpr (E <= 1 || iprod_fits<QuadIprodShape<T, NQ, E>>())
+        return E;
+    else
+        return quad_iprod_e<T, NQ, (E + 1) / 2>();
+}
+template <typename T, int NQ, int E> constexpr int hex_iprod_e()
+{
+    if constexpr (E <= 1 || iprod_fits<HexIprodShape<T, NQ, E>>())
+        return E;
+    else
+        return hex_iprod_e<T, NQ, (E + 1) / 2>();
+}
+
+template <typename T, int NQ, int E0, int THREADS, int R>
+int launch_quad_iprod(unsigned nelmt, const T *in, const T *w, T *out, cudaStream_t stream)
+{
+    constexpr int E = quad_iprod_e<T, NQ, E0>();
+    using C         = QuadIprodShape<T, NQ, E>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
+    auto kernel = iproduct_quad_rows_kernel<T, NQ, E, THREADS, R>;
+    int rc      = opt_in_smem(kernel, C::SMEM);
+    if (rc)
+        return rc;
+    const unsigned grid = (nelmt + E - 1) / E;
+    B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, w, out, nelmt));
+    count_launch();
+    t_last_backend = "iprod-rows";
+    return launch_status();
+}
+
+template <typename T, int NQ, int E0, int THREADS, int R>
+int launch_hex_iprod(unsigned nelmt, const T *in, const T *w, T *out, cudaStream_t stream)
+{
+    constexpr int E = hex_iprod_e<T, NQ, E0>();
+    using C         = HexIprodShape<T, NQ, E>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
+    auto kernel = iproduct_hex_rows_kernel<T, NQ, E, THREADS, R>;
+    int rc      = opt_in_smem(kernel, C::SMEM);
+    if (rc)
+        return rc;
+    const unsigned grid = (nelmt + E - 1) / E;
+    B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, w, out, nelmt));
+    count_launch();
+    t_last_backend = "iprod-rows";
     return launch_status();
 }
 

@@ -461,6 +461,42 @@ size_t b200fe_sumsq_scratch_bytes(void)
 }
 
 // ---- operator + checksum in one call: entry templates above ------------------
+#define IPROD_API(SUF, T)                                                                                    \
+    int b200fe_IProductWRTBaseQuad_##SUF(unsigned nm0, unsigned nm1, unsigned nq0, unsigned nq1,             \
+                                         unsigned nelmt, const T *basis0, const T *basis1,                   \
+                                         const T *weights, const T *in, T *out, void *stream)                \
+    {                                                                                                        \
+        if (!basis0 || !basis1 || !in || !out || nq0 < 2 || nq1 < 2)                                         \
+            return B200FE_EINVAL;                                                                            \
+        if (misaligned(basis0) || misaligned(basis1) || misaligned(in) || misaligned(out) ||                 \
+            (weights && misaligned(weights)))                                                                \
+            return B200FE_EALIGN;                                                                            \
+        if (nq0 != nq1 || nm0 + 1 != nq0 || nm1 + 1 != nq1 || nq0 > 32)                                      \
+            return B200FE_EUNSUPPORTED;                                                                      \
+        if (nelmt == 0)                                                                                      \
+            return B200FE_OK;                                                                                \
+        return run_iproduct_quad<T>(nq0, nelmt, basis0, basis1, weights, in, out, (cudaStream_t)stream);     \
+    }                                                                                                        \
+    int b200fe_IProductWRTBaseHex_##SUF(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nq0,              \
+                                        unsigned nq1, unsigned nq2, unsigned nelmt, const T *basis0,         \
+                                        const T *basis1, const T *basis2, const T *weights, const T *in,     \
+                                        T *out, void *stream)                                                \
+    {                                                                                                        \
+        if (!basis0 || !basis1 || !basis2 || !in || !out || nq0 < 2 || nq1 < 2 || nq2 < 2)                   \
+            return B200FE_EINVAL;                                                                            \
+        if (misaligned(basis0) || misaligned(basis1) || misaligned(basis2) || misaligned(in) ||              \
+            misaligned(out) || (weights && misaligned(weights)))                                             \
+            return B200FE_EALIGN;                                                                            \
+        if (nq0 != nq1 || nq1 != nq2 || nm0 + 1 != nq0 || nm1 + 1 != nq1 || nm2 + 1 != nq2 || nq0 > 16)      \
+            return B200FE_EUNSUPPORTED;                                                                      \
+        if (nelmt == 0)                                                                                      \
+            return B200FE_OK;                                                                                \
+        return run_iproduct_hex<T>(nq0, nelmt, basis0, basis1, basis2, weights, in, out,                     \
+                                   (cudaStream_t)stream);                                                    \
+    }
+IPROD_API(f64, double)
+IPROD_API(f32, float)
+
 #define FUSED_API(SUF, T)                                                                                    \
     int b200fe_bwdtrans_quad_sumsq_##SUF(unsigned nq0, unsigned nq1, unsigned nelmt, const T *basis0,        \
                                          const T *basis1, const T *in, T *out, double *sumsq, void *scratch, \

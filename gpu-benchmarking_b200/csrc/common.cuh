@@ -193,8 +193,24 @@ __global__ void fill_bank_kernel(T *__restrict__ bank, const T *__restrict__ b0,
         bank[i] = i < n0 ? b0[i] : (i < n0 + n1 ? b1[i - n0] : b2[i - n0 - n1]);
 }
 
+// transposed fill for IProductWRTBase: bank[d][i*nm + p] = B_d[p*nq + i] (all directions share nm, nq)
 template <typename T>
-inline int fill_basis_bank(BankGuard &g, int nb, const T *const *basis, const int *count, cudaStream_t stream)
+__global__ void fill_bank_transposed_kernel(T *__restrict__ bank, const T *__restrict__ b0, const T *__restrict__ b1,
+                                            const T *__restrict__ b2, int nb, int nm, int nq)
+{
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int per = nm * nq;
+    for (int t = threadIdx.x; t < nb * per; t += blockDim.x)
+    {
+        const int d = t / per, r = t - d * per, i = r / nm, p = r - i * nm;
+        const T *b = d == 0 ? b0 : (d == 1 ? b1 : b2);
+        bank[t]    = b[p * nq + i];
+    }
+}
+
+template <typename T>
+inline int fill_basis_bank(BankGuard &g, int nb, const T *const *basis, const int *count, cudaStream_t stream,
+                           int transpose_nm = 0, int transpose_nq = 0)
 {
     int dev = 0;
     B200FE_CUDA_TRY(cudaGetDevice(&dev));
@@ -212,8 +228,14 @@ inline int fill_basis_bank(BankGuard &g, int nb, const T *const *basis, const in
     const int n0 = count[0], n1 = nb > 1 ? count[1] : 0, n2 = nb > 2 ? count[2] : 0;
     if (n0 + n1 + n2 > kBasisBankElems)
         return B200FE_EUNSUPPORTED;
-    fill_bank_kernel<T><<<1, 256, 0, stream>>>(static_cast<T *>(g.bank[dev]), basis[0], n0, nb > 1 ? basis[1] : basis[0],
-                                               n1, nb > 2 ? basis[2] : basis[0], n2);
+    if (transpose_nm > 0)
+        fill_bank_transposed_kernel<T><<<1, 256, 0, stream>>>(static_cast<T *>(g.bank[dev]), basis[0],
+                                                              nb > 1 ? basis[1] : basis[0],
+                                                              nb > 2 ? basis[2] : basis[0], nb, transpose_nm,
+                                                              transpose_nq);
+    else
+        fill_bank_kernel<T><<<1, 256, 0, stream>>>(static_cast<T *>(g.bank[dev]), basis[0], n0,
+                                                   nb > 1 ? basis[1] : basis[0], n1, nb > 2 ? basis[2] : basis[0], n2);
     count_launch();
     return launch_status();
 }

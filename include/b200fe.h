@@ -256,6 +256,31 @@ int b200fe_bwdtrans_hex_sumsq_f32(unsigned nq0, unsigned nq1, unsigned nq2, unsi
                                   const float *basis1, const float *basis2, const float *in, float *out,
                                   double *sumsq, void *scratch, void *stream);
 
+/* ---- IProductWRTBase (extension) ---------------------------
+ * The transpose of BwdTrans -- named in the north star, not present in the reference:
+ *   quad  out[e][q][p]    = sum_j B1[q][j] ( sum_i B0[p][i] (w*in)[e][j][i] )
+ *   hex   out[e][r][q][p] = sum_k B2[r][k] ( sum_j B1[q][j] ( sum_i B0[p][i] (w*in)[e][k][j][i] ) )
+ * in: nelmt*nq^d quadrature values, out: nelmt*nm^d modes, both element-major; basis as for
+ * BwdTrans (B[p*nq + i]); weights: the quadrature metric (Jacobian * weights), one value per
+ * quadrature point in the layout of `in`, or NULL for 1.  Sums run in ascending index order
+ * from 0 with fused multiply-adds, w*in is one rounded product.  Supported: nq0 == nq1 (== nq2),
+ * nm = nq - 1, nq <= 32 (quad) / 15 (hex); other shapes return B200FE_EUNSUPPORTED.
+ * Satisfies <IProduct(u), c> == <w*u, BwdTrans(c)> to rounding (tests/test_iproduct_gpu.py). */
+int b200fe_IProductWRTBaseQuad_f64(unsigned nm0, unsigned nm1, unsigned nq0, unsigned nq1, unsigned nelmt,
+                                   const double *basis0, const double *basis1, const double *weights,
+                                   const double *in, double *out, void *stream);
+int b200fe_IProductWRTBaseQuad_f32(unsigned nm0, unsigned nm1, unsigned nq0, unsigned nq1, unsigned nelmt,
+                                   const float *basis0, const float *basis1, const float *weights,
+                                   const float *in, float *out, void *stream);
+int b200fe_IProductWRTBaseHex_f64(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nq0, unsigned nq1,
+                                  unsigned nq2, unsigned nelmt, const double *basis0, const double *basis1,
+                                  const double *basis2, const double *weights, const double *in, double *out,
+                                  void *stream);
+int b200fe_IProductWRTBaseHex_f32(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nq0, unsigned nq1,
+                                  unsigned nq2, unsigned nelmt, const float *basis0, const float *basis1,
+                                  const float *basis2, const float *weights, const float *in, float *out,
+                                  void *stream);
+
 /* ---- host-buffer operator (end-to-end path) --------------------------------------
  * Whole-operator call on HOST arrays, as an application holding its field on
  * the CPU would issue it: the element range is cut into chunks that are

@@ -119,6 +119,34 @@ def bwdtrans_hex(nq0, nq1, nq2, nelmt, b0, b1, b2, inp, coa=False, use_fma=True)
     return out
 
 
+# ---- IProductWRTBase (not in the reference; pinned through the adjoint identity) ------------
+
+def iproduct_quad(nq0, nq1, nelmt, b0, b1, inp, w=None, use_fma=True):
+    nm0, nm1 = nq0 - 1, nq1 - 1
+    inp = np.ascontiguousarray(inp)
+    assert inp.size == nelmt * nq0 * nq1 and nq0 <= 64 and nq1 <= 64
+    out = np.empty(int(nelmt) * nm0 * nm1, dtype=inp.dtype)
+    w_arr = np.ascontiguousarray(w, dtype=inp.dtype) if w is not None else None  # keep alive across the call
+    wp = _p(w_arr) if w_arr is not None else ctypes.c_void_p(None)
+    getattr(lib(), f"oracle_iproduct_quad_{_suf(inp.dtype)}")(
+        _u(nm0), _u(nm1), _u(nq0), _u(nq1), _z(nelmt), _p(b0), _p(b1), wp, _p(inp), _p(out),
+        ctypes.c_int(1 if use_fma else 0))
+    return out
+
+
+def iproduct_hex(nq0, nq1, nq2, nelmt, b0, b1, b2, inp, w=None, use_fma=True):
+    nm0, nm1, nm2 = nq0 - 1, nq1 - 1, nq2 - 1
+    inp = np.ascontiguousarray(inp)
+    assert inp.size == nelmt * nq0 * nq1 * nq2 and max(nq0, nq1, nq2) <= 16
+    out = np.empty(int(nelmt) * nm0 * nm1 * nm2, dtype=inp.dtype)
+    w_arr = np.ascontiguousarray(w, dtype=inp.dtype) if w is not None else None
+    wp = _p(w_arr) if w_arr is not None else ctypes.c_void_p(None)
+    getattr(lib(), f"oracle_iproduct_hex_{_suf(inp.dtype)}")(
+        _u(nm0), _u(nm1), _u(nm2), _u(nq0), _u(nq1), _u(nq2), _z(nelmt), _p(b0), _p(b1), _p(b2), wp,
+        _p(inp), _p(out), ctypes.c_int(1 if use_fma else 0))
+    return out
+
+
 # ---- benchmark01-03 ------------------------------------------------------------
 
 def set_data(n, dtype=np.float64, second=False, fused=False):

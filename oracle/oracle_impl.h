@@ -265,6 +265,94 @@ void FN(oracle_bwdtrans_hex_coa)(unsigned nm0, unsigned nm1, unsigned nm2,
     }
 }
 
+/* ---- IProductWRTBase: NOT in the reference ------------------------
+ * The transpose of BwdTrans, named in BASELINE.json's north_star and absent from the
+ * reference sources, so there is no reference loop to restate and no golden vector:
+ * PARITY UNPINNED against the reference.  It is pinned instead to the pinned BwdTrans
+ * through the adjoint identity  <IProduct(u), c> == <u, BwdTrans(c)>  (tests).
+ * Definition (Nektar++ StdExpansion::IProductWRTBase on a tensor-product element, with the
+ * quadrature metric w = Jacobian * weights applied first; w may be NULL = 1):
+ *   quad  out[e][q][p]    = sum_j B1[q][j] ( sum_i B0[p][i] (w*in)[e][j][i] )
+ *   hex   out[e][r][q][p] = sum_k B2[r][k] ( sum_j B1[q][j] ( sum_i B0[p][i] (w*in)[e][k][j][i] ) )
+ * every sum accumulated in ascending index order from 0 with the same multiply-add as
+ * BwdTrans (use_fma as there); w*in is one rounded product. */
+void FN(oracle_iproduct_quad)(unsigned nm0, unsigned nm1, unsigned nq0, unsigned nq1, size_t nelmt,
+                              const T *basis0, const T *basis1, const T *w, const T *in, T *out, int use_fma)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t e = 0; e < nelmt; ++e)
+    {
+        T mid[64 * 64]; /* [p][j] */
+        const T *x  = in + e * (size_t)nq0 * nq1;
+        const T *we = w ? w + e * (size_t)nq0 * nq1 : 0;
+        for (unsigned j = 0; j < nq1; ++j)
+            for (unsigned p = 0; p < nm0; ++p)
+            {
+                T tmp = 0;
+                for (unsigned i = 0; i < nq0; ++i)
+                {
+                    volatile T xi = we ? x[j * nq0 + i] * we[j * nq0 + i] : x[j * nq0 + i];
+                    tmp = FN(madd)(xi, basis0[p * nq0 + i], tmp, use_fma);
+                }
+                mid[p * nq1 + j] = tmp;
+            }
+        for (unsigned q = 0; q < nm1; ++q)
+            for (unsigned p = 0; p < nm0; ++p)
+            {
+                T tmp = 0;
+                for (unsigned j = 0; j < nq1; ++j)
+                    tmp = FN(madd)(mid[p * nq1 + j], basis1[q * nq1 + j], tmp, use_fma);
+                out[e * (size_t)nm0 * nm1 + q * nm0 + p] = tmp;
+            }
+    }
+}
+
+void FN(oracle_iproduct_hex)(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nq0, unsigned nq1, unsigned nq2,
+                             size_t nelmt, const T *basis0, const T *basis1, const T *basis2, const T *w,
+                             const T *in, T *out, int use_fma)
+{
+    const size_t nqTot = (size_t)nq0 * nq1 * nq2, nmTot = (size_t)nm0 * nm1 * nm2;
+#pragma omp parallel for schedule(static)
+    for (size_t e = 0; e < nelmt; ++e)
+    {
+        T s1[16 * 16 * 16]; /* [p][k][j] */
+        T s2[16 * 16 * 16]; /* [q][p][k] */
+        const T *x  = in + e * nqTot;
+        const T *we = w ? w + e * nqTot : 0;
+        for (unsigned k = 0; k < nq2; ++k)
+            for (unsigned j = 0; j < nq1; ++j)
+                for (unsigned p = 0; p < nm0; ++p)
+                {
+                    T tmp = 0;
+                    for (unsigned i = 0; i < nq0; ++i)
+                    {
+                        const size_t c = ((size_t)k * nq1 + j) * nq0 + i;
+                        volatile T xi  = we ? x[c] * we[c] : x[c];
+                        tmp = FN(madd)(xi, basis0[p * nq0 + i], tmp, use_fma);
+                    }
+                    s1[(p * nq2 + k) * nq1 + j] = tmp;
+                }
+        for (unsigned q = 0; q < nm1; ++q)
+            for (unsigned p = 0; p < nm0; ++p)
+                for (unsigned k = 0; k < nq2; ++k)
+                {
+                    T tmp = 0;
+                    for (unsigned j = 0; j < nq1; ++j)
+                        tmp = FN(madd)(s1[(p * nq2 + k) * nq1 + j], basis1[q * nq1 + j], tmp, use_fma);
+                    s2[(q * nm0 + p) * nq2 + k] = tmp;
+                }
+        for (unsigned r = 0; r < nm2; ++r)
+            for (unsigned q = 0; q < nm1; ++q)
+                for (unsigned p = 0; p < nm0; ++p)
+                {
+                    T tmp = 0;
+                    for (unsigned k = 0; k < nq2; ++k)
+                        tmp = FN(madd)(s2[(q * nm0 + p) * nq2 + k], basis2[r * nq2 + k], tmp, use_fma);
+                    out[e * nmTot + ((size_t)r * nm1 + q) * nm0 + p] = tmp;
+                }
+    }
+}
+
 /* ---- benchmark01: L2-norm reduction -------------------------------------- */
 
 /* data[i] = i%13 + (0.2 + 1e-5*(i%100191)): integer % on unsigned, double

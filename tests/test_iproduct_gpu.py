@@ -1,0 +1,105 @@
+"""IProductWRTBase through the C ABI.
+
+The operator is not in the reference, so it has no golden vector: the oracle's restatement is pinned to the
+(pinned) BwdTrans through the adjoint identity <IProduct(u), c> == <w*u, BwdTrans(c)>
+(tests/test_oracle_golden.py::test_iproduct_oracle_is_the_adjoint_of_bwdtrans, CPU), and the CUDA kernels are
+held bit for bit to that oracle here."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from tests import gpu_util
+    return gpu_util
+
+
+def run(G, suf, dim, nq, nelmt, b, inp, w):
+    import torch
+    tdt = torch.float64 if suf == "f64" else torch.float32
+    d_b = [G.dev(x) for x in b]
+    d_in = G.dev(inp)
+    d_w = G.dev(w) if w is not None else None
+    nm = nq - 1
+    d_out = torch.full((nelmt * nm ** dim + 2,), float("nan"), dtype=tdt, device="cuda")
+    G.fe.iproduct(suf, (nq,) * dim, nelmt, [x.data_ptr() for x in d_b], d_in.data_ptr(),
+                  d_out.data_ptr() + d_out.element_size(), weights=d_w.data_ptr() if d_w is not None else 0,
+                  stream=torch.cuda.current_stream().cuda_stream)
+    got = G.host(d_out)
+    assert np.isnan(got[0]) and np.isnan(got[-1])          # nothing written outside
+    return got[1:-1]
+
+
+@pytest.mark.parametrize("suf", ["f64", "f32"])
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("nq", [2, 3, 4, 5, 6, 8, 10, 12, 14, 16, 32])
+def test_quad_bit_exact_with_oracle(G, suf, weighted, nq):
+    dt = G.NP[suf]
+    rng = np.random.default_rng(1100 + nq)
+    nm = nq - 1
+    b = [rng.standard_normal(nm * nq).astype(dt) for _ in range(2)]
+    for nelmt in (1, 77, 2049):
+        inp = rng.standard_normal(nelmt * nq * nq).astype(dt)
+        w = rng.random(nelmt * nq * nq).astype(dt) + dt(0.5) if weighted else None
+        want = oracle.iproduct_quad(nq, nq, nelmt, b[0], b[1], inp, w)
+        got = run(G, suf, 2, nq, nelmt, b, inp, w)
+        assert np.array_equal(got, want), (nq, nelmt, G.rel_max(got, want))
+
+
+@pytest.mark.parametrize("suf", ["f64", "f32"])
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("nq", [2, 3, 4, 5, 6, 8, 10, 12, 15])
+def test_hex_bit_exact_with_oracle(G, suf, weighted, nq):
+    dt = G.NP[suf]
+    rng = np.random.default_rng(1200 + nq)
+    nm = nq - 1
+    b = [rng.standard_normal(nm * nq).astype(dt) for _ in range(3)]
+    for nelmt in (1, 37, 300) if nq <= 10 else (1, 19):
+        inp = rng.standard_normal(nelmt * nq ** 3).astype(dt)
+        w = rng.random(nelmt * nq ** 3).astype(dt) + dt(0.5) if weighted else None
+        want = oracle.iproduct_hex(nq, nq, nq, nelmt, *b, inp, w)
+        got = run(G, suf, 3, nq, nelmt, b, inp, w)
+        assert np.array_equal(got, want), (nq, nelmt, G.rel_max(got, want))
+
+
+@pytest.mark.parametrize("dim,nq,nelmt", [(2, 8, 1048576), (3, 8, 131072)])
+def test_adjoint_of_the_device_bwdtrans_at_baseline_size(G, dim, nq, nelmt):
+    """<IProduct(u), c> == <u, BwdTrans(c)> with both operators on the device, 64 Mi quadrature points"""
+    import torch
+    nm = nq - 1
+    b = torch.randn(nm * nq, dtype=torch.float64, device="cuda")
+    u = torch.randn(nelmt * nq ** dim, dtype=torch.float64, device="cuda")
+    c = torch.randn(nelmt * nm ** dim, dtype=torch.float64, device="cuda")
+    ip = torch.empty_like(c)
+    bt = torch.empty_like(u)
+    st = torch.cuda.current_stream().cuda_stream
+    G.fe.iproduct("f64", (nq,) * dim, nelmt, [b.data_ptr()] * dim, u.data_ptr(), ip.data_ptr(), stream=st)
+    if dim == 2:
+        G.fe.bwdtrans_quad("BwdTransQuadKernel_QP_Shared", "f64", nq, nq, nelmt, b.data_ptr(), b.data_ptr(), c.data_ptr(),
+                           bt.data_ptr(), stream=st)
+    else:
+        G.fe.bwdtrans_hex("BwdTransHexKernel_QP_Shared", "f64", nq, nq, nq, nelmt, b.data_ptr(), b.data_ptr(),
+                          b.data_ptr(), c.data_ptr(), bt.data_ptr(), stream=st)
+    lhs, rhs = float(torch.dot(ip, c)), float(torch.dot(u, bt))
+    assert abs(lhs - rhs) <= 1e-10 * max(abs(lhs), abs(rhs), float(torch.linalg.norm(ip) * torch.linalg.norm(c)) * 1e-2)
+
+
+def test_argument_errors(G):
+    import torch
+    t = torch.zeros(4096, dtype=torch.float64, device="cuda")
+    p = t.data_ptr()
+    with pytest.raises(G.fe.B200feError) as e:   # unequal nq: outside the instantiated shapes
+        G.fe.lib().b200fe_IProductWRTBaseQuad_f64  # symbol exists
+        G.fe.iproduct("f64", (4, 6), 8, [p, p], p, p)
+    assert e.value.code == G.fe.E_UNSUPPORTED
+    with pytest.raises(G.fe.B200feError) as e:
+        G.fe.iproduct("f64", (4, 4), 8, [p, 0], p, p)
+    assert e.value.code == G.fe.E_INVAL
+    G.fe.iproduct("f64", (4, 4, 4), 0, [p, p, p], p, p)  # empty: no-op

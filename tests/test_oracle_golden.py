@@ -184,3 +184,38 @@ def test_f32_variants_run_and_track_f64():
     o32 = oracle.bwdtrans_quad(nq, nq, nelmt, b32, b32, i32)
     assert o32.dtype == np.float32
     assert np.abs(o32 - o64).max() / np.abs(o64).max() < 1e-5
+
+
+# ---- IProductWRTBase: not in the reference, pinned through the adjoint identity --------------------
+
+@pytest.mark.parametrize("dt,tol", [(np.float64, 1e-13), (np.float32, 2e-6)])
+@pytest.mark.parametrize("nq", [2, 3, 4, 7, 8, 10])
+def test_iproduct_oracle_is_the_adjoint_of_bwdtrans(dt, tol, nq):
+    """<IProduct(u), c> == <w*u, BwdTrans(c)> for random u, c, w: ties the unpinned operator to the pinned one"""
+    rng = np.random.default_rng(5000 + nq)
+    nm, nelmt = nq - 1, 9
+    b = [rng.standard_normal(nm * nq).astype(dt) for _ in range(3)]
+    for dim in (2, 3):
+        u = rng.standard_normal(nelmt * nq ** dim).astype(dt)
+        c = rng.standard_normal(nelmt * nm ** dim).astype(dt)
+        w = (rng.random(nelmt * nq ** dim) + 0.5).astype(dt)
+        if dim == 2:
+            ip = oracle.iproduct_quad(nq, nq, nelmt, b[0], b[1], u, w)
+            bt = oracle.bwdtrans_quad(nq, nq, nelmt, b[0], b[1], c)
+        else:
+            ip = oracle.iproduct_hex(nq, nq, nq, nelmt, *b, u, w)
+            bt = oracle.bwdtrans_hex(nq, nq, nq, nelmt, *b, c)
+        lhs = np.dot(ip.astype(np.float64), c.astype(np.float64))
+        rhs = np.dot((u * w).astype(np.float64), bt.astype(np.float64))
+        scale = np.linalg.norm(ip.astype(np.float64)) * np.linalg.norm(c.astype(np.float64))
+        assert abs(lhs - rhs) <= tol * scale
+
+
+def test_iproduct_oracle_known_answer():
+    """nq = 2 by hand: one mode per direction, out = sum_ij B0[i] B1[j] w in"""
+    b0, b1 = np.array([2.0, 3.0]), np.array([5.0, 7.0])
+    x = np.array([1.0, 10.0, 100.0, 1000.0])     # [j][i]
+    w = np.array([1.0, 0.5, 0.25, 2.0])
+    want = sum(b0[i] * b1[j] * x[2 * j + i] * w[2 * j + i] for i in range(2) for j in range(2))
+    got = oracle.iproduct_quad(2, 2, 1, b0, b1, x, w)
+    assert got.shape == (1,) and got[0] == want
