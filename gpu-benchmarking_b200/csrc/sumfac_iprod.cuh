@@ -23,6 +23,33 @@ template <typename T, int NQ, int THREADS>
 __device__ __forceinline__ void iprod_tile_load(T *__restrict__ s, const T *__restrict__ g, const T *__restrict__ w,
                                                 int count, int tid)
 {
+    using V         = typename Vec16<T>::type;
+    constexpr int W = Vec16<T>::W;
+    // 16-byte loads where the slab allows it (a vector never straddles a row when W divides nq)
+    const bool vec = (NQ % W == 0) && ((reinterpret_cast<uintptr_t>(g) & 15u) == 0) &&
+                     (!w || (reinterpret_cast<uintptr_t>(w) & 15u) == 0);
+    if (vec)
+    {
+        const int nv = count / W; // count = ne * nq^d is a multiple of W here
+        for (int c = tid; c < nv; c += THREADS)
+        {
+            V v         = ld_stream(reinterpret_cast<const V *>(g) + c);
+            T *pv       = reinterpret_cast<T *>(&v);
+            if (w)
+            {
+                const V u   = ld_stream(reinterpret_cast<const V *>(w) + c);
+                const T *pu = reinterpret_cast<const T *>(&u);
+#pragma unroll
+                for (int k = 0; k < W; ++k)
+                    pv[k] = pv[k] * pu[k];
+            }
+            const int e0 = c * W, row = e0 / NQ, col = e0 - row * NQ;
+#pragma unroll
+            for (int k = 0; k < W; ++k)
+                s[row * (NQ + 1) + col + k] = pv[k];
+        }
+        return;
+    }
     for (int c = tid; c < count; c += THREADS)
     {
         const int row = c / NQ, col = c - row * NQ;
@@ -31,6 +58,13 @@ __device__ __forceinline__ void iprod_tile_load(T *__restrict__ s, const T *__re
             v = v * ld_stream(w + c);
         s[row * (NQ + 1) + col] = v;
     }
+}
+
+// contraction shape: rows fully in registers with immediate constant-bank operands for the small nq,
+// the p-loop form beyond (sumfac_rows.cuh, V = 0 / 1)
+template <int NQ> constexpr int iprod_v()
+{
+    return NQ <= 12 ? 0 : 1;
 }
 
 template <typename T, int NQ, int E> struct QuadIprodShape
@@ -61,7 +95,7 @@ __global__ void __launch_bounds__(THREADS)
     grid_dependency_wait();
     __syncthreads();
     // direction 0: rows (e, j) of nq values -> nm outputs p, to mid[e][p][j]
-    contraction_pass<T, NQ, NM, C::B0, RS, THREADS, R, 1, E * NQ, false>(
+    contraction_pass<T, NQ, NM, C::B0, RS, THREADS, R, iprod_v<NQ>(), E * NQ, false>(
         ne * NQ, tid, [&](int row) { return sA + row * RS; },
         [&](int row) {
             const int e = row / NQ, j = row - e * NQ;
@@ -69,7 +103,7 @@ __global__ void __launch_bounds__(THREADS)
         });
     __syncthreads();
     // direction 1: rows (e, p) of nq values -> nm outputs q, to the staged out[e][q][p]
-    contraction_pass<T, NQ, NM, C::B1, NM, THREADS, R, 1, E * NM, false>(
+    contraction_pass<T, NQ, NM, C::B1, NM, THREADS, R, iprod_v<NQ>(), E * NM, false>(
         ne * NM, tid, [&](int row) { return sB + row * RS; },
         [&](int row) {
             const int e = row / NM, p = row - e * NM;
@@ -110,7 +144,7 @@ __global__ void __launch_bounds__(THREADS)
     grid_dependency_wait();
     __syncthreads();
     // direction 0: rows (e, k, j) -> outputs p, to s1[e][p][k][j]
-    contraction_pass<T, NQ, NM, C::B0, NQ * RS, THREADS, R, 1, E * NQ2, false>(
+    contraction_pass<T, NQ, NM, C::B0, NQ * RS, THREADS, R, iprod_v<NQ>(), E * NQ2, false>(
         ne * NQ2, tid, [&](int row) { return sA + row * RS; },
         [&](int row) {
             const int e = row / NQ2, kj = row - e * NQ2, k = kj / NQ, j = kj - k * NQ;
@@ -118,7 +152,7 @@ __global__ void __launch_bounds__(THREADS)
         });
     __syncthreads();
     // direction 1: rows (e, p, k) -> outputs q, to s2[e][q][p][k]
-    contraction_pass<T, NQ, NM, C::B1, NM * RS, THREADS, R, 1, E * NM * NQ, false>(
+    contraction_pass<T, NQ, NM, C::B1, NM * RS, THREADS, R, iprod_v<NQ>(), E * NM * NQ, false>(
         ne * NM * NQ, tid, [&](int row) { return sB + row * RS; },
         [&](int row) {
             const int e = row / (NM * NQ), pk = row - e * (NM * NQ), p = pk / NQ, k = pk - p * NQ;
@@ -127,7 +161,7 @@ __global__ void __launch_bounds__(THREADS)
     __syncthreads();
     // direction 2: rows (e, q, p) -> outputs r, straight to out[e][r][q][p] (lanes along p: coalesced)
     T *gout = out + e0 * C::NM3;
-    contraction_pass<T, NQ, NM, C::B2, NM2, THREADS, R, 1, E * NM2, true>(
+    contraction_pass<T, NQ, NM, C::B2, NM2, THREADS, R, iprod_v<NQ>(), E * NM2, true>(
         ne * NM2, tid, [&](int row) { return sA + row * RS; },
         [&](int row) {
             const int e = row / NM2, qp = row - e * NM2;
