@@ -246,6 +246,44 @@ def sweep(fe, torch, peak, reps=5):
     return out
 
 
+def sweep_coa(fe, torch, peak, reps=5):
+    """the warp-interleaved (`_Coa`) entry points at ~64 Mi quadrature points (same algorithmic bytes)"""
+    out = []
+    st = torch.cuda.current_stream().cuda_stream
+    for dim, nqs, kern in ((2, (2, 4, 8, 10, 16), "BwdTransQuadKernel_Coa"), (3, (2, 4, 6, 8), "BwdTransHexKernel_Coa")):
+        for suf, tdt, size in (("f64", torch.float64, 8), ("f32", torch.float32, 4)):
+            for nq in nqs:
+                nm = nq - 1
+                nelmt = max(32, ((1 << 26) // nq ** dim) // 32 * 32)
+                b = torch.from_numpy(gen_basis(nm, nq, "float64")).to(tdt).cuda()
+                d_in = torch.randn(nelmt * nm ** dim, dtype=tdt, device="cuda")
+                d_out = torch.empty(nelmt * nq ** dim, dtype=tdt, device="cuda")
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * reps)]
+
+                def call():
+                    if dim == 2:
+                        fe.bwdtrans_quad(kern, suf, nq, nq, nelmt, b.data_ptr(), b.data_ptr(), d_in.data_ptr(),
+                                         d_out.data_ptr(), stream=st)
+                    else:
+                        fe.bwdtrans_hex(kern, suf, nq, nq, nq, nelmt, b.data_ptr(), b.data_ptr(), b.data_ptr(),
+                                        d_in.data_ptr(), d_out.data_ptr(), stream=st)
+                for _ in range(2):
+                    call()
+                for r in range(reps):
+                    ev[2 * r].record()
+                    call()
+                    ev[2 * r + 1].record()
+                torch.cuda.synchronize()
+                ms = min(ev[2 * r].elapsed_time(ev[2 * r + 1]) for r in range(reps))
+                gbs = 1e-9 * nelmt * alg_bytes_per_elem(dim, nq, size) / (ms * 1e-3)
+                out.append({"op": ("quad" if dim == 2 else "hex") + "_coa", "nq": nq, "dtype": suf, "nelmt": nelmt,
+                            "backend": fe.last_backend(), "ms": round(ms, 4),
+                            "gdof_s": round(1e-9 * nelmt * nm ** dim / (ms * 1e-3), 2), "gb_s": round(gbs, 1),
+                            "hbm_frac": round(gbs / peak, 4)})
+                del d_in, d_out
+    return out
+
+
 def sweep_iproduct(fe, torch, peak, reps=5):
     """IProductWRTBase, unweighted, at ~64 Mi quadrature points: same algorithmic bytes as BwdTrans"""
     import numpy as np
@@ -472,12 +510,13 @@ def main():
     cpu = None
     if ngpus == 1 and not args.no_cpu:
         cpu = cpu_reference_rate(sample_target_s=12.0)
-    sw = sw_ip = None
+    sw = sw_ip = sw_coa = None
     if ngpus == 1 and not args.no_sweep:
         del d_in, d_out
         torch.cuda.empty_cache()
         sw = sweep(fe, torch, peak)
         sw_ip = sweep_iproduct(fe, torch, peak)
+        sw_coa = sweep_coa(fe, torch, peak)
 
     line = {
         "metric": METRIC, "value": value, "unit": "GDoF/s", "n_gpus": ngpus, "steps": args.steps,
@@ -490,6 +529,7 @@ def main():
     if sw is not None:
         line["sweep"] = sw
         line["sweep_iproduct"] = sw_ip
+        line["sweep_coa"] = sw_coa
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

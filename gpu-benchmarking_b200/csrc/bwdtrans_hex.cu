@@ -73,6 +73,27 @@ static int hex_mma_switch(unsigned nq, unsigned nelmt, const T *b0, const T *b1,
     }
 }
 
+// interleaved layout through the rows passes (tile shape of the element-major rows entry)
+static int hex_rowscoa_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
+{
+    switch (nq)
+    {
+#define ROWS_CASE(NQ, E, TH, R, V)                                                                              \
+    case NQ:                                                                                                 \
+        return launch_hex_rowscoa<T, NQ, E, TH, R, V>(nelmt, in, out, s);
+#define PIPE_CASE(NQ, E, TH, R, V)
+#define PREFER(NQ, BE)
+#define MMA_CASE(NQ, G, W, MB0, NB1)
+#include B200FE_ROWS_TABLE
+#undef ROWS_CASE
+#undef PIPE_CASE
+#undef PREFER
+#undef MMA_CASE
+    default:
+        return B200FE_EUNSUPPORTED;
+    }
+}
+
 // what the table offers for this nq: bit 0 rows, bit 1 pipe, bit 2 mma; *preferred = default routing
 static int hex_table_lookup(unsigned nq, Backend *preferred)
 {
@@ -184,7 +205,7 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
         if (!regular)
             be = Backend::Generic;
         else if (coa)
-            be = nq0 <= kHexTpeMaxNq ? Backend::Tpe : Backend::Generic;
+            be = nq0 <= kHexTpeMaxNq ? Backend::Tpe : ((have & 1) ? Backend::Rows : Backend::Generic);
         else
             be = preferred;
         // the bulk-copy ring needs a 16-byte aligned slab; otherwise take the plain-load twin
@@ -200,8 +221,8 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
         t_last_backend = "generic";
         return launch_hex_generic<T>(nm0, nm1, nm2, nq0, nq1, nq2, nelmt, b0, b1, b2, in, out, coa, stream);
     }
-    if (!regular || ((be == Backend::Rows || be == Backend::Pipe || be == Backend::Mma || be == Backend::Nm1) && coa) ||
-        (be == Backend::Tpe && !coa))
+    if (!regular || ((be == Backend::Pipe || be == Backend::Mma || be == Backend::Nm1) && coa) ||
+        (be == Backend::Tpe && !coa) || (be == Backend::Rows && !(have & 1)))
         return B200FE_EUNSUPPORTED;
     if (be == Backend::Pipe && (!(have & 2) || !aligned16(in)))
         return B200FE_EUNSUPPORTED;
@@ -217,7 +238,7 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
     if (rc)
         return rc;
     if (be == Backend::Rows)
-        rc = hex_rows_switch(nq0, nelmt, in, out, stream);
+        rc = coa ? hex_rowscoa_switch(nq0, nelmt, in, out, stream) : hex_rows_switch(nq0, nelmt, in, out, stream);
     else if (be == Backend::Pipe)
         rc = hex_pipe_switch(nq0, nelmt, in, out, stream);
     else

@@ -11,6 +11,7 @@
 #include "sumfac_mma32.cuh"
 #include "sumfac_nm1.cuh"
 #include "sumfac_rows.cuh"
+#include "sumfac_rows_coa.cuh"
 #include "sumfac_tpe.cuh"
 
 namespace b200fe
@@ -186,6 +187,49 @@ int launch_quad_mma(unsigned nelmt, const float *b0, const float *b1, const floa
         kernel<<<grid, WARPS * 32, C::SMEM, stream>>>(b0, b1, in, out, nelmt, ngroups, out_vec, nullptr);
     count_launch();
     t_last_backend = "mma";
+    return launch_status();
+}
+
+// ---- interleaved layout through the rows passes: E = power of two dividing 32, whole 32-byte sectors,
+// as close to the tuned element-major tile as that allows
+template <typename T, int E0> constexpr int coa_e()
+{
+    constexpr int emin = 32 / (int)sizeof(T); // 4 doubles / 8 floats = one sector
+    int e              = emin;
+    while (e * 2 <= E0 && e * 2 <= 32)
+        e *= 2;
+    return e;
+}
+template <typename T, int NQ, int E0, int THREADS, int R, int V>
+int launch_quad_rowscoa(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
+{
+    constexpr int E = coa_e<T, E0>();
+    using C         = QuadRows<T, NQ, E, THREADS, R, V>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
+    auto kernel = bwdtrans_quad_rowscoa_kernel<T, NQ, E, THREADS, R, V>;
+    int rc      = opt_in_smem(kernel, C::SMEM);
+    if (rc)
+        return rc;
+    const unsigned grid = nelmt / E; // nelmt % 32 == 0
+    B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt));
+    count_launch();
+    t_last_backend = "rows-coa";
+    return launch_status();
+}
+template <typename T, int NQ, int E0, int THREADS, int R, int V>
+int launch_hex_rowscoa(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
+{
+    constexpr int E = coa_e<T, E0>();
+    using C         = HexRows<T, NQ, E, THREADS, R, V>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
+    auto kernel = bwdtrans_hex_rowscoa_kernel<T, NQ, E, THREADS, R, V>;
+    int rc      = opt_in_smem(kernel, C::SMEM);
+    if (rc)
+        return rc;
+    const unsigned grid = nelmt / E;
+    B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt));
+    count_launch();
+    t_last_backend = "rows-coa";
     return launch_status();
 }
 

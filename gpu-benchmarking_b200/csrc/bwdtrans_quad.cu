@@ -73,6 +73,27 @@ static int quad_mma_switch(unsigned nq, unsigned nelmt, const T *b0, const T *b1
     }
 }
 
+// interleaved layout through the rows passes (tile shape of the element-major rows entry)
+static int quad_rowscoa_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
+{
+    switch (nq)
+    {
+#define ROWS_CASE(NQ, E, TH, R, V)                                                                              \
+    case NQ:                                                                                                 \
+        return launch_quad_rowscoa<T, NQ, E, TH, R, V>(nelmt, in, out, s);
+#define PIPE_CASE(NQ, E, TH, R, V)
+#define PREFER(NQ, BE)
+#define MMA_CASE(NQ, G, W, MB0, NB1)
+#include B200FE_ROWS_TABLE
+#undef ROWS_CASE
+#undef PIPE_CASE
+#undef PREFER
+#undef MMA_CASE
+    default:
+        return B200FE_EUNSUPPORTED;
+    }
+}
+
 // what the table offers for this nq: bit 0 rows, bit 1 pipe, bit 2 mma; *preferred = default routing
 static int quad_table_lookup(unsigned nq, Backend *preferred)
 {
@@ -189,7 +210,7 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
         if (!regular)
             be = Backend::Generic;
         else if (coa)
-            be = nq0 <= kQuadTpeMaxNq ? Backend::Tpe : Backend::Generic;
+            be = nq0 <= kQuadTpeMaxNq ? Backend::Tpe : ((have & 1) ? Backend::Rows : Backend::Generic);
         else if (nq0 == 2 && sizeof(T) == 4)
             be = Backend::Nm1; // measured: 0.81 vs 0.63 (pipe) for FP32; FP64 and hex stay on the table's choice
         else
@@ -207,8 +228,8 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
         t_last_backend = "generic";
         return launch_quad_generic<T>(nm0, nm1, nq0, nq1, nelmt, b0, b1, in, out, coa, stream);
     }
-    if (!regular || ((be == Backend::Rows || be == Backend::Pipe || be == Backend::Mma || be == Backend::Nm1) && coa) ||
-        (be == Backend::Tpe && !coa))
+    if (!regular || ((be == Backend::Pipe || be == Backend::Mma || be == Backend::Nm1) && coa) ||
+        (be == Backend::Tpe && !coa) || (be == Backend::Rows && !(have & 1)))
         return B200FE_EUNSUPPORTED;
     if (be == Backend::Pipe && (!(have & 2) || !aligned16(in)))
         return B200FE_EUNSUPPORTED;
@@ -224,7 +245,7 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
     if (rc)
         return rc;
     if (be == Backend::Rows)
-        rc = quad_rows_switch(nq0, nelmt, in, out, stream);
+        rc = coa ? quad_rowscoa_switch(nq0, nelmt, in, out, stream) : quad_rows_switch(nq0, nelmt, in, out, stream);
     else if (be == Backend::Pipe)
         rc = quad_pipe_switch(nq0, nelmt, in, out, stream);
     else
