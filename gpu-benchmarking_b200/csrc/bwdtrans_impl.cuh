@@ -190,9 +190,11 @@ int launch_quad_mma(unsigned nelmt, const float *b0, const float *b1, const floa
     return launch_status();
 }
 
-// ---- interleaved layout through the rows passes: E = power of two dividing 32, whole 32-byte sectors,
-// as close to the tuned element-major tile as that allows
-template <typename T, int E0> constexpr int coa_e()
+// ---- interleaved layout through the rows passes.  E is a power of two dividing 32 with E*sizeof(T) >= 32 bytes
+// (whole sectors).  Measured at 64 Mi points (bench.py sweep_coa): the tile shape closest to the tuned
+// element-major one wins for quads and hex nq <= 6; for hex nq >= 8 the largest tile that fits ~112 KB does
+// (longer contiguous runs per idx, fewer L1 tag cycles per scattered access): 0.53 against 0.48.
+template <typename T, int E0> constexpr int coa_e_near()
 {
     constexpr int emin = 32 / (int)sizeof(T); // 4 doubles / 8 floats = one sector
     int e              = emin;
@@ -200,10 +202,21 @@ template <typename T, int E0> constexpr int coa_e()
         e *= 2;
     return e;
 }
+template <template <typename, int, int, int, int, int> class Rows, typename T, int NQ, int THREADS, int R, int V, int E>
+constexpr int coa_e_fit()
+{
+    constexpr int emin = 32 / (int)sizeof(T); // 4 doubles / 8 floats = one 32-byte sector
+    if constexpr (E <= emin)
+        return emin;
+    else if constexpr (Rows<T, NQ, E, THREADS, R, V>::SMEM <= 112 * 1024)
+        return E;
+    else
+        return coa_e_fit<Rows, T, NQ, THREADS, R, V, E / 2>();
+}
 template <typename T, int NQ, int E0, int THREADS, int R, int V>
 int launch_quad_rowscoa(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
 {
-    constexpr int E = coa_e<T, E0>();
+    constexpr int E = coa_e_near<T, E0>();
     using C         = QuadRows<T, NQ, E, THREADS, R, V>;
     static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
     auto kernel = bwdtrans_quad_rowscoa_kernel<T, NQ, E, THREADS, R, V>;
@@ -219,7 +232,7 @@ int launch_quad_rowscoa(unsigned nelmt, const T *in, T *out, cudaStream_t stream
 template <typename T, int NQ, int E0, int THREADS, int R, int V>
 int launch_hex_rowscoa(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
 {
-    constexpr int E = coa_e<T, E0>();
+    constexpr int E = NQ >= 8 ? coa_e_fit<HexRows, T, NQ, THREADS, R, V, 32>() : coa_e_near<T, E0>();
     using C         = HexRows<T, NQ, E, THREADS, R, V>;
     static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
     auto kernel = bwdtrans_hex_rowscoa_kernel<T, NQ, E, THREADS, R, V>;

@@ -17,10 +17,45 @@
 namespace b200fe
 {
 
-// interleaved global -> element-major shared tile: s[el*LEN + idx] = g[32*idx + el], el < E
+// interleaved global -> element-major shared tile: s[el*LEN + idx] = g[32*idx + el], el < E.
+// All of a thread's loads are issued before its first store (the loop is latency-bound otherwise:
+// profiles/r01_ncu_hex8_f64_coa.txt, 44 % of the stall samples on the store waiting for its load), and
+// they are 16-byte loads (W elements of the same idx) where the slab is 16-byte aligned.
 template <typename T, int E, int LEN, int THREADS>
 __device__ __forceinline__ void coa_gather(T *__restrict__ s, const T *__restrict__ g, int tid)
 {
+    using V         = typename Vec16<T>::type;
+    constexpr int W = Vec16<T>::W;
+    static_assert(E % W == 0, "a tile holds whole 16-byte vectors of elements");
+    if ((reinterpret_cast<uintptr_t>(g) & 15u) == 0)
+    {
+        constexpr int PARTS = E / W, N = PARTS * LEN, ITER = (N + THREADS - 1) / THREADS;
+        V v[ITER];
+#pragma unroll
+        for (int it = 0; it < ITER; ++it)
+        {
+            const int c = tid + it * THREADS;
+            if (c < N)
+            {
+                const int idx = c / PARTS, part = c - idx * PARTS;
+                v[it]         = ld_stream(reinterpret_cast<const V *>(g + 32 * idx + part * W));
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < ITER; ++it)
+        {
+            const int c = tid + it * THREADS;
+            if (c < N)
+            {
+                const int idx = c / PARTS, part = c - idx * PARTS;
+                const T *pv   = reinterpret_cast<const T *>(&v[it]);
+#pragma unroll
+                for (int k = 0; k < W; ++k)
+                    s[(part * W + k) * LEN + idx] = pv[k];
+            }
+        }
+        return;
+    }
     constexpr int N = E * LEN;
     for (int c = tid; c < N; c += THREADS)
     {

@@ -493,3 +493,31 @@ def test_fused_operator_and_checksum(G, suf, dim, nq, nelmt):
     assert abs(results[0][1] - want) / want < 1e-12, (backend, results[0][1], want)
     assert results[0][1] == results[1][1]                       # deterministic
     assert np.array_equal(results[0][0], results[1][0])
+
+
+def test_two_streams_with_different_bases_share_the_constant_bank_safely(G):
+    """rows / pipe kernels take their basis from a per-device constant bank that every call refills; calls from two
+    streams with different bases must not see each other's matrices (event hand-over + programmatic dependent
+    launch of the operator behind its own fill)"""
+    import torch
+    nq, nm, nelmt = 6, 5, 30011
+    rng = np.random.default_rng(4711)
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    bases = [[rnd(rng, nm * nq, np.float64) for _ in range(3)] for _ in range(2)]
+    inp = rnd(rng, nelmt * nm ** 3, np.float64)
+    d_in = G.dev(inp)
+    d_b = [[G.dev(x) for x in bs] for bs in bases]
+    outs = [[torch.empty(nelmt * nq ** 3, dtype=torch.float64, device="cuda") for _ in range(6)] for _ in range(2)]
+    torch.cuda.synchronize()
+    for rep in range(6):
+        for s in range(2):
+            with torch.cuda.stream(streams[s]):
+                G.fe.bwdtrans_hex("BwdTransHexKernel_QP_Shared", "f64", nq, nq, nq, nelmt, d_b[s][0].data_ptr(),
+                                  d_b[s][1].data_ptr(), d_b[s][2].data_ptr(), d_in.data_ptr(), outs[s][rep].data_ptr(),
+                                  stream=streams[s].cuda_stream)
+    torch.cuda.synchronize()
+    assert G.fe.last_backend() in ("rows", "pipe")
+    for s in range(2):
+        want = oracle.bwdtrans_hex(nq, nq, nq, nelmt, *bases[s], inp)
+        for rep in range(6):
+            assert np.array_equal(outs[s][rep].cpu().numpy(), want), (s, rep)
