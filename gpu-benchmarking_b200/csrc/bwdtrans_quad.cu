@@ -51,7 +51,8 @@ static int quad_pipe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cu
     }
 }
 
-// FP64 tensor-core variant (only the f64 table lists MMA_CASE lines)
+// tensor-core variants: DMMA for T = double (sumfac_mma.cuh), 3xTF32 for T = float (sumfac_mma32.cuh);
+// launch_quad_mma is overloaded on the pointer type, the table of each dtype lists its own MMA_CASE lines
 static int quad_mma_switch(unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *in, T *out, cudaStream_t s,
                            double *partials, unsigned *npartials)
 {
