@@ -137,7 +137,7 @@ __device__ __forceinline__ void contract_block(const T (&a)[R][NM], T *const (&d
 }
 
 // p-loop body for outputs [IB0, IB0 + IB)
-template <typename T, int NM, int NQ, int BOFF, int OSTRIDE, int R, int IB0, int IB, bool TO_GLOBAL>
+template <typename T, int NM, int NQ, int BOFF, int OSTRIDE, int R, int IB0, int IB, bool TO_GLOBAL, int PU = 1>
 __device__ __forceinline__ void ploop_block(const T *const (&src)[R], T *const (&dst)[R], const bool (&ok)[R])
 {
     constexpr int W        = 16 / (int)sizeof(T);
@@ -146,7 +146,7 @@ __device__ __forceinline__ void ploop_block(const T *const (&src)[R], T *const (
 #pragma unroll
     for (int k = 0; k < R; ++k)
         t[k].zero();
-#pragma unroll 1
+#pragma unroll PU
     for (int p = 0; p < NM; ++p)
     {
         T a[R];
@@ -174,14 +174,14 @@ __device__ __forceinline__ void ploop_block(const T *const (&src)[R], T *const (
         }
 }
 
-template <typename T, int NM, int NQ, int BOFF, int OSTRIDE, int R, int IB0, bool TO_GLOBAL>
+template <typename T, int NM, int NQ, int BOFF, int OSTRIDE, int R, int IB0, bool TO_GLOBAL, int PU = 1>
 __device__ __forceinline__ void ploop_blocks(const T *const (&src)[R], T *const (&dst)[R], const bool (&ok)[R])
 {
     if constexpr (IB0 < NQ)
     {
         constexpr int IB = (NQ - IB0) >= 16 ? 16 : (NQ - IB0);
-        ploop_block<T, NM, NQ, BOFF, OSTRIDE, R, IB0, IB, TO_GLOBAL>(src, dst, ok);
-        ploop_blocks<T, NM, NQ, BOFF, OSTRIDE, R, IB0 + IB, TO_GLOBAL>(src, dst, ok);
+        ploop_block<T, NM, NQ, BOFF, OSTRIDE, R, IB0, IB, TO_GLOBAL, PU>(src, dst, ok);
+        ploop_blocks<T, NM, NQ, BOFF, OSTRIDE, R, IB0 + IB, TO_GLOBAL, PU>(src, dst, ok);
     }
 }
 
@@ -233,7 +233,8 @@ __device__ __forceinline__ void contract_rows(int nrows, int row0, SrcFn src_of,
     }
     else
     {
-        ploop_blocks<T, NM, NQ, BOFF, OSTRIDE, R, 0, TO_GLOBAL>(src, dst, ok);
+        // V = 1: p is a real loop; V = 3: the same loop unrolled by 4 (loads of the next steps in flight)
+        ploop_blocks<T, NM, NQ, BOFF, OSTRIDE, R, 0, TO_GLOBAL, (V == 3 ? 4 : 1)>(src, dst, ok);
     }
 }
 

@@ -56,12 +56,12 @@ def configs(dim, tag, nq):
                         continue
                     if th * r > 2 * max_rows * e and not (th == 128 and r == 1):
                         continue                       # tile too small to fill the CTA
-                    for v in (0, 2, 1):
+                    for v in (0, 2, 1, 3):
                         if v == 0 and nq > 12:
                             continue                   # fully unrolled code spills uniform registers for large nq
                         if v == 2 and (nq < 6 or nq > 16):
                             continue
-                        if v == 1 and nq < 6:
+                        if v in (1, 3) and nq < 6:
                             continue
                         out.append((be, e, th, r, v))
     return out
