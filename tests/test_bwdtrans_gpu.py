@@ -521,3 +521,33 @@ def test_two_streams_with_different_bases_share_the_constant_bank_safely(G):
         want = oracle.bwdtrans_hex(nq, nq, nq, nelmt, *bases[s], inp)
         for rep in range(6):
             assert np.array_equal(outs[s][rep].cpu().numpy(), want), (s, rep)
+
+
+@pytest.mark.parametrize("dim,nq", [(2, 12), (2, 16), (2, 32), (3, 8)])
+def test_mma_fp64_bit_exact_over_a_wide_dynamic_range(G, dim, nq):
+    """the DMMA back-end is held bit for bit to the FMA chain also where rounding is exercised hard: magnitudes
+    spread over 60 decades, heavy cancellation, subnormal results and signed zeros"""
+    nm, nelmt = nq - 1, 515
+    rng = np.random.default_rng(31337 + nq)
+
+    def wide(n):
+        return rng.standard_normal(n) * 10.0 ** rng.integers(-30, 30, n)
+
+    b = [wide(nm * nq) for _ in range(dim)]
+    inp = wide(nelmt * nm ** dim)
+    inp[::5] = 0.0
+    inp[1::97] = -0.0
+    inp[2::89] *= 1e-290                       # products underflow into the subnormal range
+    try:
+        G.fe.set_backend("mma")
+        if dim == 2:
+            got = G.run_quad("BwdTransQuadKernel_QP_Shared", "f64", nq, nq, nelmt, b[0], b[1], inp)
+            want = oracle.bwdtrans_quad(nq, nq, nelmt, b[0], b[1], inp)
+        else:
+            got = G.run_hex("BwdTransHexKernel_QP_Shared", "f64", (nq,) * 3, nelmt, b, inp)
+            want = oracle.bwdtrans_hex(nq, nq, nq, nelmt, *b, inp)
+        assert G.fe.last_backend() == "mma"
+    finally:
+        G.fe.set_backend("auto")
+    assert np.array_equal(got, want)
+    assert np.array_equal(np.signbit(got), np.signbit(want))
