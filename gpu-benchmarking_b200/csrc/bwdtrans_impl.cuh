@@ -7,6 +7,7 @@
 #include "dispatch.h"
 #include "sumfac_generic.cuh"
 #include "sumfac_iprod.cuh"
+#include "sumfac_iprod_mma.cuh"
 #include "sumfac_mma.cuh"
 #include "sumfac_mma32.cuh"
 #include "sumfac_nm1.cuh"
@@ -298,6 +299,67 @@ int launch_hex_iprod(unsigned nelmt, const T *in, const T *w, T *out, cudaStream
     count_launch();
     t_last_backend = "iprod-rows";
     return launch_status();
+}
+
+// FP64 tensor-core IProductWRTBase (sumfac_iprod_mma.cuh); wgt may be null
+template <int NQ, int G, int WARPS, int MB, int NB>
+int launch_hex_iprod_mma(unsigned nelmt, const double *b0, const double *b1, const double *b2, const double *in,
+                         const double *wgt, double *out, cudaStream_t stream)
+{
+    static int occ[2][64]  = {};
+    const unsigned ngroups = (nelmt + G - 1) / G;
+    const unsigned need    = (ngroups + WARPS - 1) / WARPS;
+    auto go = [&](auto kernel, size_t smem, int *cache) -> int {
+        int rc = opt_in_smem(kernel, smem);
+        if (rc)
+            return rc;
+        const unsigned fit  = (unsigned)(sm_count() * ctas_per_sm(kernel, WARPS * 32, smem, cache));
+        const unsigned grid = need < fit ? need : fit;
+        kernel<<<grid, WARPS * 32, smem, stream>>>(b0, b1, b2, in, wgt, out, nelmt, ngroups);
+        count_launch();
+        t_last_backend = "iprod-mma";
+        return launch_status();
+    };
+    static_assert(HexIprodMma<NQ, G, WARPS, true>::SMEM <= (size_t)kSmemMax, "warp regions do not fit shared memory");
+    return wgt ? go(iproduct_hex_mma_kernel<NQ, G, WARPS, MB, NB, true>, HexIprodMma<NQ, G, WARPS, true>::SMEM, occ[1])
+               : go(iproduct_hex_mma_kernel<NQ, G, WARPS, MB, NB, false>, HexIprodMma<NQ, G, WARPS, false>::SMEM, occ[0]);
+}
+
+template <int NQ, int G, int WARPS, int MB, int NB>
+int launch_quad_iprod_mma(unsigned nelmt, const double *b0, const double *b1, const double *in, const double *wgt,
+                          double *out, cudaStream_t stream)
+{
+    static int occ[2][64]  = {};
+    const unsigned ngroups = (nelmt + G - 1) / G;
+    const unsigned need    = (ngroups + WARPS - 1) / WARPS;
+    auto go = [&](auto kernel, size_t smem, int *cache) -> int {
+        int rc = opt_in_smem(kernel, smem);
+        if (rc)
+            return rc;
+        const unsigned fit  = (unsigned)(sm_count() * ctas_per_sm(kernel, WARPS * 32, smem, cache));
+        const unsigned grid = need < fit ? need : fit;
+        kernel<<<grid, WARPS * 32, smem, stream>>>(b0, b1, in, wgt, out, nelmt, ngroups);
+        count_launch();
+        t_last_backend = "iprod-mma";
+        return launch_status();
+    };
+    static_assert(QuadIprodMma<NQ, G, WARPS, true>::SMEM <= (size_t)kSmemMax, "warp regions do not fit shared memory");
+    return wgt ? go(iproduct_quad_mma_kernel<NQ, G, WARPS, MB, NB, true>, QuadIprodMma<NQ, G, WARPS, true>::SMEM, occ[1])
+               : go(iproduct_quad_mma_kernel<NQ, G, WARPS, MB, NB, false>, QuadIprodMma<NQ, G, WARPS, false>::SMEM,
+                    occ[0]);
+}
+
+// there is no FP32 tensor-core IProductWRTBase: the row kernel serves float
+template <int NQ, int G, int WARPS, int MB, int NB>
+int launch_hex_iprod_mma(unsigned, const float *, const float *, const float *, const float *, const float *, float *,
+                         cudaStream_t)
+{
+    return B200FE_EUNSUPPORTED;
+}
+template <int NQ, int G, int WARPS, int MB, int NB>
+int launch_quad_iprod_mma(unsigned, const float *, const float *, const float *, const float *, float *, cudaStream_t)
+{
+    return B200FE_EUNSUPPORTED;
 }
 
 template <typename T, int NQ> int launch_quad_tpe_coa(unsigned nelmt, const T *in, T *out, cudaStream_t stream)

@@ -277,10 +277,42 @@ static int quad_iprod_switch(unsigned nq, unsigned nelmt, const T *in, const T *
     }
 }
 
-template <>
-int run_iproduct_quad<T>(unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *w, const T *in, T *out,
-                         cudaStream_t stream)
+// FP64 tensor-core variant: (G elements per warp, warps per CTA, MB, NB) per nq
+static int quad_iprod_mma_switch(unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *in, const T *w, T *out,
+                                 cudaStream_t s)
 {
+    {
+        switch (nq)
+        {
+#define IPM(NQ, G, W, MB, NB)                                                                                \
+    case NQ:                                                                                                 \
+        return launch_quad_iprod_mma<NQ, G, W, MB, NB>(nelmt, b0, b1, in, w, out, s);
+            // (G, WARPS) from a sweep at 64 Mi points (tools/ipm_probe.py): fraction of the roofline, row kernel in ()
+            IPM(8, 8, 4, 4, 4)  // 0.89 (0.65)
+            IPM(12, 2, 4, 4, 4) // 0.63 (0.57)
+            IPM(14, 2, 4, 4, 4) // 0.64 (0.57)
+            IPM(16, 2, 8, 4, 4) // 0.70 (0.63)
+            IPM(32, 1, 2, 4, 4) // 0.40 (0.23)
+#undef IPM
+        default:
+            break;
+        }
+    }
+    return B200FE_EUNSUPPORTED;
+}
+
+template <>
+int run_iproduct_quad<T>(Backend be, unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *w, const T *in,
+                         T *out, cudaStream_t stream)
+{
+    if (be == Backend::Auto || be == Backend::Mma)
+    {
+        const int rc = quad_iprod_mma_switch(nq, nelmt, b0, b1, in, w, out, stream);
+        if (rc != B200FE_EUNSUPPORTED || be == Backend::Mma)
+            return rc;
+    }
+    else if (be != Backend::Rows)
+        return B200FE_EUNSUPPORTED;
     std::lock_guard<std::mutex> lock(g_bank_lock);
     const T *bases[2]   = {b0, b1};
     const int counts[2] = {(int)((nq - 1) * nq), (int)((nq - 1) * nq)};

@@ -475,7 +475,8 @@ size_t b200fe_sumsq_scratch_bytes(void)
             return B200FE_EUNSUPPORTED;                                                                      \
         if (nelmt == 0)                                                                                      \
             return B200FE_OK;                                                                                \
-        return run_iproduct_quad<T>(nq0, nelmt, basis0, basis1, weights, in, out, (cudaStream_t)stream);     \
+        return run_iproduct_quad<T>(pick(Backend::Auto), nq0, nelmt, basis0, basis1, weights, in, out,                \
+                                    (cudaStream_t)stream);     \
     }                                                                                                        \
     int b200fe_IProductWRTBaseHex_##SUF(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nq0,              \
                                         unsigned nq1, unsigned nq2, unsigned nelmt, const T *basis0,         \
@@ -491,7 +492,7 @@ size_t b200fe_sumsq_scratch_bytes(void)
             return B200FE_EUNSUPPORTED;                                                                      \
         if (nelmt == 0)                                                                                      \
             return B200FE_OK;                                                                                \
-        return run_iproduct_hex<T>(nq0, nelmt, basis0, basis1, basis2, weights, in, out,                     \
+        return run_iproduct_hex<T>(pick(Backend::Auto), nq0, nelmt, basis0, basis1, basis2, weights, in, out,       \
                                    (cudaStream_t)stream);                                                    \
     }
 IPROD_API(f64, double)

@@ -34,10 +34,11 @@ int run_bwdtrans_hex(Backend be, bool coa, unsigned nm0, unsigned nm1, unsigned 
 // IProductWRTBase (sumfac_iprod.cuh): element-major, nq0 == nq1 (== nq2), nm = nq - 1, nq within the
 // per-nq table; w (quadrature metric, one value per point) may be null.  0 / cudaError_t / B200FE_E*
 template <typename T>
-int run_iproduct_quad(unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *w, const T *in, T *out,
-                      cudaStream_t stream);
+int run_iproduct_quad(Backend be, unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *w, const T *in,
+                      T *out, cudaStream_t stream);
 template <typename T>
-int run_iproduct_hex(unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *b2, const T *w, const T *in,
-                     T *out, cudaStream_t stream);
+int run_iproduct_hex(Backend be, unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *b2, const T *w,
+                     const T *in, T *out, cudaStream_t stream);
+// be: Auto = the FP64 tensor-core kernel where one is instantiated, else the row kernel; Rows / Mma force one
 
 } // namespace b200fe

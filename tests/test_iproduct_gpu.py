@@ -69,6 +69,42 @@ def test_hex_bit_exact_with_oracle(G, suf, weighted, nq):
         assert np.array_equal(got, want), (nq, nelmt, G.rel_max(got, want))
 
 
+@pytest.mark.parametrize("backend", ["rows", "mma"])
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("dim,nq", [(2, 8), (2, 12), (2, 14), (2, 16), (2, 32), (3, 8)])
+def test_fp64_backends_bit_exact_ragged_groups_and_alignment(G, backend, weighted, dim, nq):
+    """row kernel and tensor-core kernel forced in turn; group sizes that do not divide nelmt; 8-byte aligned slabs"""
+    import torch
+    nm = nq - 1
+    rng = np.random.default_rng(1300 + nq)
+    b = [rng.standard_normal(nm * nq) for _ in range(dim)]
+    for nelmt, shift in ((1, 0), (13, 1), (1001, 0), (1001, 1)):
+        if dim == 2 and nq == 32 and nelmt > 100:
+            nelmt = 333
+        inp = rng.standard_normal(nelmt * nq ** dim)
+        w = rng.random(nelmt * nq ** dim) + 0.5 if weighted else None
+        big_in = torch.zeros(inp.size + 2, dtype=torch.float64, device="cuda")
+        big_in[shift:shift + inp.size] = torch.from_numpy(inp).cuda()
+        big_w = None
+        if weighted:
+            big_w = torch.zeros(inp.size + 2, dtype=torch.float64, device="cuda")
+            big_w[1 - shift:1 - shift + inp.size] = torch.from_numpy(w).cuda()   # the metric at the OTHER alignment
+        d_b = [G.dev(x) for x in b]
+        d_out = torch.full((nelmt * nm ** dim + 2,), float("nan"), dtype=torch.float64, device="cuda")
+        try:
+            G.fe.set_backend(backend)
+            G.fe.iproduct("f64", (nq,) * dim, nelmt, [x.data_ptr() for x in d_b], big_in.data_ptr() + 8 * shift,
+                          d_out.data_ptr() + 8, weights=(big_w.data_ptr() + 8 * (1 - shift)) if weighted else 0)
+            assert G.fe.last_backend() == ("iprod-mma" if backend == "mma" else "iprod-rows")
+        finally:
+            G.fe.set_backend("auto")
+        got = G.host(d_out)
+        want = (oracle.iproduct_quad(nq, nq, nelmt, b[0], b[1], inp, w) if dim == 2
+                else oracle.iproduct_hex(nq, nq, nq, nelmt, *b, inp, w))
+        assert np.isnan(got[0]) and np.isnan(got[-1])
+        assert np.array_equal(got[1:-1], want), (backend, nq, nelmt, shift, G.rel_max(got[1:-1], want))
+
+
 @pytest.mark.parametrize("dim,nq,nelmt", [(2, 8, 1048576), (3, 8, 131072)])
 def test_adjoint_of_the_device_bwdtrans_at_baseline_size(G, dim, nq, nelmt):
     """<IProduct(u), c> == <u, BwdTrans(c)> with both operators on the device, 64 Mi quadrature points"""
