@@ -233,8 +233,7 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
 
     std::lock_guard<std::mutex> lock(g_bank_lock);
     const T *bases[3]   = {b0, b1, b2};
-    const int counts[3] = {(int)(nm0 * nq0), (int)(nm1 * nq1), (int)(nm2 * nq2)};
-    int rc              = fill_basis_bank<T>(g_bank, 3, bases, counts, stream);
+    int rc              = fill_basis_bank<T>(g_bank, 3, bases, (int)nm0, (int)nq0, false, stream);
     if (rc)
         return rc;
     if (be == Backend::Rows)
@@ -297,8 +296,7 @@ int run_iproduct_hex<T>(Backend be, unsigned nq, unsigned nelmt, const T *b0, co
         return B200FE_EUNSUPPORTED;
     std::lock_guard<std::mutex> lock(g_bank_lock);
     const T *bases[3]   = {b0, b1, b2};
-    const int counts[3] = {(int)((nq - 1) * nq), (int)((nq - 1) * nq), (int)((nq - 1) * nq)};
-    int rc = fill_basis_bank<T>(g_bank, 3, bases, counts, stream, (int)nq - 1, (int)nq); // transposed
+    int rc = fill_basis_bank<T>(g_bank, 3, bases, (int)nq - 1, (int)nq, true, stream); // transposed
     if (rc)
         return rc;
     rc = hex_iprod_switch(nq, nelmt, in, w, out, stream);

@@ -241,8 +241,7 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
 
     std::lock_guard<std::mutex> lock(g_bank_lock);
     const T *bases[2]   = {b0, b1};
-    const int counts[2] = {(int)(nm0 * nq0), (int)(nm1 * nq1)};
-    int rc              = fill_basis_bank<T>(g_bank, 2, bases, counts, stream);
+    int rc              = fill_basis_bank<T>(g_bank, 2, bases, (int)nm0, (int)nq0, false, stream);
     if (rc)
         return rc;
     if (be == Backend::Rows)
@@ -315,8 +314,7 @@ int run_iproduct_quad<T>(Backend be, unsigned nq, unsigned nelmt, const T *b0, c
         return B200FE_EUNSUPPORTED;
     std::lock_guard<std::mutex> lock(g_bank_lock);
     const T *bases[2]   = {b0, b1};
-    const int counts[2] = {(int)((nq - 1) * nq), (int)((nq - 1) * nq)};
-    int rc = fill_basis_bank<T>(g_bank, 2, bases, counts, stream, (int)nq - 1, (int)nq); // transposed
+    int rc = fill_basis_bank<T>(g_bank, 2, bases, (int)nq - 1, (int)nq, true, stream); // transposed
     if (rc)
         return rc;
     rc = quad_iprod_switch(nq, nelmt, in, w, out, stream);

@@ -75,7 +75,7 @@ __device__ __forceinline__ float fmadd(float a, float b, float c)
 // no load instruction, no register, no shared-memory traffic.  Sized for quad
 // nq <= 32 (2*31*32) and hex nq <= 16 (3*15*16).  `static`: one bank per
 // translation unit, filled by that unit's launcher.
-constexpr int kBasisBankElems = 1984;
+constexpr int kBasisBankElems = 2304; // incl. the pitched / transposed layouts (2 x 32 rows x pitch 32 = 2048)
 static __constant__ __align__(16) double c_basis_f64[kBasisBankElems];
 static __constant__ __align__(16) float c_basis_f32[kBasisBankElems];
 
@@ -168,10 +168,16 @@ struct BankGuard
     void *bank[64]        = {}; // global address of this translation unit's constant bank, per device
 };
 
-// One tiny kernel writes the bank through the symbol's global address (constant caches are
-// invalidated at kernel boundaries, so the next kernel on the stream sees the new values).  This
-// replaces three cudaMemcpyToSymbolAsync calls, which cost ~10 us of stream time per operator call --
-// 6-12 % of a 64 Mi-point operator.
+// Bank layout: matrix d occupies rows [d*nrows, (d+1)*nrows) of `pitch` values each, pitch = the row length
+// rounded up to a whole 16-byte vector (bank_pitch), so that every row -- and every block of 2 / 4 consecutive
+// outputs inside it -- starts on a 16-byte boundary whatever nq is (nq = 6, 10, 14 in FP32 would otherwise
+// put every other row on an 8-byte boundary and force 8-byte uniform loads).
+template <typename T> constexpr int bank_pitch(int n)
+{
+    constexpr int W = 16 / (int)sizeof(T);
+    return (n + W - 1) / W * W;
+}
+
 // Programmatic dependent launch: the operator kernel that follows the fill on the stream is launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs are scheduled and fetch their first tiles
 // while this kernel runs; they call grid_dependency_wait() before their first constant-bank read, which
@@ -183,34 +189,30 @@ __device__ __forceinline__ void grid_dependency_wait()
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// One tiny kernel writes the bank through the symbol's global address (constant caches are invalidated at
+// kernel boundaries, so the next kernel on the stream sees the new values).
+//   plain:       bank[(d*nm + p)*pitch(nq) + i] = B_d[p*nq + i]        (BwdTrans: contraction index p, outputs i)
+//   transposed:  bank[(d*nq + i)*pitch(nm) + p] = B_d[p*nq + i]        (IProductWRTBase: contraction index i, outputs p)
 template <typename T>
-__global__ void fill_bank_kernel(T *__restrict__ bank, const T *__restrict__ b0, int n0, const T *__restrict__ b1,
-                                 int n1, const T *__restrict__ b2, int n2)
+__global__ void fill_bank_kernel(T *__restrict__ bank, const T *__restrict__ b0, const T *__restrict__ b1,
+                                 const T *__restrict__ b2, int nb, int nm, int nq, int transposed)
 {
     asm volatile("griddepcontrol.launch_dependents;"); // let the dependent operator kernel start its prologue now
-    const int n = n0 + n1 + n2;
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-        bank[i] = i < n0 ? b0[i] : (i < n0 + n1 ? b1[i - n0] : b2[i - n0 - n1]);
-}
-
-// transposed fill for IProductWRTBase: bank[d][i*nm + p] = B_d[p*nq + i] (all directions share nm, nq)
-template <typename T>
-__global__ void fill_bank_transposed_kernel(T *__restrict__ bank, const T *__restrict__ b0, const T *__restrict__ b1,
-                                            const T *__restrict__ b2, int nb, int nm, int nq)
-{
-    asm volatile("griddepcontrol.launch_dependents;");
-    const int per = nm * nq;
-    for (int t = threadIdx.x; t < nb * per; t += blockDim.x)
+    const int rows = transposed ? nq : nm, cols = transposed ? nm : nq, pitch = bank_pitch<T>(cols);
+    for (int t = threadIdx.x; t < nb * rows * pitch; t += blockDim.x)
     {
-        const int d = t / per, r = t - d * per, i = r / nm, p = r - i * nm;
+        const int d = t / (rows * pitch), r = (t - d * rows * pitch) / pitch, c = t - (d * rows + r) * pitch;
         const T *b = d == 0 ? b0 : (d == 1 ? b1 : b2);
-        bank[t]    = b[p * nq + i];
+        T v        = T(0);
+        if (c < cols)
+            v = transposed ? b[c * nq + r] : b[r * nq + c];
+        bank[t] = v;
     }
 }
 
 template <typename T>
-inline int fill_basis_bank(BankGuard &g, int nb, const T *const *basis, const int *count, cudaStream_t stream,
-                           int transpose_nm = 0, int transpose_nq = 0)
+inline int fill_basis_bank(BankGuard &g, int nb, const T *const *basis, int nm, int nq, bool transposed,
+                           cudaStream_t stream)
 {
     int dev = 0;
     B200FE_CUDA_TRY(cudaGetDevice(&dev));
@@ -225,17 +227,11 @@ inline int fill_basis_bank(BankGuard &g, int nb, const T *const *basis, const in
         else
             B200FE_CUDA_TRY(cudaGetSymbolAddress(&g.bank[dev], c_basis_f32));
     }
-    const int n0 = count[0], n1 = nb > 1 ? count[1] : 0, n2 = nb > 2 ? count[2] : 0;
-    if (n0 + n1 + n2 > kBasisBankElems)
+    const int rows = transposed ? nq : nm, cols = transposed ? nm : nq;
+    if (nb * rows * bank_pitch<T>(cols) > kBasisBankElems)
         return B200FE_EUNSUPPORTED;
-    if (transpose_nm > 0)
-        fill_bank_transposed_kernel<T><<<1, 256, 0, stream>>>(static_cast<T *>(g.bank[dev]), basis[0],
-                                                              nb > 1 ? basis[1] : basis[0],
-                                                              nb > 2 ? basis[2] : basis[0], nb, transpose_nm,
-                                                              transpose_nq);
-    else
-        fill_bank_kernel<T><<<1, 256, 0, stream>>>(static_cast<T *>(g.bank[dev]), basis[0], n0,
-                                                   nb > 1 ? basis[1] : basis[0], n1, nb > 2 ? basis[2] : basis[0], n2);
+    fill_bank_kernel<T><<<1, 256, 0, stream>>>(static_cast<T *>(g.bank[dev]), basis[0], nb > 1 ? basis[1] : basis[0],
+                                               nb > 2 ? basis[2] : basis[0], nb, nm, nq, transposed ? 1 : 0);
     count_launch();
     return launch_status();
 }

@@ -75,7 +75,7 @@ template <typename T, int NQ, int E> struct QuadIprodShape
     static constexpr int S_OUT = E * NM2;      // staged output [e][q][p] (aliases the input tile)
     static constexpr int SA    = S_IN > S_OUT ? S_IN : S_OUT;
     static constexpr size_t SMEM = (size_t)((SA + 1) / 2 * 2 + S_MID) * sizeof(T);
-    static constexpr int B0 = 0, B1 = NQ * NM; // transposed basis matrices in the bank
+    static constexpr int B0 = 0, B1 = NQ * bank_pitch<T>(NM); // transposed basis matrices in the bank
 };
 
 template <typename T, int NQ, int E, int THREADS, int R>
@@ -124,7 +124,7 @@ template <typename T, int NQ, int E> struct HexIprodShape
     static constexpr int S2   = E * NM2 * RS;      // after direction 1: [e][q][p][k] (aliases the input tile)
     static constexpr int SA   = S_IN > S2 ? S_IN : S2;
     static constexpr size_t SMEM = (size_t)((SA + 1) / 2 * 2 + S1) * sizeof(T);
-    static constexpr int B0 = 0, B1 = NQ * NM, B2 = 2 * NQ * NM;
+    static constexpr int B0 = 0, B1 = NQ * bank_pitch<T>(NM), B2 = 2 * NQ * bank_pitch<T>(NM);
 };
 
 template <typename T, int NQ, int E, int THREADS, int R>

@@ -45,9 +45,10 @@ namespace b200fe
 //         of NM.  Best for large nq.
 template <int NM, int NQ, int SIZE> constexpr int unrolled_ib()
 {
-    // largest power of two dividing NQ whose block stays within ~60 uniform registers
+    // largest power of two <= NQ whose block stays within ~60 uniform registers; NQ % IB outputs are left for
+    // one narrower tail block (the bank rows are pitched to 16 bytes, so every block start is vector aligned)
     for (int ib = 8; ib >= 2; ib /= 2)
-        if (NQ % ib == 0 && NM * ib * (SIZE / 4) <= 60)
+        if (ib <= NQ && NM * ib * (SIZE / 4) <= 60)
             return ib;
     return 1;
 }
@@ -107,7 +108,8 @@ template <typename T, int NM, int NQ, int BOFF, int OSTRIDE, int R, int IB, bool
 __device__ __forceinline__ void contract_block(const T (&a)[R][NM], T *const (&dst)[R], const bool (&ok)[R], int ib)
 {
     constexpr int W       = 16 / (int)sizeof(T);
-    constexpr bool ALIGNED = (NQ % W == 0) && (BOFF % W == 0) && (IB % W == 0 || IB % 2 == 0);
+    constexpr int PITCH   = bank_pitch<T>(NQ); // bank row length (common.cuh)
+    constexpr bool ALIGNED = (BOFF % W == 0) && (IB % W == 0 || IB % 2 == 0);
     RowAcc<T, IB> t[R];
 #pragma unroll
     for (int k = 0; k < R; ++k)
@@ -116,7 +118,7 @@ __device__ __forceinline__ void contract_block(const T (&a)[R][NM], T *const (&d
     for (int p = 0; p < NM; ++p)
     {
         T b[IB];
-        cbasis_load<IB, ALIGNED>(BOFF + p * NQ + ib, b);
+        cbasis_load<IB, ALIGNED>(BOFF + p * PITCH + ib, b);
 #pragma unroll
         for (int k = 0; k < R; ++k)
             t[k].fma(a[k][p], b);
@@ -141,7 +143,8 @@ template <typename T, int NM, int NQ, int BOFF, int OSTRIDE, int R, int IB0, int
 __device__ __forceinline__ void ploop_block(const T *const (&src)[R], T *const (&dst)[R], const bool (&ok)[R])
 {
     constexpr int W        = 16 / (int)sizeof(T);
-    constexpr bool ALIGNED = (NQ % W == 0) && (BOFF % W == 0) && (IB0 % W == 0);
+    constexpr int PITCH    = bank_pitch<T>(NQ);
+    constexpr bool ALIGNED = (BOFF % W == 0) && (IB0 % W == 0);
     RowAcc<T, IB> t[R];
 #pragma unroll
     for (int k = 0; k < R; ++k)
@@ -154,7 +157,7 @@ __device__ __forceinline__ void ploop_block(const T *const (&src)[R], T *const (
         for (int k = 0; k < R; ++k)
             a[k] = src[k][p];
         T b[IB];
-        cbasis_load<IB, ALIGNED>(BOFF + p * NQ + IB0, b);
+        cbasis_load<IB, ALIGNED>(BOFF + p * PITCH + IB0, b);
 #pragma unroll
         for (int k = 0; k < R; ++k)
             t[k].fma(a[k], b);
@@ -218,7 +221,7 @@ __device__ __forceinline__ void contract_rows(int nrows, int row0, SrcFn src_of,
             // ALL of them to the top of the block; beyond ~60 uniform registers it spills them
             // through vector registers, so this shape only pays for small nq.
 #pragma unroll
-            for (int ib = 0; ib < NQ; ib += IB)
+            for (int ib = 0; ib + IB <= NQ; ib += IB)
                 contract_block<T, NM, NQ, BOFF, OSTRIDE, R, IB, TO_GLOBAL>(a, dst, ok, ib);
         }
         else
@@ -227,9 +230,12 @@ __device__ __forceinline__ void contract_rows(int nrows, int row0, SrcFn src_of,
             // (no spills, small code), at the price of 8-byte uniform loads (a register-indexed
             // LDCU moves at most 64 bits)
 #pragma unroll 1
-            for (int ib = 0; ib < NQ; ib += IB)
+            for (int ib = 0; ib + IB <= NQ; ib += IB)
                 contract_block<T, NM, NQ, BOFF, OSTRIDE, R, IB, TO_GLOBAL>(a, dst, ok, ib);
         }
+        constexpr int TAIL = NQ % IB; // outputs left over when IB does not divide NQ: one narrower block
+        if constexpr (TAIL > 0)
+            contract_block<T, NM, NQ, BOFF, OSTRIDE, R, TAIL, TO_GLOBAL>(a, dst, ok, NQ - TAIL);
     }
     else
     {
@@ -408,7 +414,7 @@ template <typename T, int NQ, int E> struct QuadShape
     static constexpr int SO  = E * OS;  // staged output [e][j][i] (padded)
     static constexpr bool IN_VEC_OK  = ((size_t)E * NM2 * sizeof(T)) % 16 == 0;
     static constexpr bool OUT_VEC_OK = ((size_t)E * NQ2 * sizeof(T)) % 16 == 0;
-    static constexpr int B0 = 0, B1 = NM * NQ;
+    static constexpr int B0 = 0, B1 = NM * bank_pitch<T>(NQ); // bank offsets of the two basis matrices
     static constexpr int align16(int elems) { return (elems * (int)sizeof(T) + 15) / 16 * 16 / (int)sizeof(T); }
 };
 
@@ -606,7 +612,7 @@ template <typename T, int NQ, int E> struct HexShape
     static constexpr int S1  = E * ES1; // after dir 0   [e][i][r][q]
     static constexpr int S2  = E * ES2; // after dir 1   [e][j][i][r]
     static constexpr bool IN_VEC_OK = ((size_t)E * NM3 * sizeof(T)) % 16 == 0;
-    static constexpr int B0 = 0, B1 = NM * NQ, B2 = 2 * NM * NQ;
+    static constexpr int B0 = 0, B1 = NM * bank_pitch<T>(NQ), B2 = 2 * NM * bank_pitch<T>(NQ);
     static constexpr int align16(int elems) { return (elems * (int)sizeof(T) + 15) / 16 * 16 / (int)sizeof(T); }
 };
 

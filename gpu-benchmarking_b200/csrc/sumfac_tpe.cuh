@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(THREADS)
     bwdtrans_quad_tpe_coa_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
 {
     constexpr int NM = NQ - 1, NM2 = NM * NM, NQ2 = NQ * NQ;
-    constexpr int B0 = 0, B1 = NM * NQ;
+    constexpr int BP = bank_pitch<T>(NQ), B0 = 0, B1 = NM * BP; // pitched bank rows (common.cuh)
     const size_t e = (size_t)blockIdx.x * THREADS + threadIdx.x;
     if (e >= nelmt)
         return;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(THREADS)
             T t = T(0);
 #pragma unroll
             for (int p = 0; p < NM; ++p)
-                t = fmadd(a[q * NM + p], cbasis<T>(B0 + p * NQ + i), t);
+                t = fmadd(a[q * NM + p], cbasis<T>(B0 + p * BP + i), t);
             w[q] = t;
         }
 #pragma unroll
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(THREADS)
             T t = T(0);
 #pragma unroll
             for (int q = 0; q < NM; ++q)
-                t = fmadd(w[q], cbasis<T>(B1 + q * NQ + j), t);
+                t = fmadd(w[q], cbasis<T>(B1 + q * BP + j), t);
             st_stream(pout + 32 * (j * NQ + i), t);
         }
     }
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(THREADS)
     bwdtrans_hex_tpe_coa_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
 {
     constexpr int NM = NQ - 1, NM2 = NM * NM, NM3 = NM2 * NM, NQ2 = NQ * NQ, NQ3 = NQ2 * NQ;
-    constexpr int B0 = 0, B1 = NM * NQ, B2 = 2 * NM * NQ;
+    constexpr int BP = bank_pitch<T>(NQ), B0 = 0, B1 = NM * BP, B2 = 2 * NM * BP;
     const size_t e = (size_t)blockIdx.x * THREADS + threadIdx.x;
     if (e >= nelmt)
         return;
@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(THREADS)
             T t = T(0);
 #pragma unroll
             for (int p = 0; p < NM; ++p)
-                t = fmadd(a[rq * NM + p], cbasis<T>(B0 + p * NQ + i), t);
+                t = fmadd(a[rq * NM + p], cbasis<T>(B0 + p * BP + i), t);
             w0[rq] = t;
         }
 #pragma unroll
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(THREADS)
                 T t = T(0);
 #pragma unroll
                 for (int q = 0; q < NM; ++q)
-                    t = fmadd(w0[r * NM + q], cbasis<T>(B1 + q * NQ + j), t);
+                    t = fmadd(w0[r * NM + q], cbasis<T>(B1 + q * BP + j), t);
                 w1[r] = t;
             }
 #pragma unroll
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(THREADS)
                 T t = T(0);
 #pragma unroll
                 for (int r = 0; r < NM; ++r)
-                    t = fmadd(w1[r], cbasis<T>(B2 + r * NQ + k), t);
+                    t = fmadd(w1[r], cbasis<T>(B2 + r * BP + k), t);
                 st_stream(pout + 32 * (k * NQ2 + j * NQ + i), t);
             }
         }

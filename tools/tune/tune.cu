@@ -163,7 +163,8 @@ int main(int argc, char **argv)
     CK(cudaMemcpy(d_basis, hb.data(), hb.size() * sizeof(T), cudaMemcpyHostToDevice));
     const T *bases[3]   = {d_basis, d_basis + NM * NQ, d_basis + 2 * NM * NQ};
     const int counts[3] = {NM * NQ, NM * NQ, NM * NQ};
-    if (fill_basis_bank<T>(g_bank, DIM, bases, counts, 0))
+    (void)counts;
+    if (fill_basis_bank<T>(g_bank, DIM, bases, NM, NQ, false, 0))
         return 1;
     CK(cudaDeviceSynchronize());
 
