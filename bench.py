@@ -250,7 +250,8 @@ def sweep_coa(fe, torch, peak, reps=5):
     """the warp-interleaved (`_Coa`) entry points at ~64 Mi quadrature points (same algorithmic bytes)"""
     out = []
     st = torch.cuda.current_stream().cuda_stream
-    for dim, nqs, kern in ((2, (2, 4, 8, 10, 16), "BwdTransQuadKernel_Coa"), (3, (2, 4, 6, 8), "BwdTransHexKernel_Coa")):
+    for dim, nqs, kern in ((2, (2, 4, 6, 8, 10, 12, 14, 16, 32), "BwdTransQuadKernel_Coa"),
+                           (3, (2, 4, 6, 8, 10), "BwdTransHexKernel_Coa")):
         for suf, tdt, size in (("f64", torch.float64, 8), ("f32", torch.float32, 4)):
             for nq in nqs:
                 nm = nq - 1

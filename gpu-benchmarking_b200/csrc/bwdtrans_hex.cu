@@ -170,8 +170,37 @@ static int hex_table_lookup(unsigned nq, Backend *preferred)
     return have;
 }
 
+// interleaved layout, lanes back-end (sumfac_lanes.cuh).  Tile shapes (elements per CTA, min CTAs per SM for the register
+// cap) measured with tools/tune/lanes_probe.cu at 64 Mi points (profiles/r01_lanes_probe.csv):
+//   nq            4     5     6     7     8     9    10 (q-outer, 2 slices)
+//   FP64 EL      16    32    32    16    16    16     8
+//   FP32 EL      32    16    16    16    16    16    32
+constexpr unsigned kHexLanesMinNq = 4, kHexLanesMaxNq = 10;
+static int hex_lanes_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
+{
+    constexpr bool D = sizeof(T) == 8;
+    switch (nq)
+    {
+    case 4:
+        return launch_hex_lanes<T, 4, D ? 16 : 32, 1>(nelmt, in, out, s);
+    case 5:
+        return launch_hex_lanes<T, 5, D ? 32 : 16, 1>(nelmt, in, out, s);
+    case 6:
+        return launch_hex_lanes<T, 6, D ? 32 : 16, 1>(nelmt, in, out, s);
+    case 7:
+        return launch_hex_lanes<T, 7, 16, 1>(nelmt, in, out, s);
+    case 8:
+        return launch_hex_lanes<T, 8, 16, D ? 1 : 5>(nelmt, in, out, s);
+    case 9:
+        return launch_hex_lanes<T, 9, 16, 1>(nelmt, in, out, s);
+    case 10:
+        return launch_hex_lanesq<T, 10, D ? 8 : 32, 2>(nelmt, in, out, s);
+    default:
+        return B200FE_EUNSUPPORTED;
+    }
+}
+
 // registers hold nm^3 + nm^2 + nm values per thread
-constexpr unsigned kHexTpeMaxNq = 5;
 
 static int hex_tpe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
 {
@@ -205,7 +234,9 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
         if (!regular)
             be = Backend::Generic;
         else if (coa)
-            be = nq0 <= kHexTpeMaxNq ? Backend::Tpe : ((have & 1) ? Backend::Rows : Backend::Generic);
+            be = (nq0 < kHexLanesMinNq || (nq0 == 5 && sizeof(T) == 8)) ? Backend::Tpe // FP64 nq = 5: 0.94 against 0.88
+                 : nq0 <= kHexLanesMaxNq ? Backend::Lanes
+                                         : ((have & 1) ? Backend::Rows : Backend::Generic);
         else
             be = preferred;
         // the bulk-copy ring needs a 16-byte aligned slab; otherwise take the plain-load twin
@@ -222,7 +253,7 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
         return launch_hex_generic<T>(nm0, nm1, nm2, nq0, nq1, nq2, nelmt, b0, b1, b2, in, out, coa, stream);
     }
     if (!regular || ((be == Backend::Pipe || be == Backend::Mma || be == Backend::Nm1) && coa) ||
-        (be == Backend::Tpe && !coa) || (be == Backend::Rows && !(have & 1)))
+        (be == Backend::Tpe && !coa) || (be == Backend::Lanes && !coa) || (be == Backend::Rows && !(have & 1)))
         return B200FE_EUNSUPPORTED;
     if (be == Backend::Pipe && (!(have & 2) || !aligned16(in)))
         return B200FE_EUNSUPPORTED;
@@ -240,6 +271,8 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
         rc = coa ? hex_rowscoa_switch(nq0, nelmt, in, out, stream) : hex_rows_switch(nq0, nelmt, in, out, stream);
     else if (be == Backend::Pipe)
         rc = hex_pipe_switch(nq0, nelmt, in, out, stream);
+    else if (be == Backend::Lanes)
+        rc = hex_lanes_switch(nq0, nelmt, in, out, stream);
     else
         rc = hex_tpe_switch(nq0, nelmt, in, out, stream);
     if (rc)

@@ -12,6 +12,7 @@
 #include "sumfac_mma32.cuh"
 #include "sumfac_nm1.cuh"
 #include "sumfac_rows.cuh"
+#include "sumfac_lanes.cuh"
 #include "sumfac_rows_coa.cuh"
 #include "sumfac_tpe.cuh"
 
@@ -244,6 +245,52 @@ int launch_hex_rowscoa(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
     B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt));
     count_launch();
     t_last_backend = "rows-coa";
+    return launch_status();
+}
+
+// ---- interleaved layout, lanes = elements, an element's work split over the warps of the CTA (sumfac_lanes.cuh)
+template <typename T, int NQ, int EL> int launch_quad_lanes(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
+{
+    using C = QuadLanes<T, NQ, EL>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "intermediate does not fit shared memory");
+    auto kernel = bwdtrans_quad_lanes_kernel<T, NQ, EL>;
+    int rc      = opt_in_smem(kernel, C::SMEM);
+    if (rc)
+        return rc;
+    const unsigned grid = nelmt / EL; // nelmt % 32 == 0
+    B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt));
+    count_launch();
+    t_last_backend = "lanes";
+    return launch_status();
+}
+template <typename T, int NQ, int EL, int MINB>
+int launch_hex_lanes(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
+{
+    using C = HexLanes<T, NQ, EL>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "intermediate does not fit shared memory");
+    auto kernel = bwdtrans_hex_lanes_kernel<T, NQ, EL, MINB>;
+    int rc      = opt_in_smem(kernel, C::SMEM);
+    if (rc)
+        return rc;
+    const unsigned grid = nelmt / EL;
+    B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt));
+    count_launch();
+    t_last_backend = "lanes";
+    return launch_status();
+}
+
+template <typename T, int NQ, int EL, int IH> int launch_hex_lanesq(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
+{
+    using C = HexLanesQ<T, NQ, EL, IH>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "intermediate does not fit shared memory");
+    auto kernel = bwdtrans_hex_lanesq_kernel<T, NQ, EL, IH, 1>;
+    int rc      = opt_in_smem(kernel, C::SMEM);
+    if (rc)
+        return rc;
+    const unsigned grid = nelmt / EL;
+    B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt));
+    count_launch();
+    t_last_backend = "lanes";
     return launch_status();
 }
 

@@ -171,8 +171,45 @@ static int quad_table_lookup(unsigned nq, Backend *preferred)
     return have;
 }
 
+// interleaved layout, lanes back-end (sumfac_lanes.cuh): nq = 4 .. 16 and 32.  A CTA takes a whole interleave group
+// (EL = 32) except where the block would exceed 1024 threads or, FP64 nq = 16, two half groups per SM measured better
+// (tools/tune/lanes_probe.cu, profiles/r01_lanes_probe.csv).
+// Against the thread-per-element kernel (tools/coa_compare.py, profiles/r01_coa_compare.csv): FP64 lanes wins from
+// nq = 4 (0.96-1.01 of the measured copy bandwidth against 0.67-0.97), FP32 from nq = 7 (small CTAs below that).
+constexpr unsigned kQuadLanesMinNq = sizeof(T) == 8 ? 4 : 7;
+static bool quad_has_lanes(unsigned nq)
+{
+    return (nq >= 4 && nq <= 16) || nq == 32;
+}
+static int quad_lanes_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
+{
+    constexpr bool D = sizeof(T) == 8;
+    switch (nq)
+    {
+#define LANES_CASE(NQ, EL)                                                                                   \
+    case NQ:                                                                                                 \
+        return launch_quad_lanes<T, NQ, EL>(nelmt, in, out, s);
+        LANES_CASE(4, 32)
+        LANES_CASE(5, 32)
+        LANES_CASE(6, 32)
+        LANES_CASE(7, 32)
+        LANES_CASE(8, 32)
+        LANES_CASE(9, 32)
+        LANES_CASE(10, 32)
+        LANES_CASE(11, 32)
+        LANES_CASE(12, 32)
+        LANES_CASE(13, 32)
+        LANES_CASE(14, 32)
+        LANES_CASE(15, 32)
+        LANES_CASE(16, (D ? 16 : 32))
+        LANES_CASE(32, 16)
+#undef LANES_CASE
+    default:
+        return B200FE_EUNSUPPORTED;
+    }
+}
+
 // registers hold nm^2 + nm values per thread
-constexpr unsigned kQuadTpeMaxNq = 10;
 
 static int quad_tpe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
 {
@@ -211,7 +248,9 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
         if (!regular)
             be = Backend::Generic;
         else if (coa)
-            be = nq0 <= kQuadTpeMaxNq ? Backend::Tpe : ((have & 1) ? Backend::Rows : Backend::Generic);
+            be = nq0 < kQuadLanesMinNq ? Backend::Tpe
+                 : quad_has_lanes(nq0) ? Backend::Lanes
+                                       : ((have & 1) ? Backend::Rows : Backend::Generic);
         else if (nq0 == 2 && sizeof(T) == 4)
             be = Backend::Nm1; // measured: 0.81 vs 0.63 (pipe) for FP32; FP64 and hex stay on the table's choice
         else
@@ -230,7 +269,7 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
         return launch_quad_generic<T>(nm0, nm1, nq0, nq1, nelmt, b0, b1, in, out, coa, stream);
     }
     if (!regular || ((be == Backend::Pipe || be == Backend::Mma || be == Backend::Nm1) && coa) ||
-        (be == Backend::Tpe && !coa) || (be == Backend::Rows && !(have & 1)))
+        (be == Backend::Tpe && !coa) || (be == Backend::Lanes && !coa) || (be == Backend::Rows && !(have & 1)))
         return B200FE_EUNSUPPORTED;
     if (be == Backend::Pipe && (!(have & 2) || !aligned16(in)))
         return B200FE_EUNSUPPORTED;
@@ -248,6 +287,8 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
         rc = coa ? quad_rowscoa_switch(nq0, nelmt, in, out, stream) : quad_rows_switch(nq0, nelmt, in, out, stream);
     else if (be == Backend::Pipe)
         rc = quad_pipe_switch(nq0, nelmt, in, out, stream);
+    else if (be == Backend::Lanes)
+        rc = quad_lanes_switch(nq0, nelmt, in, out, stream);
     else
         rc = quad_tpe_switch(nq0, nelmt, in, out, stream);
     if (rc)

@@ -337,6 +337,8 @@ int b200fe_set_backend(const char *name)
         g_forced_backend = (int)Backend::Nm1;
     else if (!strcmp(name, "tpe"))
         g_forced_backend = (int)Backend::Tpe;
+    else if (!strcmp(name, "lanes"))
+        g_forced_backend = (int)Backend::Lanes;
     else if (!strcmp(name, "generic"))
         g_forced_backend = (int)Backend::Generic;
     else

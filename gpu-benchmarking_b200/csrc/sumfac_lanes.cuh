@@ -1,0 +1,359 @@
+// sumfac_lanes.cuh -- "lanes" back-end for the warp-interleaved layout of the reference's
+// "Coales" kernels (benchmark04.cc:78-147, benchmark05.cc:104-201)
+//     x[(e/32)*32*len + 32*idx + e%32]
+// at the nq where one thread can no longer hold a whole element (sumfac_tpe.cuh).
+//
+// The lanes of a warp still run over the elements of an interleave group, so every global access
+// is a run of EL consecutive values of one in-element index (whole 128-byte lines for EL = 32, or
+// for EL = 16 doubles) and every shared-memory access is conflict-free by construction -- no
+// gather into an element-major tile as in sumfac_rows_coa.cuh.  What is split over the warps of a
+// CTA is the element's work:
+//   hex   phase A  worker r owns the plane in[r][.][.] (nm^2 registers, read from HBM with all the
+//                  loads of the plane in flight), contracts directions 0 and 1 in registers and
+//                  leaves t2[r][j][i] in shared memory;
+//         phase B  worker w takes (j, i) rows w, w + NW, ...: nm values from shared memory,
+//                  direction 2, nq coalesced stores.
+//   quad  phase A  worker q owns the row in[q][.] -> t1[q][i] in shared memory;
+//         phase B  worker i owns the column t1[.][i] -> out[.][i], stored straight to global.
+// Summation order is the reference's (p, then q, then r, ascending, starting from +0), the basis
+// operand comes from the constant bank, FP32 accumulators are FFMA2 pairs (RowAcc, sumfac_rows.cuh).
+// Shared memory holds only the last intermediate: nm*nq^2*EL values (hex), nm*nq*EL (quad).
+#pragma once
+
+#include "sumfac_rows.cuh"
+
+namespace b200fe
+{
+
+// NQ outputs of one row of NM register values against bank matrix BOFF, in blocks of IB outputs;
+// st(j, value) consumes output j
+template <typename T, int NM, int NQ, int BOFF, typename St>
+__device__ __forceinline__ void lanes_row(const T (&x)[NM], St st)
+{
+    constexpr int PITCH = bank_pitch<T>(NQ);
+    if constexpr (unrolled_ib<NM, NQ, (int)sizeof(T)>() < 2)
+    {
+        // very long rows (nq = 32): the basis of even a 2-wide block exceeds the uniform registers, so the
+        // loop over the output blocks stays a loop (register-indexed 8-byte uniform loads, one per FMA pair)
+        constexpr int RB = 8;
+        static_assert(NQ % RB == 0, "rolled blocks");
+#pragma unroll 1
+        for (int ib = 0; ib < NQ; ib += RB)
+        {
+            RowAcc<T, RB> t;
+            t.zero();
+#pragma unroll
+            for (int p = 0; p < NM; ++p)
+            {
+                T b[RB];
+                cbasis_load<RB, (sizeof(T) == 4)>(BOFF + p * PITCH + ib, b);
+                t.fma(x[p], b);
+            }
+#pragma unroll
+            for (int j = 0; j < RB; ++j)
+                st(ib + j, t.get(j));
+        }
+    }
+    else
+    {
+        constexpr int IB = unrolled_ib<NM, NQ, (int)sizeof(T)>();
+#pragma unroll
+        for (int ib = 0; ib + IB <= NQ; ib += IB)
+        {
+            RowAcc<T, IB> t;
+            t.zero();
+#pragma unroll
+            for (int p = 0; p < NM; ++p)
+            {
+                T b[IB];
+                cbasis_load<IB, true>(BOFF + p * PITCH + ib, b);
+                t.fma(x[p], b);
+            }
+#pragma unroll
+            for (int j = 0; j < IB; ++j)
+                st(ib + j, t.get(j));
+        }
+        constexpr int TAIL = NQ % IB;
+        if constexpr (TAIL > 0)
+        {
+            RowAcc<T, TAIL> t;
+            t.zero();
+#pragma unroll
+            for (int p = 0; p < NM; ++p)
+            {
+                T b[TAIL];
+                cbasis_load<TAIL, true>(BOFF + p * PITCH + (NQ - TAIL), b);
+                t.fma(x[p], b);
+            }
+#pragma unroll
+            for (int j = 0; j < TAIL; ++j)
+                st(NQ - TAIL + j, t.get(j));
+        }
+    }
+}
+
+template <typename T, int NQ, int EL> struct QuadLanes
+{
+    static_assert(EL == 8 || EL == 16 || EL == 32, "a tile is a power-of-two slice of an interleave group");
+    static constexpr int NM = NQ - 1, NM2 = NM * NM, NQ2 = NQ * NQ;
+    static constexpr int THREADS = EL * NQ;
+    static constexpr size_t SMEM = (size_t)NM * NQ * EL * sizeof(T);
+    static_assert(THREADS <= 1024 && THREADS % 32 == 0, "block size");
+};
+
+template <typename T, int NQ, int EL>
+__global__ void __launch_bounds__(QuadLanes<T, NQ, EL>::THREADS)
+    bwdtrans_quad_lanes_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
+{
+    using C           = QuadLanes<T, NQ, EL>;
+    constexpr int NM  = C::NM;
+    constexpr int BP  = bank_pitch<T>(NQ), B0 = 0, B1 = NM * BP;
+    constexpr int PER = 32 / EL; // tiles per interleave group
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *s1 = reinterpret_cast<T *>(smem_raw);
+    (void)nelmt; // nelmt % 32 == 0 is checked at the C ABI: every tile is full
+
+    const int e = threadIdx.x % EL, w = threadIdx.x / EL;
+    const unsigned group = blockIdx.x / PER, l0 = (blockIdx.x % PER) * EL;
+    const T *gin = in + (size_t)group * 32 * C::NM2 + l0 + e;
+    T *gout      = out + (size_t)group * 32 * C::NQ2 + l0 + e;
+
+    if (w < NM)
+    {
+        T x[NM];
+        const T *px = gin + (size_t)w * (32 * NM);
+#pragma unroll
+        for (int p = 0; p < NM; ++p)
+            x[p] = ld_stream(px + 32 * p);
+        grid_dependency_wait();
+        T *dst = s1 + (size_t)(w * NQ) * EL + e;
+        lanes_row<T, NM, NQ, B0>(x, [&](int i, T v) { dst[i * EL] = v; });
+    }
+    else
+        grid_dependency_wait();
+    __syncthreads();
+    {
+        T x[NM];
+        const T *src = s1 + (size_t)w * EL + e;
+#pragma unroll
+        for (int q = 0; q < NM; ++q)
+            x[q] = src[q * NQ * EL];
+        T *dst = gout + 32 * w;
+        lanes_row<T, NM, NQ, B1>(x, [&](int j, T v) { st_stream(dst + 32 * NQ * j, v); });
+    }
+}
+
+// directions 0 and 1 of one plane for the IBW outputs i in [ib, ib + IBW): t1[q][i] for every q in registers
+// (the basis values of a (p, i-block) are shared by the nm rows q), then column i of t1 against B1 -> t2[j][i]
+template <typename T, int NQ, int EL, int IBW>
+__device__ __forceinline__ void hex_lanes_block(const T (&a)[(NQ - 1) * (NQ - 1)], T *dst, int ib)
+{
+    constexpr int NM = NQ - 1, BP = bank_pitch<T>(NQ), B0 = 0, B1 = NM * BP;
+    RowAcc<T, IBW> t1[NM];
+#pragma unroll
+    for (int q = 0; q < NM; ++q)
+        t1[q].zero();
+#pragma unroll
+    for (int p = 0; p < NM; ++p)
+    {
+        T b[IBW];
+        cbasis_load<IBW, true>(B0 + p * BP + ib, b);
+#pragma unroll
+        for (int q = 0; q < NM; ++q)
+            t1[q].fma(a[q * NM + p], b);
+    }
+#pragma unroll
+    for (int ii = 0; ii < IBW; ++ii)
+    {
+        T x[NM];
+#pragma unroll
+        for (int q = 0; q < NM; ++q)
+            x[q] = t1[q].get(ii);
+        T *d = dst + (ib + ii) * EL;
+        lanes_row<T, NM, NQ, B1>(x, [&](int j, T v) { d[j * NQ * EL] = v; });
+    }
+}
+
+template <typename T, int NQ, int EL> struct HexLanes
+{
+    static_assert(EL == 8 || EL == 16 || EL == 32, "a tile is a power-of-two slice of an interleave group");
+    static constexpr int NM = NQ - 1, NM2 = NM * NM, NM3 = NM2 * NM, NQ2 = NQ * NQ, NQ3 = NQ2 * NQ;
+    static constexpr int THREADS = (EL * NM + 31) / 32 * 32;
+    static constexpr int NW      = THREADS / EL; // workers per element (>= NM)
+    static constexpr size_t SMEM = (size_t)NM * NQ2 * EL * sizeof(T);
+    // direction-0 outputs kept per register block: pairs for the packed FP32 FMA
+    static constexpr int IB0 = sizeof(T) == 4 ? 2 : 1;
+    // FP64: the loop over the direction-0 output blocks stays a loop.  Unrolled, ptxas computes t1 for every i
+    // at once (nm*nq live doubles on top of the plane: 230 registers at nq = 8, spills at nq = 10).
+    static constexpr bool ROLLED = sizeof(T) == 8;
+};
+
+template <typename T, int NQ, int EL, int MINB = 1>
+__global__ void __launch_bounds__(HexLanes<T, NQ, EL>::THREADS, MINB)
+    bwdtrans_hex_lanes_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
+{
+    using C           = HexLanes<T, NQ, EL>;
+    constexpr int NM = C::NM, NM2 = C::NM2, NQ2 = C::NQ2, NW = C::NW, IB0 = C::IB0;
+    constexpr int BP  = bank_pitch<T>(NQ), B2 = 2 * NM * BP;
+    constexpr int PER = 32 / EL;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *s2 = reinterpret_cast<T *>(smem_raw);
+    (void)nelmt;
+
+    const int e = threadIdx.x % EL, w = threadIdx.x / EL;
+    const unsigned group = blockIdx.x / PER, l0 = (blockIdx.x % PER) * EL;
+    const T *gin = in + (size_t)group * 32 * C::NM3 + l0 + e;
+    T *gout      = out + (size_t)group * 32 * C::NQ3 + l0 + e; // intended group stride (benchmark05.cc:810-812)
+
+    if (w < NM)
+    {
+        // plane r = w of the element, whole in registers
+        T a[NM2];
+        const T *pa = gin + (size_t)w * (32 * NM2); // one base register, immediate offsets
+#pragma unroll
+        for (int k = 0; k < NM2; ++k)
+            a[k] = ld_stream(pa + 32 * k);
+        grid_dependency_wait();
+        T *dst = s2 + (size_t)(w * NQ2) * EL + e;
+        if constexpr (C::ROLLED)
+        {
+#pragma unroll 1
+            for (int ib = 0; ib + IB0 <= NQ; ib += IB0)
+                hex_lanes_block<T, NQ, EL, IB0>(a, dst, ib);
+        }
+        else
+        {
+#pragma unroll
+            for (int ib = 0; ib + IB0 <= NQ; ib += IB0)
+                hex_lanes_block<T, NQ, EL, IB0>(a, dst, ib);
+        }
+        if constexpr (NQ % IB0 != 0) // odd nq in FP32: the last output alone
+            hex_lanes_block<T, NQ, EL, 1>(a, dst, NQ - 1);
+    }
+    else
+        grid_dependency_wait();
+    __syncthreads();
+
+    // direction 2: rows (j, i) of t2 over r, nq outputs each straight to global
+    constexpr int ITER = (NQ2 + NW - 1) / NW;
+#pragma unroll 1
+    for (int it = 0; it < ITER; ++it)
+    {
+        const int ji = w + it * NW;
+        if (ji >= NQ2)
+            break;
+        T x[NM];
+        const T *src = s2 + (size_t)ji * EL + e;
+#pragma unroll
+        for (int r = 0; r < NM; ++r)
+            x[r] = src[r * NQ2 * EL];
+        T *dst = gout + 32 * ji;
+        lanes_row<T, NM, NQ, B2>(x, [&](int k, T v) { st_stream(dst + 32 * NQ2 * k, v); });
+    }
+}
+
+// ---- hex, q-outer variant for the nq whose plane no longer fits the register file (nq = 10): worker (r, ih) streams
+// the rows in[r][q][.] of its plane one at a time and keeps the accumulators t2[r][.][i] of its slice of NQ/IH outputs i
+// (fma over q ascending: the reference's order), so only nq*nq/IH accumulators + one row are live.  The IH workers of
+// a plane read the same rows (the second read hits L1).
+template <typename T, int NQ, int EL, int IH, int I0>
+__device__ __forceinline__ void hex_lanes_plane_q(const T *pa, T *dst)
+{
+    constexpr int NM = NQ - 1, NI = NQ / IH, W = 16 / (int)sizeof(T);
+    constexpr int BP = bank_pitch<T>(NQ), B0 = 0, B1 = NM * BP;
+    RowAcc<T, NQ> acc[NI];
+#pragma unroll
+    for (int ii = 0; ii < NI; ++ii)
+        acc[ii].zero();
+#pragma unroll
+    for (int q = 0; q < NM; ++q)
+    {
+        T a[NM];
+#pragma unroll
+        for (int p = 0; p < NM; ++p)
+            a[p] = ld_stream(pa + 32 * (q * NM + p));
+        RowAcc<T, NI> t;
+        t.zero();
+#pragma unroll
+        for (int p = 0; p < NM; ++p)
+        {
+            T b[NI];
+            cbasis_load<NI, (I0 % W == 0)>(B0 + p * BP + I0, b);
+            t.fma(a[p], b);
+        }
+        T b1[NQ];
+        cbasis_load<NQ, true>(B1 + q * BP, b1);
+#pragma unroll
+        for (int ii = 0; ii < NI; ++ii)
+            acc[ii].fma(t.get(ii), b1);
+    }
+#pragma unroll
+    for (int ii = 0; ii < NI; ++ii)
+#pragma unroll
+        for (int j = 0; j < NQ; ++j)
+            dst[(j * NQ + I0 + ii) * EL] = acc[ii].get(j);
+}
+
+template <typename T, int NQ, int EL, int IH> struct HexLanesQ
+{
+    static constexpr int NM = NQ - 1, NM2 = NM * NM, NM3 = NM2 * NM, NQ2 = NQ * NQ, NQ3 = NQ2 * NQ;
+    static constexpr int WPI     = (NM * EL + 31) / 32 * 32 / EL; // workers per i-slice: whole warps, so a warp's slice is uniform
+    static constexpr int NW      = WPI * IH;
+    static constexpr int THREADS = NW * EL;
+    static constexpr size_t SMEM = (size_t)NM * NQ2 * EL * sizeof(T);
+    static_assert(NQ % IH == 0, "");
+};
+
+template <typename T, int NQ, int EL, int IH, int MINB>
+__global__ void __launch_bounds__(HexLanesQ<T, NQ, EL, IH>::THREADS, MINB)
+    bwdtrans_hex_lanesq_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
+{
+    using C           = HexLanesQ<T, NQ, EL, IH>;
+    constexpr int NM = C::NM, NM2 = C::NM2, NQ2 = C::NQ2, NW = C::NW, NI = NQ / IH;
+    constexpr int BP  = bank_pitch<T>(NQ), B2 = 2 * NM * BP;
+    constexpr int PER = 32 / EL;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *s2 = reinterpret_cast<T *>(smem_raw);
+    (void)nelmt;
+    const int e = threadIdx.x % EL, w = threadIdx.x / EL;
+    const unsigned group = blockIdx.x / PER, l0 = (blockIdx.x % PER) * EL;
+    const T *gin = in + (size_t)group * 32 * C::NM3 + l0 + e;
+    T *gout      = out + (size_t)group * 32 * C::NQ3 + l0 + e;
+    const int ih = w / C::WPI, r = w - ih * C::WPI;
+    if (r < NM)
+    {
+        const T *pa = gin + (size_t)r * (32 * NM2);
+        T *dst      = s2 + (size_t)(r * NQ2) * EL + e;
+        grid_dependency_wait();
+        if constexpr (IH == 1)
+            hex_lanes_plane_q<T, NQ, EL, IH, 0>(pa, dst);
+        else if constexpr (IH == 2)
+        {
+            if (ih == 0)
+                hex_lanes_plane_q<T, NQ, EL, IH, 0>(pa, dst);
+            else
+                hex_lanes_plane_q<T, NQ, EL, IH, NI>(pa, dst);
+        }
+    }
+    else
+        grid_dependency_wait();
+    __syncthreads();
+    constexpr int ITER = (NQ2 + NW - 1) / NW;
+#pragma unroll 1
+    for (int it = 0; it < ITER; ++it)
+    {
+        const int ji = w + it * NW;
+        if (ji >= NQ2)
+            break;
+        T x[NM];
+        const T *src = s2 + (size_t)ji * EL + e;
+#pragma unroll
+        for (int rr = 0; rr < NM; ++rr)
+            x[rr] = src[rr * NQ2 * EL];
+        T *dst = gout + 32 * ji;
+        lanes_row<T, NM, NQ, B2>(x, [&](int k, T v) { st_stream(dst + 32 * NQ2 * k, v); });
+    }
+}
+
+
+} // namespace b200fe

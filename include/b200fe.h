@@ -306,7 +306,7 @@ int b200fe_bwdtrans_hex_host_f32(unsigned nq0, unsigned nq1, unsigned nq2, size_
 
 /* ---- tuning / introspection (not part of the reference surface) -----------------
  * Force a back-end for the BwdTrans entry points of the calling process:
- * "auto" (default routing), "rows", "pipe", "mma", "nm1", "tpe", "generic".  Returns 0 or
+ * "auto" (default routing), "rows", "pipe", "mma", "nm1", "tpe", "lanes", "generic".  Returns 0 or
  * B200FE_EINVAL for an unknown name; an entry point then returns
  * B200FE_EUNSUPPORTED where the forced back-end has no instantiation.  Used by the tuner and the parity tests to
  * exercise every back-end through the same C ABI. */

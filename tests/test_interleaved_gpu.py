@@ -1,0 +1,160 @@
+"""The warp-interleaved ("Coales") entry points, back-end by back-end, through the C ABI.
+
+Layout (reference benchmark04.cc:78-147, benchmark05.cc:104-201): x[(e/32)*32*len + 32*idx + e%32].
+Three back-ends serve it -- thread per element (tpe, small nq), lanes (lanes = elements, an element's planes /
+rows split over the warps of a CTA; the default from nq = 4), rows through a gather (the remaining nq) -- and
+every one of them must reproduce the oracle BIT FOR BIT: they all accumulate in the reference's order with fused
+multiply-adds.  Inputs differ per element and per interleave group, so a wrong lane / group offset shows.
+"""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from tests import gpu_util
+    assert gpu_util.fe.check_device() == 0, "not an sm_100 device"
+    return gpu_util
+
+
+def rnd(rng, n, dt):
+    return rng.standard_normal(n).astype(dt)
+
+
+def quad_case(G, suf, nq, nelmt, seed):
+    dt, nm = G.NP[suf], nq - 1
+    rng = np.random.default_rng(seed)
+    b0, b1 = rnd(rng, nm * nq, dt), rnd(rng, nm * nq, dt)
+    inp_em = rnd(rng, nelmt * nm * nm, dt)
+    want_em = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp_em)
+    return b0, b1, oracle.to_coa(inp_em, nelmt, nm * nm), want_em
+
+
+def hex_case(G, suf, nq, nelmt, seed):
+    dt, nm = G.NP[suf], nq - 1
+    rng = np.random.default_rng(seed)
+    b = [rnd(rng, nm * nq, dt) for _ in range(3)]
+    inp_em = rnd(rng, nelmt * nm ** 3, dt)
+    want_em = oracle.bwdtrans_hex(nq, nq, nq, nelmt, *b, inp_em)
+    return b, oracle.to_coa(inp_em, nelmt, nm ** 3), want_em
+
+
+QUAD_LANES_NQ = list(range(4, 17)) + [32]
+HEX_LANES_NQ = list(range(4, 11))
+
+
+@pytest.mark.parametrize("suf", ["f64", "f32"])
+@pytest.mark.parametrize("nq", QUAD_LANES_NQ)
+def test_quad_lanes_backend_bit_exact(G, suf, nq):
+    nelmt = 32 * 7  # several groups, not a multiple of anything else
+    b0, b1, inp, want_em = quad_case(G, suf, nq, nelmt, 3000 + nq)
+    try:
+        G.fe.set_backend("lanes")
+        got = G.run_quad("BwdTransQuadKernel_Coa", suf, nq, nq, nelmt, b0, b1, inp)
+        assert G.fe.last_backend() == "lanes"
+    finally:
+        G.fe.set_backend("auto")
+    assert np.array_equal(oracle.from_coa(got, nelmt, nq * nq), want_em)
+    # the default routing: lanes, except FP32 nq <= 6 where the thread-per-element kernel measured faster
+    got = G.run_quad("BwdTransQuadKernel_Coa", suf, nq, nq, nelmt, b0, b1, inp)
+    assert G.fe.last_backend() == ("tpe" if suf == "f32" and nq <= 6 else "lanes")
+    assert np.array_equal(oracle.from_coa(got, nelmt, nq * nq), want_em)
+
+
+@pytest.mark.parametrize("suf", ["f64", "f32"])
+@pytest.mark.parametrize("nq", HEX_LANES_NQ)
+def test_hex_lanes_backend_bit_exact(G, suf, nq):
+    nelmt = 32 * 5
+    b, inp, want_em = hex_case(G, suf, nq, nelmt, 3100 + nq)
+    try:
+        G.fe.set_backend("lanes")
+        got = G.run_hex("BwdTransHexKernel_Coa", suf, (nq, nq, nq), nelmt, b, inp)
+        assert G.fe.last_backend() == "lanes"
+    finally:
+        G.fe.set_backend("auto")
+    assert np.array_equal(oracle.from_coa(got, nelmt, nq ** 3), want_em)
+    got = G.run_hex("BwdTransHexKernel_Coa", suf, (nq, nq, nq), nelmt, b, inp)
+    assert G.fe.last_backend() == ("tpe" if suf == "f64" and nq == 5 else "lanes")
+    assert np.array_equal(oracle.from_coa(got, nelmt, nq ** 3), want_em)
+
+
+@pytest.mark.parametrize("suf", ["f64", "f32"])
+@pytest.mark.parametrize("backend,nqs", [("tpe", [2, 3, 4, 6, 8, 10]), ("rows", [4, 8, 11, 16, 20, 32])])
+def test_quad_other_interleaved_backends_stay_bit_exact(G, suf, backend, nqs):
+    for nq in nqs:
+        nelmt = 32 * 3
+        b0, b1, inp, want_em = quad_case(G, suf, nq, nelmt, 3200 + nq)
+        try:
+            G.fe.set_backend(backend)
+            got = G.run_quad("BwdTransQuadKernel_Coa", suf, nq, nq, nelmt, b0, b1, inp)
+            assert G.fe.last_backend() == ("rows-coa" if backend == "rows" else backend)
+        finally:
+            G.fe.set_backend("auto")
+        assert np.array_equal(oracle.from_coa(got, nelmt, nq * nq), want_em), (backend, nq)
+
+
+@pytest.mark.parametrize("suf", ["f64", "f32"])
+@pytest.mark.parametrize("backend,nqs", [("tpe", [2, 3, 4, 5]), ("rows", [4, 6, 8, 11, 12])])
+def test_hex_other_interleaved_backends_stay_bit_exact(G, suf, backend, nqs):
+    for nq in nqs:
+        nelmt = 32 * 2
+        b, inp, want_em = hex_case(G, suf, nq, nelmt, 3300 + nq)
+        try:
+            G.fe.set_backend(backend)
+            got = G.run_hex("BwdTransHexKernel_Coa", suf, (nq, nq, nq), nelmt, b, inp)
+            assert G.fe.last_backend() == ("rows-coa" if backend == "rows" else backend)
+        finally:
+            G.fe.set_backend("auto")
+        assert np.array_equal(oracle.from_coa(got, nelmt, nq ** 3), want_em), (backend, nq)
+
+
+def test_lanes_backend_is_interleaved_only(G):
+    b0, b1, inp, _ = quad_case(G, "f64", 8, 32, 1)
+    try:
+        G.fe.set_backend("lanes")
+        with pytest.raises(Exception):
+            G.run_quad("BwdTransQuadKernel", "f64", 8, 8, 32, b0, b1, inp)
+        with pytest.raises(Exception):  # no lanes instantiation at this nq
+            G.run_quad("BwdTransQuadKernel_Coa", "f64", 20, 20, 32, *quad_case(G, "f64", 20, 32, 2)[:3])
+    finally:
+        G.fe.set_backend("auto")
+
+
+@pytest.mark.parametrize("suf", ["f64", "f32"])
+def test_lanes_full_size_checksum_of_checksums(G, suf):
+    """BASELINE.json's size (64 Mi points) through a size-independent property: every element gets the same modes,
+    so every element's output must equal element 0's, which the oracle checks; the layout makes lane e of group g
+    a different address pattern for every (g, e)."""
+    import torch
+    dt = G.NP[suf]
+    for dim, nq in ((2, 16), (3, 8)):
+        nm = nq - 1
+        nelmt = (64 << 20) // nq ** dim // 32 * 32
+        rng = np.random.default_rng(77 + nq)
+        b = [rnd(rng, nm * nq, dt) for _ in range(dim)]
+        one = rnd(rng, nm ** dim, dt)
+        d_in = G.dev(one).repeat_interleave(32).reshape(1, -1).repeat(nelmt // 32, 1).reshape(-1).contiguous()
+        d_b = [G.dev(x) for x in b]
+        d_out = torch.empty(nelmt * nq ** dim, dtype=d_in.dtype, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        if dim == 2:
+            want = oracle.bwdtrans_quad(nq, nq, 1, b[0], b[1], one)
+            G.fe.bwdtrans_quad("BwdTransQuadKernel_Coa", suf, nq, nq, nelmt, d_b[0].data_ptr(), d_b[1].data_ptr(),
+                               d_in.data_ptr(), d_out.data_ptr(), stream=st)
+        else:
+            want = oracle.bwdtrans_hex(nq, nq, nq, 1, *b, one)
+            G.fe.bwdtrans_hex("BwdTransHexKernel_Coa", suf, nq, nq, nq, nelmt, d_b[0].data_ptr(), d_b[1].data_ptr(),
+                              d_b[2].data_ptr(), d_in.data_ptr(), d_out.data_ptr(), stream=st)
+        assert G.fe.last_backend() == "lanes"
+        torch.cuda.synchronize()
+        # out_coa[g][m][e] == want[m] for every g, e
+        view = d_out.reshape(nelmt // 32, nq ** dim, 32)
+        d_want = G.dev(want).reshape(1, -1, 1)
+        assert bool((view == d_want).all()), (dim, nq, suf)

@@ -1,0 +1,204 @@
+// lanes_probe.cu -- on-device comparison of the tile shapes of the interleaved-layout "lanes" kernels
+// (csrc/sumfac_lanes.cuh): times every variant listed in main() at ~64 Mi quadrature points and checks it
+// bit for bit against the run-time-size generic kernel.  Build: see tools/README.md.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../gpu-benchmarking_b200/csrc/sumfac_generic.cuh"
+#include "../../gpu-benchmarking_b200/csrc/sumfac_lanes.cuh"
+
+using namespace b200fe;
+namespace b200fe
+{
+std::atomic<unsigned long long> g_launch_count{0};
+thread_local const char *t_last_backend = "";
+}
+
+#define CK(x)                                                                                                \
+    do                                                                                                       \
+    {                                                                                                        \
+        cudaError_t e_ = (x);                                                                                \
+        if (e_ != cudaSuccess)                                                                               \
+        {                                                                                                    \
+            printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__);                  \
+            exit(1);                                                                                         \
+        }                                                                                                    \
+    } while (0)
+
+template <typename T> __global__ void fill_kernel(T *x, size_t n, unsigned seed)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        unsigned h = (unsigned)i * 2654435761u + seed;
+        h ^= h >> 15;
+        h *= 2246822519u;
+        h ^= h >> 13;
+        x[i] = (T)((double)(h & 0xffffff) / 16777216.0 - 0.5);
+    }
+}
+template <typename T> __global__ void diff_kernel(const T *a, const T *b, size_t n, unsigned long long *bad)
+{
+    unsigned long long c = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        if (sizeof(T) == 8)
+            c += (reinterpret_cast<const unsigned long long *>(a)[i] != reinterpret_cast<const unsigned long long *>(b)[i]);
+        else
+            c += (reinterpret_cast<const unsigned *>(a)[i] != reinterpret_cast<const unsigned *>(b)[i]);
+    }
+    if (c)
+        atomicAdd(bad, c);
+}
+
+template <typename T> struct Case
+{
+    int dim, nq;
+    unsigned nelmt;
+    T *b[3], *in, *out, *ref;
+    size_t nin, nout;
+    unsigned long long *bad;
+    BankGuard bank;
+
+    void setup(int dim_, int nq_)
+    {
+        dim = dim_;
+        nq  = nq_;
+        const int nm = nq - 1;
+        size_t pts = 1, modes = 1;
+        for (int d = 0; d < dim; ++d)
+            pts *= nq, modes *= nm;
+        nelmt = (unsigned)((64ull << 20) / pts) / 32 * 32;
+        nin   = modes * nelmt;
+        nout  = pts * nelmt;
+        for (int d = 0; d < 3; ++d)
+        {
+            CK(cudaMalloc(&b[d], sizeof(T) * nm * nq));
+            fill_kernel<T><<<1, 256>>>(b[d], (size_t)nm * nq, 17u + d);
+        }
+        CK(cudaMalloc(&in, sizeof(T) * nin));
+        CK(cudaMalloc(&out, sizeof(T) * nout));
+        CK(cudaMalloc(&ref, sizeof(T) * nout));
+        CK(cudaMalloc(&bad, 8));
+        fill_kernel<T><<<1024, 256>>>(in, nin, 99u);
+        const unsigned n = nm, q = nq;
+        if (dim == 2)
+        {
+            const size_t smem = sizeof(T) * (2 * n * q + n * n + q * n);
+            bwdtrans_quad_generic_kernel<T><<<148 * 8, 128, smem>>>(n, n, q, q, nelmt, b[0], b[1], in, ref, 1);
+        }
+        else
+        {
+            const size_t smem = sizeof(T) * (3 * n * q + n * n * n + q * n * n + q * q * n);
+            CK(cudaFuncSetAttribute(bwdtrans_hex_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            bwdtrans_hex_generic_kernel<T><<<148 * 4, 256, smem>>>(n, n, n, q, q, q, nelmt, b[0], b[1], b[2], in, ref, 1);
+        }
+        CK(cudaDeviceSynchronize());
+        const T *bs[3] = {b[0], b[1], b[2]};
+        if (fill_basis_bank<T>(bank, dim, bs, nm, nq, false, 0))
+        {
+            printf("bank fill failed\n");
+            exit(1);
+        }
+        CK(cudaDeviceSynchronize());
+    }
+    void teardown()
+    {
+        for (int d = 0; d < 3; ++d)
+            cudaFree(b[d]);
+        cudaFree(in);
+        cudaFree(out);
+        cudaFree(ref);
+        cudaFree(bad);
+    }
+    template <typename K> void run(const char *name, K kernel, unsigned grid, int threads, size_t smem)
+    {
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+        CK(cudaMemset(out, 0xff, sizeof(T) * nout));
+        CK(cudaMemset(bad, 0, 8));
+        kernel<<<grid, threads, smem>>>(in, out, nelmt);
+        CK(cudaGetLastError());
+        diff_kernel<T><<<1024, 256>>>(out, ref, nout, bad);
+        unsigned long long nbad = 0;
+        CK(cudaMemcpy(&nbad, bad, 8, cudaMemcpyDeviceToHost));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        float best = 1e30f, sum = 0;
+        const int reps = 12;
+        for (int r = 0; r < reps; ++r)
+        {
+            cudaEventRecord(e0);
+            kernel<<<grid, threads, smem>>>(in, out, nelmt);
+            cudaEventRecord(e1);
+            CK(cudaEventSynchronize(e1));
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            best = ms < best ? ms : best;
+            if (r >= 2)
+                sum += ms;
+        }
+        const double bytes = (double)sizeof(T) * (nin + nout);
+        printf("%s,%d,%s,%d,%d,%zu,%d,%.4f,%.4f,%.1f,%llu\n", dim == 2 ? "quad" : "hex", nq, sizeof(T) == 8 ? "f64" : "f32",
+               0, threads, smem, occ, best, sum / (reps - 2), bytes / (sum / (reps - 2)) * 1e-6, nbad);
+        printf("#   ^ %s\n", name);
+        fflush(stdout);
+    }
+};
+
+#define HP(T, NQ, EL, MB)                                                                                    \
+    c.run("plane EL=" #EL " MINB=" #MB, bwdtrans_hex_lanes_kernel<T, NQ, EL, MB>, c.nelmt / EL,               \
+          HexLanes<T, NQ, EL>::THREADS, HexLanes<T, NQ, EL>::SMEM);
+#define HQ(T, NQ, EL, IH, MB)                                                                                \
+    c.run("q-outer EL=" #EL " IH=" #IH " MINB=" #MB, bwdtrans_hex_lanesq_kernel<T, NQ, EL, IH, MB>, c.nelmt / EL, \
+          HexLanesQ<T, NQ, EL, IH>::THREADS, HexLanesQ<T, NQ, EL, IH>::SMEM);
+#define QL(T, NQ, EL)                                                                                        \
+    c.run("quad EL=" #EL, bwdtrans_quad_lanes_kernel<T, NQ, EL>, c.nelmt / EL, QuadLanes<T, NQ, EL>::THREADS,  \
+          QuadLanes<T, NQ, EL>::SMEM);
+
+#define H3(T, NQ, EL, NWK, MB)                                                                               \
+    c.run("3-phase EL=" #EL " NWK=" #NWK " MINB=" #MB, bwdtrans_hex_lanes3_kernel<T, NQ, EL, NWK, MB>, c.nelmt / EL, \
+          HexLanes3<T, NQ, EL, NWK>::THREADS, HexLanes3<T, NQ, EL, NWK>::SMEM);
+
+int main()
+{
+    printf("op,nq,dtype,_,threads,smem,ctas_per_sm,ms_best,ms_avg,gb_s,mismatches\n");
+    {
+        Case<double> c;
+        c.setup(3, 4); HP(double, 4, 32, 1) HP(double, 4, 16, 1) c.teardown();
+        c.setup(3, 5); HP(double, 5, 32, 1) HP(double, 5, 16, 1) c.teardown();
+        c.setup(3, 7); HP(double, 7, 32, 1) HP(double, 7, 16, 1) H3(double, 7, 16, 16, 1) c.teardown();
+        c.setup(3, 8); H3(double, 8, 16, 16, 1) H3(double, 8, 16, 32, 1) H3(double, 8, 8, 32, 1) c.teardown();
+        c.setup(3, 9); HP(double, 9, 16, 1) H3(double, 9, 8, 32, 1) H3(double, 9, 8, 64, 1) H3(double, 9, 16, 32, 1) c.teardown();
+        c.setup(3, 10); H3(double, 10, 8, 32, 1) H3(double, 10, 8, 64, 1) H3(double, 10, 16, 32, 1) H3(double, 10, 8, 48, 1) c.teardown();
+    }
+    {
+        Case<float> c;
+        c.setup(3, 4); HP(float, 4, 32, 1) HP(float, 4, 16, 1) c.teardown();
+        c.setup(3, 5); HP(float, 5, 32, 1) HP(float, 5, 16, 1) c.teardown();
+        c.setup(3, 7); HP(float, 7, 32, 1) HP(float, 7, 16, 1) HP(float, 7, 16, 6) c.teardown();
+        c.setup(3, 8); HP(float, 8, 16, 4) HP(float, 8, 16, 6) H3(float, 8, 16, 32, 1) H3(float, 8, 32, 16, 1) c.teardown();
+        c.setup(3, 9); HP(float, 9, 16, 1) HP(float, 9, 32, 1) H3(float, 9, 16, 32, 1) H3(float, 9, 32, 16, 1) H3(float, 9, 16, 64, 1) c.teardown();
+        c.setup(3, 10); H3(float, 10, 16, 32, 1) H3(float, 10, 32, 16, 1) H3(float, 10, 16, 64, 1) H3(float, 10, 32, 32, 1) H3(float, 10, 8, 64, 1) c.teardown();
+    }
+    {
+        Case<double> c;
+        c.setup(2, 4); QL(double, 4, 32) QL(double, 4, 16) c.teardown();
+        c.setup(2, 6); QL(double, 6, 32) QL(double, 6, 16) c.teardown();
+        c.setup(2, 8); QL(double, 8, 32) QL(double, 8, 16) c.teardown();
+        c.setup(2, 14); QL(double, 14, 32) QL(double, 14, 16) c.teardown();
+        c.setup(2, 32); QL(double, 32, 16) QL(double, 32, 32) QL(double, 32, 8) c.teardown();
+    }
+    {
+        Case<float> c;
+        c.setup(2, 4); QL(float, 4, 32) QL(float, 4, 16) c.teardown();
+        c.setup(2, 6); QL(float, 6, 32) QL(float, 6, 16) c.teardown();
+        c.setup(2, 8); QL(float, 8, 32) QL(float, 8, 16) c.teardown();
+        c.setup(2, 14); QL(float, 14, 32) QL(float, 14, 16) c.teardown();
+        c.setup(2, 32); QL(float, 32, 16) QL(float, 32, 32) QL(float, 32, 8) c.teardown();
+    }
+    return 0;
+}
