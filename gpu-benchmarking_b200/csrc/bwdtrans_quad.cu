@@ -209,6 +209,45 @@ static int quad_lanes_switch(unsigned nq, unsigned nelmt, const T *in, T *out, c
     }
 }
 
+// element-major lanes kernel (sumfac_lanes.cuh, "lanes-em"): even nq where it measured faster than the table's choice
+// at 64 Mi points (tools/tune/lanesem_probe.cu, profiles/r01_lanesem_probe.csv; fraction of the HBM roofline):
+//   FP64  nq   6     8     10    12    14    16          FP32  nq   12    14    16
+//   EL        16    32     16    16     4     4                EL   16     8     8
+//   lanes-em 0.94  1.00   0.99  0.99  0.98  0.97                    0.92  0.89  0.93
+//   before   0.89  0.93   0.91  0.96  0.94  0.92                    0.85  0.66  0.82
+static bool quad_has_lanesem(unsigned nq)
+{
+    return nq % 2 == 0 && nq <= 16 && nq >= (sizeof(T) == 8 ? 6u : 12u);
+}
+static int quad_lanesem_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
+{
+    constexpr bool D = sizeof(T) == 8;
+    switch (nq)
+    {
+    case 6:
+        if constexpr (D)
+            return launch_quad_lanesem<T, 6, 16>(nelmt, in, out, s);
+        break;
+    case 8:
+        if constexpr (D)
+            return launch_quad_lanesem<T, 8, 32>(nelmt, in, out, s);
+        break;
+    case 10:
+        if constexpr (D)
+            return launch_quad_lanesem<T, 10, 16>(nelmt, in, out, s);
+        break;
+    case 12:
+        return launch_quad_lanesem<T, 12, 16>(nelmt, in, out, s);
+    case 14:
+        return launch_quad_lanesem<T, 14, (D ? 4 : 8)>(nelmt, in, out, s);
+    case 16:
+        return launch_quad_lanesem<T, 16, (D ? 4 : 8)>(nelmt, in, out, s);
+    default:
+        break;
+    }
+    return B200FE_EUNSUPPORTED;
+}
+
 // registers hold nm^2 + nm values per thread
 
 static int quad_tpe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
@@ -253,6 +292,8 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
                                        : ((have & 1) ? Backend::Rows : Backend::Generic);
         else if (nq0 == 2 && sizeof(T) == 4)
             be = Backend::Nm1; // measured: 0.81 vs 0.63 (pipe) for FP32; FP64 and hex stay on the table's choice
+        else if (quad_has_lanesem(nq0) && aligned16(in) && !partials)
+            be = Backend::Lanes; // the fused operator + checksum stays with the back-end that can fuse (mma)
         else
             be = preferred;
         // the bulk-copy ring needs a 16-byte aligned slab; otherwise take the plain-load twin
@@ -269,8 +310,10 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
         return launch_quad_generic<T>(nm0, nm1, nq0, nq1, nelmt, b0, b1, in, out, coa, stream);
     }
     if (!regular || ((be == Backend::Pipe || be == Backend::Mma || be == Backend::Nm1) && coa) ||
-        (be == Backend::Tpe && !coa) || (be == Backend::Lanes && !coa) || (be == Backend::Rows && !(have & 1)))
+        (be == Backend::Tpe && !coa) || (be == Backend::Rows && !(have & 1)))
         return B200FE_EUNSUPPORTED;
+    if (be == Backend::Lanes && !coa && (!quad_has_lanesem(nq0) || !aligned16(in)))
+        return B200FE_EUNSUPPORTED; // the bulk copy of the slab needs a 16-byte aligned `in`
     if (be == Backend::Pipe && (!(have & 2) || !aligned16(in)))
         return B200FE_EUNSUPPORTED;
     if (be == Backend::Nm1)
@@ -288,7 +331,7 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
     else if (be == Backend::Pipe)
         rc = quad_pipe_switch(nq0, nelmt, in, out, stream);
     else if (be == Backend::Lanes)
-        rc = quad_lanes_switch(nq0, nelmt, in, out, stream);
+        rc = coa ? quad_lanes_switch(nq0, nelmt, in, out, stream) : quad_lanesem_switch(nq0, nelmt, in, out, stream);
     else
         rc = quad_tpe_switch(nq0, nelmt, in, out, stream);
     if (rc)

@@ -15,7 +15,8 @@ enum class Backend : int
     Generic = 3, // run-time sizes, any shape
     Pipe    = 4, // rows + persistent CTAs fed by bulk (TMA) copies through an mbarrier ring
     Nm1     = 6, // nq = 2: scaled broadcast, one thread per 16-byte output chunk, no basis staging
-    Lanes   = 7, // interleaved layout: lanes = elements, an element's planes / rows split over the warps of a CTA
+    Lanes   = 7, // lanes = elements, an element's planes / rows split over the warps of a CTA (interleaved layout;
+                 // element-major even-nq quads through a bulk-copied slab: "lanes-em")
     Mma     = 5, // FP64 tensor cores (DMMA m8n8k4), one element group per warp, bulk (TMA) fed (quad, even nq)
 };
 

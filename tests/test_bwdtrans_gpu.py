@@ -48,7 +48,7 @@ def test_quad_every_nq_bit_exact(G, suf, nq):
         inp = rnd(rng, nelmt * nm * nm, dt)
         want = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp, use_fma=True)
         got = G.run_quad("BwdTransQuadKernel_QP_Shared", suf, nq, nq, nelmt, b0, b1, inp)
-        assert G.fe.last_backend() in ("rows", "pipe", "mma", "nm1")
+        assert G.fe.last_backend() in ("rows", "pipe", "mma", "nm1", "lanes-em")
         G.assert_parity(got, want, suf, (nq, nelmt))
         plain = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp, use_fma=False)
         assert G.rel_max(got, plain) < G.TOL[suf]
@@ -487,9 +487,13 @@ def test_fused_operator_and_checksum(G, suf, dim, nq, nelmt):
         plain = G.run_quad("BwdTransQuadKernel_QP_Shared", suf, nq, nq, nelmt, b[0], b[1], inp)
     else:
         plain = G.run_hex("BwdTransHexKernel_QP_Shared", suf, (nq,) * 3, nelmt, b, inp)
-    assert G.fe.last_backend() == backend
-    assert np.array_equal(results[0][0], plain)                 # the fused kernel stores exactly what the plain one does
-    want = oracle.sumsq(plain)
+    # the plain call may take another back-end (lanes-em cannot fuse); every back-end but the FP32 tensor-core one
+    # is bit-identical, so the fused kernel must store exactly what the plain one does
+    if suf == "f32" and "mma" in (backend, G.fe.last_backend()) and backend != G.fe.last_backend():
+        assert G.rel_max(results[0][0], plain) < G.TOL["f32"]
+    else:
+        assert np.array_equal(results[0][0], plain)
+    want = oracle.sumsq(results[0][0])                          # the checksum of what the fused kernel itself stored
     assert abs(results[0][1] - want) / want < 1e-12, (backend, results[0][1], want)
     assert results[0][1] == results[1][1]                       # deterministic
     assert np.array_equal(results[0][0], results[1][0])

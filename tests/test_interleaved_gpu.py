@@ -1,4 +1,5 @@
-"""The warp-interleaved ("Coales") entry points, back-end by back-end, through the C ABI.
+"""The warp-interleaved ("Coales") entry points, back-end by back-end, through the C ABI -- and the element-major
+twin of the lanes kernel ("lanes-em").
 
 Layout (reference benchmark04.cc:78-147, benchmark05.cc:104-201): x[(e/32)*32*len + 32*idx + e%32].
 Three back-ends serve it -- thread per element (tpe, small nq), lanes (lanes = elements, an element's planes /
@@ -115,16 +116,85 @@ def test_hex_other_interleaved_backends_stay_bit_exact(G, suf, backend, nqs):
         assert np.array_equal(oracle.from_coa(got, nelmt, nq ** 3), want_em), (backend, nq)
 
 
-def test_lanes_backend_is_interleaved_only(G):
-    b0, b1, inp, _ = quad_case(G, "f64", 8, 32, 1)
+def test_lanes_backend_where_it_has_no_instantiation(G):
+    try:
+        G.fe.set_backend("lanes")
+        with pytest.raises(Exception):  # interleaved: nq = 4 .. 16 and 32 only
+            G.run_quad("BwdTransQuadKernel_Coa", "f64", 20, 20, 32, *quad_case(G, "f64", 20, 32, 2)[:3])
+        b0, b1, inp, _ = quad_case(G, "f32", 8, 32, 1)
+        with pytest.raises(Exception):  # element-major FP32: nq = 12, 14, 16 only
+            G.run_quad("BwdTransQuadKernel", "f32", 8, 8, 32, b0, b1, oracle.from_coa(inp, 32, 49))
+        b, inph, _ = hex_case(G, "f64", 6, 32, 3)
+        with pytest.raises(Exception):  # no element-major hex variant
+            G.run_hex("BwdTransHexKernel", "f64", (6, 6, 6), 32, b, inph)
+    finally:
+        G.fe.set_backend("auto")
+
+
+LANES_EM = [("f64", nq) for nq in (6, 8, 10, 12, 14, 16)] + [("f32", nq) for nq in (12, 14, 16)]
+
+
+@pytest.mark.parametrize("suf,nq", LANES_EM)
+@pytest.mark.parametrize("nelmt", [1, 37, 160, 20011])
+def test_quad_element_major_lanes_kernel_bit_exact(G, suf, nq, nelmt):
+    """"lanes-em": the element-major even-nq quads that route to the bulk-copied-slab kernel; whole and ragged
+    tiles (the ragged tail of the slab is fetched with plain loads), forced and through the default routing"""
+    dt, nm = G.NP[suf], nq - 1
+    rng = np.random.default_rng(3400 + nq + nelmt)
+    b0, b1 = rnd(rng, nm * nq, dt), rnd(rng, nm * nq, dt)
+    inp = rnd(rng, nelmt * nm * nm, dt)
+    want = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp)
+    try:
+        G.fe.set_backend("lanes")
+        got = G.run_quad("BwdTransQuadKernel_QP_Shared", suf, nq, nq, nelmt, b0, b1, inp)
+        assert G.fe.last_backend() == "lanes-em"
+    finally:
+        G.fe.set_backend("auto")
+    assert np.array_equal(got, want)
+    got = G.run_quad("BwdTransQuadKernel", suf, nq, nq, nelmt, b0, b1, inp)
+    assert G.fe.last_backend() == "lanes-em"
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("suf,nq", [("f64", 8), ("f32", 14)])
+def test_quad_element_major_lanes_kernel_needs_an_aligned_slab(G, suf, nq):
+    """the slab is fetched with a bulk copy (16-byte aligned source): a misaligned `in` takes the table's back-end
+    under the default routing and is refused when lanes is forced; either way nothing is written outside `out`"""
+    import torch
+    dt, nm, nelmt = G.NP[suf], nq - 1, 333
+    tdt = torch.float64 if suf == "f64" else torch.float32
+    rng = np.random.default_rng(3500 + nq)
+    b0, b1 = rnd(rng, nm * nq, dt), rnd(rng, nm * nq, dt)
+    inp = rnd(rng, nelmt * nm * nm, dt)
+    want = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp)
+    big_in = torch.zeros(nelmt * nm * nm + 4, dtype=tdt, device="cuda")
+    big_in[1:1 + inp.size] = G.dev(inp)
+    d_b0, d_b1 = G.dev(b0), G.dev(b1)
+    d_out = torch.full((nelmt * nq * nq + 2,), float("nan"), dtype=tdt, device="cuda")
+    isz = inp.itemsize
+    st = torch.cuda.current_stream().cuda_stream
+    G.fe.bwdtrans_quad("BwdTransQuadKernel_QP_Shared", suf, nq, nq, nelmt, d_b0.data_ptr(), d_b1.data_ptr(),
+                       big_in.data_ptr() + isz, d_out.data_ptr() + isz, stream=st)
+    assert G.fe.last_backend() != "lanes-em"
+    got = G.host(d_out)
+    G.assert_parity(got[1:-1], want, suf)
+    assert np.isnan(got[0]) and np.isnan(got[-1])
     try:
         G.fe.set_backend("lanes")
         with pytest.raises(Exception):
-            G.run_quad("BwdTransQuadKernel", "f64", 8, 8, 32, b0, b1, inp)
-        with pytest.raises(Exception):  # no lanes instantiation at this nq
-            G.run_quad("BwdTransQuadKernel_Coa", "f64", 20, 20, 32, *quad_case(G, "f64", 20, 32, 2)[:3])
+            G.fe.bwdtrans_quad("BwdTransQuadKernel_QP_Shared", suf, nq, nq, nelmt, d_b0.data_ptr(), d_b1.data_ptr(),
+                               big_in.data_ptr() + isz, d_out.data_ptr() + isz, stream=st)
     finally:
         G.fe.set_backend("auto")
+    # aligned `in`, misaligned `out` (scalar stores: any alignment)
+    d_in = G.dev(inp)
+    d_out.fill_(float("nan"))
+    G.fe.bwdtrans_quad("BwdTransQuadKernel_QP_Shared", suf, nq, nq, nelmt, d_b0.data_ptr(), d_b1.data_ptr(),
+                       d_in.data_ptr(), d_out.data_ptr() + isz, stream=st)
+    assert G.fe.last_backend() == "lanes-em"
+    got = G.host(d_out)
+    assert np.array_equal(got[1:-1], want)
+    assert np.isnan(got[0]) and np.isnan(got[-1])
 
 
 @pytest.mark.parametrize("suf", ["f64", "f32"])

@@ -1,0 +1,171 @@
+// lanesem_probe.cu -- on-device comparison of the tile shapes of the element-major "lanes-em" quad kernel
+// (csrc/sumfac_lanes.cuh) at ~64 Mi quadrature points, checked bit for bit against the generic kernel.
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../gpu-benchmarking_b200/csrc/sumfac_generic.cuh"
+#include "../../gpu-benchmarking_b200/csrc/sumfac_lanes.cuh"
+
+using namespace b200fe;
+namespace b200fe
+{
+std::atomic<unsigned long long> g_launch_count{0};
+thread_local const char *t_last_backend = "";
+}
+
+#define CK(x)                                                                                                \
+    do                                                                                                       \
+    {                                                                                                        \
+        cudaError_t e_ = (x);                                                                                \
+        if (e_ != cudaSuccess)                                                                               \
+        {                                                                                                    \
+            printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__);                  \
+            exit(1);                                                                                         \
+        }                                                                                                    \
+    } while (0)
+
+template <typename T> __global__ void fill_kernel(T *x, size_t n, unsigned seed)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        unsigned h = (unsigned)i * 2654435761u + seed;
+        h ^= h >> 15;
+        h *= 2246822519u;
+        h ^= h >> 13;
+        x[i] = (T)((double)(h & 0xffffff) / 16777216.0 - 0.5);
+    }
+}
+template <typename T> __global__ void diff_kernel(const T *a, const T *b, size_t n, unsigned long long *bad)
+{
+    unsigned long long c = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        if (sizeof(T) == 8)
+            c += (reinterpret_cast<const unsigned long long *>(a)[i] != reinterpret_cast<const unsigned long long *>(b)[i]);
+        else
+            c += (reinterpret_cast<const unsigned *>(a)[i] != reinterpret_cast<const unsigned *>(b)[i]);
+    }
+    if (c)
+        atomicAdd(bad, c);
+}
+
+template <typename T> struct Case
+{
+    int nq;
+    unsigned nelmt;
+    T *b[2], *in, *out, *ref;
+    size_t nin, nout;
+    unsigned long long *bad;
+    BankGuard bank;
+
+    void setup(int nq_)
+    {
+        nq = nq_;
+        const int nm = nq - 1;
+        nelmt = (unsigned)((64ull << 20) / (nq * nq)) - 3; // ragged last tile
+        nin   = (size_t)nm * nm * nelmt;
+        nout  = (size_t)nq * nq * nelmt;
+        for (int d = 0; d < 2; ++d)
+        {
+            CK(cudaMalloc(&b[d], sizeof(T) * nm * nq));
+            fill_kernel<T><<<1, 256>>>(b[d], (size_t)nm * nq, 17u + d);
+        }
+        CK(cudaMalloc(&in, sizeof(T) * nin));
+        CK(cudaMalloc(&out, sizeof(T) * nout));
+        CK(cudaMalloc(&ref, sizeof(T) * nout));
+        CK(cudaMalloc(&bad, 8));
+        fill_kernel<T><<<1024, 256>>>(in, nin, 99u);
+        const unsigned n = nm, q = nq;
+        const size_t smem = sizeof(T) * (2 * n * q + n * n + q * n);
+        bwdtrans_quad_generic_kernel<T><<<148 * 8, 128, smem>>>(n, n, q, q, nelmt, b[0], b[1], in, ref, 0);
+        CK(cudaDeviceSynchronize());
+        const T *bs[2] = {b[0], b[1]};
+        if (fill_basis_bank<T>(bank, 2, bs, nm, nq, false, 0))
+        {
+            printf("bank fill failed\n");
+            exit(1);
+        }
+        CK(cudaDeviceSynchronize());
+    }
+    void teardown()
+    {
+        cudaFree(b[0]);
+        cudaFree(b[1]);
+        cudaFree(in);
+        cudaFree(out);
+        cudaFree(ref);
+        cudaFree(bad);
+    }
+    template <typename K> void run(const char *name, K kernel, unsigned grid, int threads, size_t smem)
+    {
+        if (smem > 227 * 1024)
+        {
+            printf("# skipped %s (smem %zu)\n", name, smem);
+            return;
+        }
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+        CK(cudaMemset(out, 0xff, sizeof(T) * nout));
+        CK(cudaMemset(bad, 0, 8));
+        kernel<<<grid, threads, smem>>>(in, out, nelmt);
+        CK(cudaGetLastError());
+        diff_kernel<T><<<1024, 256>>>(out, ref, nout, bad);
+        unsigned long long nbad = 0;
+        CK(cudaMemcpy(&nbad, bad, 8, cudaMemcpyDeviceToHost));
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        float best = 1e30f, sum = 0;
+        const int reps = 12;
+        for (int r = 0; r < reps; ++r)
+        {
+            cudaEventRecord(e0);
+            kernel<<<grid, threads, smem>>>(in, out, nelmt);
+            cudaEventRecord(e1);
+            CK(cudaEventSynchronize(e1));
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            best = ms < best ? ms : best;
+            if (r >= 2)
+                sum += ms;
+        }
+        const double bytes = (double)sizeof(T) * (nin + nout);
+        printf("quad,%d,%s,%s,%d,%zu,%d,%.4f,%.4f,%.1f,%.3f,%llu\n", nq, sizeof(T) == 8 ? "f64" : "f32", name, threads, smem,
+               occ, best, sum / (reps - 2), bytes / (sum / (reps - 2)) * 1e-6, bytes / (sum / (reps - 2)) * 1e-6 / 6546.9, nbad);
+        fflush(stdout);
+    }
+};
+
+#define QE(T, NQ, EL, MB)                                                                                    \
+    c.run("EL=" #EL "/MINB=" #MB, bwdtrans_quad_lanesem_kernel<T, NQ, EL, MB>, (c.nelmt + EL - 1) / EL,       \
+          QuadLanesEm<T, NQ, EL>::THREADS, QuadLanesEm<T, NQ, EL>::SMEM);
+
+int main()
+{
+    printf("op,nq,dtype,shape,threads,smem,ctas_per_sm,ms_best,ms_avg,gb_s,hbm_frac,mismatches\n");
+    {
+        Case<float> c;
+        c.setup(4); QE(float, 4, 16, 1) QE(float, 4, 8, 1) c.teardown();
+        c.setup(6); QE(float, 6, 16, 1) QE(float, 6, 8, 1) c.teardown();
+        c.setup(8); QE(float, 8, 16, 1) QE(float, 8, 8, 1) c.teardown();
+        c.setup(10); QE(float, 10, 16, 1) QE(float, 10, 8, 1) c.teardown();
+        c.setup(12); QE(float, 12, 16, 1) QE(float, 12, 8, 1) c.teardown();
+        c.setup(14); QE(float, 14, 8, 1) QE(float, 14, 16, 2) c.teardown();
+        c.setup(16); QE(float, 16, 8, 1) QE(float, 16, 4, 1) c.teardown();
+        c.setup(32); QE(float, 32, 8, 1) QE(float, 32, 4, 1) c.teardown();
+    }
+    {
+        Case<double> c;
+        c.setup(4); QE(double, 4, 16, 1) QE(double, 4, 8, 1) c.teardown();
+        c.setup(6); QE(double, 6, 16, 1) QE(double, 6, 8, 1) c.teardown();
+        c.setup(8); QE(double, 8, 16, 1) QE(double, 8, 8, 1) c.teardown();
+        c.setup(10); QE(double, 10, 8, 1) c.teardown();
+        c.setup(12); QE(double, 12, 8, 1) c.teardown();
+        c.setup(14); QE(double, 14, 8, 1) QE(double, 14, 4, 1) c.teardown();
+        c.setup(16); QE(double, 16, 8, 1) QE(double, 16, 4, 1) c.teardown();
+        c.setup(32); QE(double, 32, 4, 1) c.teardown();
+    }
+    return 0;
+}
