@@ -200,6 +200,36 @@ static int hex_lanes_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cu
     }
 }
 
+// element-major lanes kernel (sumfac_lanes.cuh, "lanes-em"): even nq where it measured faster than the table's choice
+// at 64 Mi points (tools/tune/lanesem_probe.cu, profiles/r01_lanesem_probe.csv; fraction of the HBM roofline):
+//   FP64  nq   4     6          FP32  nq   4     6     8
+//   EL        16    16                EL  64    16    16
+//   lanes-em 0.97  0.98                   0.91  0.91  0.90
+//   before   0.94  0.93                   0.82  0.84  0.84
+// (FP64 nq = 8: 0.79 against 0.92 for the tensor-core kernel; nq = 10 does not fit the register file: 0.38-0.48)
+static bool hex_has_lanesem(unsigned nq)
+{
+    return nq == 4 || nq == 6 || (nq == 8 && sizeof(T) == 4);
+}
+static int hex_lanesem_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
+{
+    constexpr bool D = sizeof(T) == 8;
+    switch (nq)
+    {
+    case 4:
+        return launch_hex_lanesem<T, 4, (D ? 16 : 64)>(nelmt, in, out, s);
+    case 6:
+        return launch_hex_lanesem<T, 6, 16>(nelmt, in, out, s);
+    case 8:
+        if constexpr (!D)
+            return launch_hex_lanesem<T, 8, 16>(nelmt, in, out, s);
+        break;
+    default:
+        break;
+    }
+    return B200FE_EUNSUPPORTED;
+}
+
 // registers hold nm^3 + nm^2 + nm values per thread
 
 static int hex_tpe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
@@ -237,6 +267,8 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
             be = (nq0 < kHexLanesMinNq || (nq0 == 5 && sizeof(T) == 8)) ? Backend::Tpe // FP64 nq = 5: 0.94 against 0.88
                  : nq0 <= kHexLanesMaxNq ? Backend::Lanes
                                          : ((have & 1) ? Backend::Rows : Backend::Generic);
+        else if (hex_has_lanesem(nq0) && aligned16(in) && !partials)
+            be = Backend::Lanes;
         else
             be = preferred;
         // the bulk-copy ring needs a 16-byte aligned slab; otherwise take the plain-load twin
@@ -253,8 +285,10 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
         return launch_hex_generic<T>(nm0, nm1, nm2, nq0, nq1, nq2, nelmt, b0, b1, b2, in, out, coa, stream);
     }
     if (!regular || ((be == Backend::Pipe || be == Backend::Mma || be == Backend::Nm1) && coa) ||
-        (be == Backend::Tpe && !coa) || (be == Backend::Lanes && !coa) || (be == Backend::Rows && !(have & 1)))
+        (be == Backend::Tpe && !coa) || (be == Backend::Rows && !(have & 1)))
         return B200FE_EUNSUPPORTED;
+    if (be == Backend::Lanes && !coa && (!hex_has_lanesem(nq0) || !aligned16(in)))
+        return B200FE_EUNSUPPORTED; // the bulk copy of the slab needs a 16-byte aligned `in`
     if (be == Backend::Pipe && (!(have & 2) || !aligned16(in)))
         return B200FE_EUNSUPPORTED;
     if (be == Backend::Nm1)
@@ -272,7 +306,7 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
     else if (be == Backend::Pipe)
         rc = hex_pipe_switch(nq0, nelmt, in, out, stream);
     else if (be == Backend::Lanes)
-        rc = hex_lanes_switch(nq0, nelmt, in, out, stream);
+        rc = coa ? hex_lanes_switch(nq0, nelmt, in, out, stream) : hex_lanesem_switch(nq0, nelmt, in, out, stream);
     else
         rc = hex_tpe_switch(nq0, nelmt, in, out, stream);
     if (rc)

@@ -310,6 +310,21 @@ template <typename T, int NQ, int EL> int launch_quad_lanesem(unsigned nelmt, co
     return launch_status();
 }
 
+template <typename T, int NQ, int EL> int launch_hex_lanesem(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
+{
+    using C = HexLanesEm<T, NQ, EL>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
+    auto kernel = bwdtrans_hex_lanesem_kernel<T, NQ, EL, 1>;
+    int rc      = opt_in_smem(kernel, C::SMEM);
+    if (rc)
+        return rc;
+    const unsigned grid = (nelmt + EL - 1) / EL;
+    B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt));
+    count_launch();
+    t_last_backend = "lanes-em";
+    return launch_status();
+}
+
 // ---- IProductWRTBase: the BwdTrans tile shape of the same nq, elements per CTA cut so the padded tiles fit ----
 template <typename Shape> constexpr bool iprod_fits()
 {

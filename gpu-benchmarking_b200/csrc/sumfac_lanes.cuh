@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(QuadLanes<T, NQ, EL>::THREADS)
 // directions 0 and 1 of one plane for the IBW outputs i in [ib, ib + IBW): t1[q][i] for every q in registers
 // (the basis values of a (p, i-block) are shared by the nm rows q), then column i of t1 against B1 -> t2[j][i]
 template <typename T, int NQ, int EL, int IBW>
-__device__ __forceinline__ void hex_lanes_block(const T (&a)[(NQ - 1) * (NQ - 1)], T *dst, int ib)
+__device__ __forceinline__ void hex_lanes_block(const T (&a)[(NQ - 1) * (NQ - 1)], T *dst, int ib) // t2[(j, i)] at dst[(j*NQ + i)*EL]
 {
     constexpr int NM = NQ - 1, BP = bank_pitch<T>(NQ), B0 = 0, B1 = NM * BP;
     RowAcc<T, IBW> t1[NM];
@@ -427,6 +427,100 @@ __global__ void __launch_bounds__(QuadLanesEm<T, NQ, EL>::THREADS, MINB)
         {
             T *dst = out + (e0 + e) * NQ2 + i;
             lanes_row<T, NM, NQ, B1>(x, [&](int j, T v) { st_stream(dst + j * NQ, v); });
+        }
+    }
+}
+
+// ---- element-major hexes in the same style ("lanes-em") -------------------------------------------------------
+// As for the quads: the CTA's slab of EL elements arrives with one bulk copy and is read with lanes = elements
+// (stride nm^3, odd for even nq: conflict-free).  Worker r takes its plane into registers; after a barrier the slab's
+// shared memory is reused for t2[e][r][(j, i)] (element stride padded to an odd count, so the lanes = elements stores
+// of phase A and the lanes = (j, i) loads of phase B are both conflict-free).  Phase B flattens (e, (j, i)) over the
+// threads, (j, i) fastest: for every k a warp stores 32 consecutive values of out[e][k][.][.].
+template <typename T, int NQ, int EL> struct HexLanesEm
+{
+    static_assert(NQ % 2 == 0, "nm^3 must be odd for conflict-free lane access to the unpadded slab");
+    static constexpr int NM = NQ - 1, NM2 = NM * NM, NM3 = NM2 * NM, NQ2 = NQ * NQ, NQ3 = NQ2 * NQ;
+    static constexpr int THREADS = (EL * NM + 31) / 32 * 32;
+    static constexpr int ES      = NM * NQ2 + 1; // element stride of t2: nm * nq^2 is even
+    static constexpr int SIN     = (EL * NM3 * (int)sizeof(T) + 15) / 16 * 16 / (int)sizeof(T);
+    static constexpr int SBUF    = SIN > EL * ES ? SIN : EL * ES;
+    static constexpr size_t SMEM = (size_t)SBUF * sizeof(T) + 16;
+    static constexpr int IB0     = sizeof(T) == 4 ? 2 : 1;
+    static constexpr bool ROLLED = sizeof(T) == 8; // see HexLanes
+};
+
+template <typename T, int NQ, int EL, int MINB = 1>
+__global__ void __launch_bounds__(HexLanesEm<T, NQ, EL>::THREADS, MINB)
+    bwdtrans_hex_lanesem_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
+{
+    using C = HexLanesEm<T, NQ, EL>;
+    constexpr int NM = C::NM, NM2 = C::NM2, NM3 = C::NM3, NQ2 = C::NQ2, ES = C::ES, IB0 = C::IB0;
+    constexpr int BP = bank_pitch<T>(NQ), B2 = 2 * NM * BP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *s_in       = reinterpret_cast<T *>(smem_raw);
+    T *s2         = s_in; // reused once every worker holds its plane
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)C::SBUF * sizeof(T));
+
+    const int tid   = threadIdx.x;
+    const size_t e0 = (size_t)blockIdx.x * EL;
+    const int ne    = (nelmt - e0 < (size_t)EL) ? (int)(nelmt - e0) : EL;
+    if (tid == 0)
+    {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0)
+        ring_issue<T, EL, NM3>(s_in, bar, in, blockIdx.x, nelmt);
+    ring_wait<T, NM3>(s_in, bar, 0u, in + e0 * NM3, ne, tid);
+
+    const int e = tid % EL, r = tid / EL;
+    T a[NM2];
+    if (r < NM)
+    {
+        const T *src = s_in + e * NM3 + r * NM2;
+#pragma unroll
+        for (int k = 0; k < NM2; ++k)
+            a[k] = src[k];
+    }
+    __syncthreads();
+    grid_dependency_wait();
+    if (r < NM)
+    {
+        T *dst = s2 + e * ES + r * NQ2;
+        if constexpr (C::ROLLED)
+        {
+#pragma unroll 1
+            for (int ib = 0; ib + IB0 <= NQ; ib += IB0)
+                hex_lanes_block<T, NQ, 1, IB0>(a, dst, ib);
+        }
+        else
+        {
+#pragma unroll
+            for (int ib = 0; ib + IB0 <= NQ; ib += IB0)
+                hex_lanes_block<T, NQ, 1, IB0>(a, dst, ib);
+        }
+    }
+    __syncthreads();
+
+    constexpr int ROWS = EL * NQ2, ITER = (ROWS + C::THREADS - 1) / C::THREADS;
+#pragma unroll 1
+    for (int it = 0; it < ITER; ++it)
+    {
+        const int row = it * C::THREADS + tid;
+        if (row >= ROWS)
+            break;
+        const int e2 = row / NQ2, ji = row - e2 * NQ2;
+        T x[NM];
+        const T *src = s2 + e2 * ES + ji;
+#pragma unroll
+        for (int rr = 0; rr < NM; ++rr)
+            x[rr] = src[rr * NQ2];
+        if (e2 < ne)
+        {
+            T *dst = out + (e0 + e2) * C::NQ3 + ji;
+            lanes_row<T, NM, NQ, B2>(x, [&](int k, T v) { st_stream(dst + k * NQ2, v); });
         }
     }
 }

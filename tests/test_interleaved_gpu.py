@@ -124,9 +124,9 @@ def test_lanes_backend_where_it_has_no_instantiation(G):
         b0, b1, inp, _ = quad_case(G, "f32", 8, 32, 1)
         with pytest.raises(Exception):  # element-major FP32: nq = 12, 14, 16 only
             G.run_quad("BwdTransQuadKernel", "f32", 8, 8, 32, b0, b1, oracle.from_coa(inp, 32, 49))
-        b, inph, _ = hex_case(G, "f64", 6, 32, 3)
-        with pytest.raises(Exception):  # no element-major hex variant
-            G.run_hex("BwdTransHexKernel", "f64", (6, 6, 6), 32, b, inph)
+        b, inph, _ = hex_case(G, "f64", 8, 32, 3)
+        with pytest.raises(Exception):  # element-major hexes: nq = 4, 6 (and 8 in FP32) only
+            G.run_hex("BwdTransHexKernel", "f64", (8, 8, 8), 32, b, inph)
     finally:
         G.fe.set_backend("auto")
 
@@ -152,6 +152,29 @@ def test_quad_element_major_lanes_kernel_bit_exact(G, suf, nq, nelmt):
         G.fe.set_backend("auto")
     assert np.array_equal(got, want)
     got = G.run_quad("BwdTransQuadKernel", suf, nq, nq, nelmt, b0, b1, inp)
+    assert G.fe.last_backend() == "lanes-em"
+    assert np.array_equal(got, want)
+
+
+HEX_LANES_EM = [("f64", 4), ("f64", 6), ("f32", 4), ("f32", 6), ("f32", 8)]
+
+
+@pytest.mark.parametrize("suf,nq", HEX_LANES_EM)
+@pytest.mark.parametrize("nelmt", [1, 37, 160, 5003])
+def test_hex_element_major_lanes_kernel_bit_exact(G, suf, nq, nelmt):
+    dt, nm = G.NP[suf], nq - 1
+    rng = np.random.default_rng(3600 + nq + nelmt)
+    b = [rnd(rng, nm * nq, dt) for _ in range(3)]
+    inp = rnd(rng, nelmt * nm ** 3, dt)
+    want = oracle.bwdtrans_hex(nq, nq, nq, nelmt, *b, inp)
+    try:
+        G.fe.set_backend("lanes")
+        got = G.run_hex("BwdTransHexKernel_QP_Shared", suf, (nq, nq, nq), nelmt, b, inp)
+        assert G.fe.last_backend() == "lanes-em"
+    finally:
+        G.fe.set_backend("auto")
+    assert np.array_equal(got, want)
+    got = G.run_hex("BwdTransHexKernel", suf, (nq, nq, nq), nelmt, b, inp)
     assert G.fe.last_backend() == "lanes-em"
     assert np.array_equal(got, want)
 

@@ -51,21 +51,26 @@ template <typename T> __global__ void diff_kernel(const T *a, const T *b, size_t
 
 template <typename T> struct Case
 {
+    int dim = 2;
     int nq;
     unsigned nelmt;
-    T *b[2], *in, *out, *ref;
+    T *b[3], *in, *out, *ref;
     size_t nin, nout;
     unsigned long long *bad;
     BankGuard bank;
 
-    void setup(int nq_)
+    void setup(int nq_, int dim_ = 2)
     {
-        nq = nq_;
+        nq  = nq_;
+        dim = dim_;
         const int nm = nq - 1;
-        nelmt = (unsigned)((64ull << 20) / (nq * nq)) - 3; // ragged last tile
-        nin   = (size_t)nm * nm * nelmt;
-        nout  = (size_t)nq * nq * nelmt;
-        for (int d = 0; d < 2; ++d)
+        size_t pts = 1, modes = 1;
+        for (int d = 0; d < dim; ++d)
+            pts *= nq, modes *= nm;
+        nelmt = (unsigned)((64ull << 20) / pts) - 3; // ragged last tile
+        nin   = modes * nelmt;
+        nout  = pts * nelmt;
+        for (int d = 0; d < 3; ++d)
         {
             CK(cudaMalloc(&b[d], sizeof(T) * nm * nq));
             fill_kernel<T><<<1, 256>>>(b[d], (size_t)nm * nq, 17u + d);
@@ -76,11 +81,20 @@ template <typename T> struct Case
         CK(cudaMalloc(&bad, 8));
         fill_kernel<T><<<1024, 256>>>(in, nin, 99u);
         const unsigned n = nm, q = nq;
-        const size_t smem = sizeof(T) * (2 * n * q + n * n + q * n);
-        bwdtrans_quad_generic_kernel<T><<<148 * 8, 128, smem>>>(n, n, q, q, nelmt, b[0], b[1], in, ref, 0);
+        if (dim == 2)
+        {
+            const size_t smem = sizeof(T) * (2 * n * q + n * n + q * n);
+            bwdtrans_quad_generic_kernel<T><<<148 * 8, 128, smem>>>(n, n, q, q, nelmt, b[0], b[1], in, ref, 0);
+        }
+        else
+        {
+            const size_t smem = sizeof(T) * (3 * n * q + n * n * n + q * n * n + q * q * n);
+            CK(cudaFuncSetAttribute(bwdtrans_hex_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            bwdtrans_hex_generic_kernel<T><<<148 * 4, 256, smem>>>(n, n, n, q, q, q, nelmt, b[0], b[1], b[2], in, ref, 0);
+        }
         CK(cudaDeviceSynchronize());
-        const T *bs[2] = {b[0], b[1]};
-        if (fill_basis_bank<T>(bank, 2, bs, nm, nq, false, 0))
+        const T *bs[3] = {b[0], b[1], b[2]};
+        if (fill_basis_bank<T>(bank, dim, bs, nm, nq, false, 0))
         {
             printf("bank fill failed\n");
             exit(1);
@@ -91,6 +105,7 @@ template <typename T> struct Case
     {
         cudaFree(b[0]);
         cudaFree(b[1]);
+        cudaFree(b[2]);
         cudaFree(in);
         cudaFree(out);
         cudaFree(ref);
@@ -132,7 +147,7 @@ template <typename T> struct Case
                 sum += ms;
         }
         const double bytes = (double)sizeof(T) * (nin + nout);
-        printf("quad,%d,%s,%s,%d,%zu,%d,%.4f,%.4f,%.1f,%.3f,%llu\n", nq, sizeof(T) == 8 ? "f64" : "f32", name, threads, smem,
+        printf("%s,%d,%s,%s,%d,%zu,%d,%.4f,%.4f,%.1f,%.3f,%llu\n", dim == 2 ? "quad" : "hex", nq, sizeof(T) == 8 ? "f64" : "f32", name, threads, smem,
                occ, best, sum / (reps - 2), bytes / (sum / (reps - 2)) * 1e-6, bytes / (sum / (reps - 2)) * 1e-6 / 6546.9, nbad);
         fflush(stdout);
     }
@@ -142,30 +157,26 @@ template <typename T> struct Case
     c.run("EL=" #EL "/MINB=" #MB, bwdtrans_quad_lanesem_kernel<T, NQ, EL, MB>, (c.nelmt + EL - 1) / EL,       \
           QuadLanesEm<T, NQ, EL>::THREADS, QuadLanesEm<T, NQ, EL>::SMEM);
 
+#define HE(T, NQ, EL, MB)                                                                                    \
+    c.run("EL=" #EL "/MINB=" #MB, bwdtrans_hex_lanesem_kernel<T, NQ, EL, MB>, (c.nelmt + EL - 1) / EL,        \
+          HexLanesEm<T, NQ, EL>::THREADS, HexLanesEm<T, NQ, EL>::SMEM);
+
 int main()
 {
     printf("op,nq,dtype,shape,threads,smem,ctas_per_sm,ms_best,ms_avg,gb_s,hbm_frac,mismatches\n");
     {
         Case<float> c;
-        c.setup(4); QE(float, 4, 16, 1) QE(float, 4, 8, 1) c.teardown();
-        c.setup(6); QE(float, 6, 16, 1) QE(float, 6, 8, 1) c.teardown();
-        c.setup(8); QE(float, 8, 16, 1) QE(float, 8, 8, 1) c.teardown();
-        c.setup(10); QE(float, 10, 16, 1) QE(float, 10, 8, 1) c.teardown();
-        c.setup(12); QE(float, 12, 16, 1) QE(float, 12, 8, 1) c.teardown();
-        c.setup(14); QE(float, 14, 8, 1) QE(float, 14, 16, 2) c.teardown();
-        c.setup(16); QE(float, 16, 8, 1) QE(float, 16, 4, 1) c.teardown();
-        c.setup(32); QE(float, 32, 8, 1) QE(float, 32, 4, 1) c.teardown();
+        c.setup(4, 3); HE(float, 4, 32, 1) HE(float, 4, 16, 1) HE(float, 4, 64, 1) c.teardown();
+        c.setup(6, 3); HE(float, 6, 32, 1) HE(float, 6, 16, 1) HE(float, 6, 8, 1) c.teardown();
+        c.setup(8, 3); HE(float, 8, 32, 1) HE(float, 8, 16, 1) HE(float, 8, 8, 1) HE(float, 8, 16, 4) c.teardown();
+        c.setup(10, 3); HE(float, 10, 16, 1) HE(float, 10, 8, 1) HE(float, 10, 32, 1) c.teardown();
     }
     {
         Case<double> c;
-        c.setup(4); QE(double, 4, 16, 1) QE(double, 4, 8, 1) c.teardown();
-        c.setup(6); QE(double, 6, 16, 1) QE(double, 6, 8, 1) c.teardown();
-        c.setup(8); QE(double, 8, 16, 1) QE(double, 8, 8, 1) c.teardown();
-        c.setup(10); QE(double, 10, 8, 1) c.teardown();
-        c.setup(12); QE(double, 12, 8, 1) c.teardown();
-        c.setup(14); QE(double, 14, 8, 1) QE(double, 14, 4, 1) c.teardown();
-        c.setup(16); QE(double, 16, 8, 1) QE(double, 16, 4, 1) c.teardown();
-        c.setup(32); QE(double, 32, 4, 1) c.teardown();
+        c.setup(4, 3); HE(double, 4, 32, 1) HE(double, 4, 16, 1) c.teardown();
+        c.setup(6, 3); HE(double, 6, 32, 1) HE(double, 6, 16, 1) HE(double, 6, 8, 1) c.teardown();
+        c.setup(8, 3); HE(double, 8, 16, 1) HE(double, 8, 8, 1) c.teardown();
+        c.setup(10, 3); HE(double, 10, 8, 1) HE(double, 10, 16, 1) c.teardown();
     }
     return 0;
 }
