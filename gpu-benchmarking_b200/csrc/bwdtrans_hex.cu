@@ -172,9 +172,9 @@ static int hex_table_lookup(unsigned nq, Backend *preferred)
 
 // interleaved layout, lanes back-end (sumfac_lanes.cuh).  Tile shapes (elements per CTA, min CTAs per SM for the register
 // cap) measured with tools/tune/lanes_probe.cu at 64 Mi points (profiles/r01_lanes_probe.csv):
-//   nq            4     5     6     7     8     9    10 (q-outer, 2 slices)
-//   FP64 EL      16    32    32    16    16    16     8
-//   FP32 EL      32    16    16    16    16    16    32
+//   nq            4     5     6     7     8     9    10
+//   FP64 EL      16    32    32    16    16    16     8 (q-outer, 2 slices)
+//   FP32 EL      32    16    16    16    16    32    16 (3 CTAs per SM)
 constexpr unsigned kHexLanesMinNq = 4, kHexLanesMaxNq = 10;
 static int hex_lanes_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
 {
@@ -192,9 +192,12 @@ static int hex_lanes_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cu
     case 8:
         return launch_hex_lanes<T, 8, 16, D ? 1 : 5>(nelmt, in, out, s);
     case 9:
-        return launch_hex_lanes<T, 9, 16, 1>(nelmt, in, out, s);
+        return launch_hex_lanes<T, 9, D ? 16 : 32, 1>(nelmt, in, out, s);
     case 10:
-        return launch_hex_lanesq<T, 10, D ? 8 : 32, 2>(nelmt, in, out, s);
+        if constexpr (D)
+            return launch_hex_lanesq<T, 10, 8, 2>(nelmt, in, out, s);
+        else
+            return launch_hex_lanes<T, 10, 16, 3>(nelmt, in, out, s);
     default:
         return B200FE_EUNSUPPORTED;
     }
@@ -206,10 +209,11 @@ static int hex_lanes_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cu
 //   EL        16    16                EL  64    16    16
 //   lanes-em 0.97  0.98                   0.91  0.91  0.90
 //   before   0.94  0.93                   0.82  0.84  0.84
-// (FP64 nq = 8: 0.79 against 0.92 for the tensor-core kernel; nq = 10 does not fit the register file: 0.38-0.48)
+//   FP32 nq = 10, EL = 16, 3 CTAs per SM: 0.76 against 0.70
+// (FP64 nq = 8: 0.79 against 0.92 for the tensor-core kernel; FP64 nq = 10 does not fit the register file: 0.38)
 static bool hex_has_lanesem(unsigned nq)
 {
-    return nq == 4 || nq == 6 || (nq == 8 && sizeof(T) == 4);
+    return nq == 4 || nq == 6 || ((nq == 8 || nq == 10) && sizeof(T) == 4);
 }
 static int hex_lanesem_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
 {
@@ -223,6 +227,10 @@ static int hex_lanesem_switch(unsigned nq, unsigned nelmt, const T *in, T *out, 
     case 8:
         if constexpr (!D)
             return launch_hex_lanesem<T, 8, 16>(nelmt, in, out, s);
+        break;
+    case 10:
+        if constexpr (!D)
+            return launch_hex_lanesem<T, 10, 16, 3>(nelmt, in, out, s);
         break;
     default:
         break;

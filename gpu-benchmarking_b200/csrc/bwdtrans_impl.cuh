@@ -310,11 +310,12 @@ template <typename T, int NQ, int EL> int launch_quad_lanesem(unsigned nelmt, co
     return launch_status();
 }
 
-template <typename T, int NQ, int EL> int launch_hex_lanesem(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
+template <typename T, int NQ, int EL, int MINB = 1>
+int launch_hex_lanesem(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
 {
     using C = HexLanesEm<T, NQ, EL>;
     static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
-    auto kernel = bwdtrans_hex_lanesem_kernel<T, NQ, EL, 1>;
+    auto kernel = bwdtrans_hex_lanesem_kernel<T, NQ, EL, MINB>;
     int rc      = opt_in_smem(kernel, C::SMEM);
     if (rc)
         return rc;

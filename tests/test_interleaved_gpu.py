@@ -125,7 +125,7 @@ def test_lanes_backend_where_it_has_no_instantiation(G):
         with pytest.raises(Exception):  # element-major FP32: nq = 12, 14, 16 only
             G.run_quad("BwdTransQuadKernel", "f32", 8, 8, 32, b0, b1, oracle.from_coa(inp, 32, 49))
         b, inph, _ = hex_case(G, "f64", 8, 32, 3)
-        with pytest.raises(Exception):  # element-major hexes: nq = 4, 6 (and 8 in FP32) only
+        with pytest.raises(Exception):  # element-major hexes: nq = 4, 6 (and 8, 10 in FP32) only
             G.run_hex("BwdTransHexKernel", "f64", (8, 8, 8), 32, b, inph)
     finally:
         G.fe.set_backend("auto")
@@ -156,7 +156,7 @@ def test_quad_element_major_lanes_kernel_bit_exact(G, suf, nq, nelmt):
     assert np.array_equal(got, want)
 
 
-HEX_LANES_EM = [("f64", 4), ("f64", 6), ("f32", 4), ("f32", 6), ("f32", 8)]
+HEX_LANES_EM = [("f64", 4), ("f64", 6), ("f32", 4), ("f32", 6), ("f32", 8), ("f32", 10)]
 
 
 @pytest.mark.parametrize("suf,nq", HEX_LANES_EM)

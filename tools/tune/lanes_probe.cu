@@ -167,38 +167,9 @@ int main()
 {
     printf("op,nq,dtype,_,threads,smem,ctas_per_sm,ms_best,ms_avg,gb_s,mismatches\n");
     {
-        Case<double> c;
-        c.setup(3, 4); HP(double, 4, 32, 1) HP(double, 4, 16, 1) c.teardown();
-        c.setup(3, 5); HP(double, 5, 32, 1) HP(double, 5, 16, 1) c.teardown();
-        c.setup(3, 7); HP(double, 7, 32, 1) HP(double, 7, 16, 1) H3(double, 7, 16, 16, 1) c.teardown();
-        c.setup(3, 8); H3(double, 8, 16, 16, 1) H3(double, 8, 16, 32, 1) H3(double, 8, 8, 32, 1) c.teardown();
-        c.setup(3, 9); HP(double, 9, 16, 1) H3(double, 9, 8, 32, 1) H3(double, 9, 8, 64, 1) H3(double, 9, 16, 32, 1) c.teardown();
-        c.setup(3, 10); H3(double, 10, 8, 32, 1) H3(double, 10, 8, 64, 1) H3(double, 10, 16, 32, 1) H3(double, 10, 8, 48, 1) c.teardown();
-    }
-    {
         Case<float> c;
-        c.setup(3, 4); HP(float, 4, 32, 1) HP(float, 4, 16, 1) c.teardown();
-        c.setup(3, 5); HP(float, 5, 32, 1) HP(float, 5, 16, 1) c.teardown();
-        c.setup(3, 7); HP(float, 7, 32, 1) HP(float, 7, 16, 1) HP(float, 7, 16, 6) c.teardown();
-        c.setup(3, 8); HP(float, 8, 16, 4) HP(float, 8, 16, 6) H3(float, 8, 16, 32, 1) H3(float, 8, 32, 16, 1) c.teardown();
-        c.setup(3, 9); HP(float, 9, 16, 1) HP(float, 9, 32, 1) H3(float, 9, 16, 32, 1) H3(float, 9, 32, 16, 1) H3(float, 9, 16, 64, 1) c.teardown();
-        c.setup(3, 10); H3(float, 10, 16, 32, 1) H3(float, 10, 32, 16, 1) H3(float, 10, 16, 64, 1) H3(float, 10, 32, 32, 1) H3(float, 10, 8, 64, 1) c.teardown();
-    }
-    {
-        Case<double> c;
-        c.setup(2, 4); QL(double, 4, 32) QL(double, 4, 16) c.teardown();
-        c.setup(2, 6); QL(double, 6, 32) QL(double, 6, 16) c.teardown();
-        c.setup(2, 8); QL(double, 8, 32) QL(double, 8, 16) c.teardown();
-        c.setup(2, 14); QL(double, 14, 32) QL(double, 14, 16) c.teardown();
-        c.setup(2, 32); QL(double, 32, 16) QL(double, 32, 32) QL(double, 32, 8) c.teardown();
-    }
-    {
-        Case<float> c;
-        c.setup(2, 4); QL(float, 4, 32) QL(float, 4, 16) c.teardown();
-        c.setup(2, 6); QL(float, 6, 32) QL(float, 6, 16) c.teardown();
-        c.setup(2, 8); QL(float, 8, 32) QL(float, 8, 16) c.teardown();
-        c.setup(2, 14); QL(float, 14, 32) QL(float, 14, 16) c.teardown();
-        c.setup(2, 32); QL(float, 32, 16) QL(float, 32, 32) QL(float, 32, 8) c.teardown();
+        c.setup(3, 9); HP(float, 9, 16, 1) HP(float, 9, 16, 3) HP(float, 9, 16, 4) HP(float, 9, 32, 1) c.teardown();
+        c.setup(3, 10); HP(float, 10, 16, 1) HP(float, 10, 16, 2) HP(float, 10, 16, 3) HP(float, 10, 32, 1) c.teardown();
     }
     return 0;
 }

@@ -161,22 +161,15 @@ template <typename T> struct Case
     c.run("EL=" #EL "/MINB=" #MB, bwdtrans_hex_lanesem_kernel<T, NQ, EL, MB>, (c.nelmt + EL - 1) / EL,        \
           HexLanesEm<T, NQ, EL>::THREADS, HexLanesEm<T, NQ, EL>::SMEM);
 
+#define HP(T, NQ, EL, MB)                                                                                    \
+    c.run("coa-plane EL=" #EL "/MINB=" #MB, bwdtrans_hex_lanes_kernel<T, NQ, EL, MB>, c.nelmt / EL,            \
+          HexLanes<T, NQ, EL>::THREADS, HexLanes<T, NQ, EL>::SMEM);
 int main()
 {
     printf("op,nq,dtype,shape,threads,smem,ctas_per_sm,ms_best,ms_avg,gb_s,hbm_frac,mismatches\n");
     {
         Case<float> c;
-        c.setup(4, 3); HE(float, 4, 32, 1) HE(float, 4, 16, 1) HE(float, 4, 64, 1) c.teardown();
-        c.setup(6, 3); HE(float, 6, 32, 1) HE(float, 6, 16, 1) HE(float, 6, 8, 1) c.teardown();
-        c.setup(8, 3); HE(float, 8, 32, 1) HE(float, 8, 16, 1) HE(float, 8, 8, 1) HE(float, 8, 16, 4) c.teardown();
-        c.setup(10, 3); HE(float, 10, 16, 1) HE(float, 10, 8, 1) HE(float, 10, 32, 1) c.teardown();
-    }
-    {
-        Case<double> c;
-        c.setup(4, 3); HE(double, 4, 32, 1) HE(double, 4, 16, 1) c.teardown();
-        c.setup(6, 3); HE(double, 6, 32, 1) HE(double, 6, 16, 1) HE(double, 6, 8, 1) c.teardown();
-        c.setup(8, 3); HE(double, 8, 16, 1) HE(double, 8, 8, 1) c.teardown();
-        c.setup(10, 3); HE(double, 10, 8, 1) HE(double, 10, 16, 1) c.teardown();
+        c.setup(10, 3); HE(float, 10, 16, 1) HE(float, 10, 16, 2) HE(float, 10, 16, 3) HE(float, 10, 8, 1) HE(float, 10, 8, 4) HE(float, 10, 32, 1) c.teardown();
     }
     return 0;
 }
