@@ -286,36 +286,45 @@ def sweep_coa(fe, torch, peak, reps=5):
 
 
 def sweep_iproduct(fe, torch, peak, reps=5):
-    """IProductWRTBase, unweighted, at ~64 Mi quadrature points: same algorithmic bytes as BwdTrans"""
-    import numpy as np
+    """IProductWRTBase at ~64 Mi quadrature points, without and with the quadrature metric w (one value
+    per point: its nq^d values per element are algorithmic bytes of the weighted operator)"""
     out = []
     st = torch.cuda.current_stream().cuda_stream
-    for dim, nqs in ((2, (4, 8, 12, 16)), (3, (4, 6, 8, 10))):
+    for dim, nqs in ((2, (4, 6, 8, 10, 12, 14, 16)), (3, (4, 6, 8, 10))):
         for suf, tdt, size in (("f64", torch.float64, 8), ("f32", torch.float32, 4)):
             for nq in nqs:
                 nm = nq - 1
                 nelmt = max(32, ((1 << 26) // nq ** dim) // 32 * 32)
                 b = torch.from_numpy(gen_basis(nm, nq, "float64")).to(tdt).cuda()
                 d_in = torch.randn(nelmt * nq ** dim, dtype=tdt, device="cuda")
+                d_w = torch.rand(nelmt * nq ** dim, dtype=tdt, device="cuda") + 0.5
                 d_out = torch.empty(nelmt * nm ** dim, dtype=tdt, device="cuda")
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * reps)]
+                rec = {"op": "iproduct_" + ("quad" if dim == 2 else "hex"), "nq": nq, "dtype": suf, "nelmt": nelmt}
+                for weighted in (False, True):
+                    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * reps)]
 
-                def call():
-                    fe.iproduct(suf, (nq,) * dim, nelmt, [b.data_ptr()] * dim, d_in.data_ptr(), d_out.data_ptr(),
-                                stream=st)
-                for _ in range(3):
-                    call()
-                for r in range(reps):
-                    ev[2 * r].record()
-                    call()
-                    ev[2 * r + 1].record()
-                torch.cuda.synchronize()
-                ms = min(ev[2 * r].elapsed_time(ev[2 * r + 1]) for r in range(reps))
-                gbs = 1e-9 * nelmt * alg_bytes_per_elem(dim, nq, size) / (ms * 1e-3)
-                out.append({"op": "iproduct_" + ("quad" if dim == 2 else "hex"), "nq": nq, "dtype": suf, "nelmt": nelmt,
-                            "ms": round(ms, 4), "gdof_s": round(1e-9 * nelmt * nm ** dim / (ms * 1e-3), 2),
-                            "gb_s": round(gbs, 1), "hbm_frac": round(gbs / peak, 4)})
-                del d_in, d_out
+                    def call():
+                        fe.iproduct(suf, (nq,) * dim, nelmt, [b.data_ptr()] * dim, d_in.data_ptr(), d_out.data_ptr(),
+                                    weights=d_w.data_ptr() if weighted else 0, stream=st)
+                    for _ in range(3):
+                        call()
+                    for r in range(reps):
+                        ev[2 * r].record()
+                        call()
+                        ev[2 * r + 1].record()
+                    torch.cuda.synchronize()
+                    ms = min(ev[2 * r].elapsed_time(ev[2 * r + 1]) for r in range(reps))
+                    byts = nelmt * (alg_bytes_per_elem(dim, nq, size) + (size * nq ** dim if weighted else 0))
+                    gbs = 1e-9 * byts / (ms * 1e-3)
+                    if not weighted:
+                        rec.update({"backend": fe.last_backend(), "ms": round(ms, 4),
+                                    "gdof_s": round(1e-9 * nelmt * nm ** dim / (ms * 1e-3), 2), "gb_s": round(gbs, 1),
+                                    "hbm_frac": round(gbs / peak, 4)})
+                    else:
+                        rec.update({"weighted": {"backend": fe.last_backend(), "ms": round(ms, 4), "gb_s": round(gbs, 1),
+                                                 "hbm_frac": round(gbs / peak, 4)}})
+                out.append(rec)
+                del d_in, d_out, d_w
     return out
 
 

@@ -361,20 +361,60 @@ static int hex_iprod_mma_switch(unsigned nq, unsigned nelmt, const T *b0, const 
     return B200FE_EUNSUPPORTED;
 }
 
+// lanes-style kernel (sumfac_iprod_lanes.cuh): even nq, 16-byte aligned in / w.  Elements per CTA from
+// tools/ipl_probe.py at 64 Mi points (profiles/r01_ipl_probe.csv); fraction of the roofline unweighted / weighted,
+// row kernel in ():
+//   FP64 nq   4            6                      FP32 nq   4            6            8 (unweighted)  10
+//   EL        32           4                           EL   16           8            4               8
+//             0.66 / 0.68  0.85 / 0.87                      0.87 / 0.97  0.83 / 0.89  0.62            0.65 / 0.56
+//            (0.51 / 0.68)(0.57 / 0.71)                    (0.57 / 0.75)(0.47 / 0.66)(0.53)          (0.31 / 0.42)
+// FP64 nq = 8: 0.68 / 0.70 against 0.67 / 0.93 for the row kernel (a plane of 64 doubles plus the direction-0 block
+// leaves 2-3 CTAs of 64 threads per SM); FP32 nq = 8 weighted: 0.68 against 0.79.
+static bool hex_has_iprod_lanes(unsigned nq, bool weighted)
+{
+    if (sizeof(T) == 8)
+        return nq == 4 || nq == 6;
+    return nq == 4 || nq == 6 || (nq == 8 && !weighted) || nq == 10;
+}
+static int hex_iprod_lanes_switch(unsigned nq, unsigned nelmt, const T *in, const T *w, T *out, cudaStream_t s)
+{
+    constexpr bool D = sizeof(T) == 8;
+    switch (nq)
+    {
+    case 4:
+        return launch_hex_iprod_lanes<T, 4, (D ? 32 : 16)>(nelmt, in, w, out, s);
+    case 6:
+        return launch_hex_iprod_lanes<T, 6, (D ? 4 : 8)>(nelmt, in, w, out, s);
+    case 8:
+        return launch_hex_iprod_lanes<T, 8, 4>(nelmt, in, w, out, s);
+    case 10:
+        if constexpr (!D)
+            return launch_hex_iprod_lanes<T, 10, 8>(nelmt, in, w, out, s);
+        return B200FE_EUNSUPPORTED;
+    default:
+        return B200FE_EUNSUPPORTED;
+    }
+}
+
 template <>
 int run_iproduct_hex<T>(Backend be, unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *b2, const T *w,
                         const T *in, T *out, cudaStream_t stream)
 {
     if (be == Backend::Mma) // the tensor-core variant exists (nq = 8) but does not beat the row kernel yet: forced only
         return hex_iprod_mma_switch(nq, nelmt, b0, b1, b2, in, w, out, stream);
-    if (be != Backend::Auto && be != Backend::Rows)
+    const bool aligned = aligned16(in) && (!w || aligned16(w)); // planes are fetched with 16-byte loads
+    const bool has_any = hex_has_iprod_lanes(nq, false) || (nq == 8 && sizeof(T) == 8);
+    if (be == Backend::Lanes && !(has_any && aligned))
+        return B200FE_EUNSUPPORTED;
+    const bool lanes = be == Backend::Lanes || (be == Backend::Auto && hex_has_iprod_lanes(nq, w != nullptr) && aligned);
+    if (!lanes && be != Backend::Auto && be != Backend::Rows)
         return B200FE_EUNSUPPORTED;
     std::lock_guard<std::mutex> lock(g_bank_lock);
     const T *bases[3]   = {b0, b1, b2};
     int rc = fill_basis_bank<T>(g_bank, 3, bases, (int)nq - 1, (int)nq, true, stream); // transposed
     if (rc)
         return rc;
-    rc = hex_iprod_switch(nq, nelmt, in, w, out, stream);
+    rc = lanes ? hex_iprod_lanes_switch(nq, nelmt, in, w, out, stream) : hex_iprod_switch(nq, nelmt, in, w, out, stream);
     if (rc)
         return rc;
     return release_basis_bank(g_bank, stream);

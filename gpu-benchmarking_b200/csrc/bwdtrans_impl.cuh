@@ -7,6 +7,7 @@
 #include "dispatch.h"
 #include "sumfac_generic.cuh"
 #include "sumfac_iprod.cuh"
+#include "sumfac_iprod_lanes.cuh"
 #include "sumfac_iprod_mma.cuh"
 #include "sumfac_mma.cuh"
 #include "sumfac_mma32.cuh"
@@ -377,6 +378,47 @@ int launch_hex_iprod(unsigned nelmt, const T *in, const T *w, T *out, cudaStream
     B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, w, out, nelmt));
     count_launch();
     t_last_backend = "iprod-rows";
+    return launch_status();
+}
+
+// IProductWRTBase, lanes style (sumfac_iprod_lanes.cuh): in / w 16-byte aligned, even nq
+template <typename T, int NQ, int EL> int launch_quad_iprod_lanes(unsigned nelmt, const T *in, const T *w, T *out, cudaStream_t stream)
+{
+    using C = QuadIprodLanes<T, NQ, EL>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
+    const unsigned grid = (nelmt + EL - 1) / EL;
+    auto go = [&](auto kernel) -> int {
+        int rc = opt_in_smem(kernel, C::SMEM);
+        if (rc)
+            return rc;
+        B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, w, out, nelmt));
+        return 0;
+    };
+    int rc = w ? go(iproduct_quad_lanes_kernel<T, NQ, EL, true>) : go(iproduct_quad_lanes_kernel<T, NQ, EL, false>);
+    if (rc)
+        return rc;
+    count_launch();
+    t_last_backend = "iprod-lanes";
+    return launch_status();
+}
+template <typename T, int NQ, int EL, int MINB = 1>
+int launch_hex_iprod_lanes(unsigned nelmt, const T *in, const T *w, T *out, cudaStream_t stream)
+{
+    using C = HexIprodLanes<T, NQ, EL>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
+    const unsigned grid = (nelmt + EL - 1) / EL;
+    auto go = [&](auto kernel) -> int {
+        int rc = opt_in_smem(kernel, C::SMEM);
+        if (rc)
+            return rc;
+        B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, w, out, nelmt));
+        return 0;
+    };
+    int rc = w ? go(iproduct_hex_lanes_kernel<T, NQ, EL, true, MINB>) : go(iproduct_hex_lanes_kernel<T, NQ, EL, false, MINB>);
+    if (rc)
+        return rc;
+    count_launch();
+    t_last_backend = "iprod-lanes";
     return launch_status();
 }
 

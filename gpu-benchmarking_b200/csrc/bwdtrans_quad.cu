@@ -384,24 +384,65 @@ static int quad_iprod_mma_switch(unsigned nq, unsigned nelmt, const T *b0, const
     return B200FE_EUNSUPPORTED;
 }
 
+// lanes-style kernel (sumfac_iprod_lanes.cuh): even nq, 16-byte aligned in / w.  Elements per CTA from
+// tools/ipl_probe.py at 64 Mi points (profiles/r01_ipl_probe.csv); fraction of the roofline unweighted / weighted,
+// row or tensor-core kernel in ():
+//   FP64 nq   4            6            8            10           12           14           16
+//   EL        32           8            4            8            8            16           4 (unweighted only)
+//             0.96 / 1.03  0.97 / 1.05  0.92 / 1.05  0.97 / 1.02  0.98 / 1.02  0.93 / 0.90  0.77 / 0.63
+//            (0.57 / 0.85)(0.54 / 0.73)(0.90 / 1.00)(0.63 / 0.88)(0.62 / 0.88)(0.64 / 0.79)(0.69 / 0.73)
+//   FP32 EL   32           16           8            8            8            8            4
+//             0.79 / 1.00  0.85 / 1.01  0.83 / 1.01  0.86 / 0.99  0.90 / 0.99  0.82 / 0.97  0.80 / 0.93
+//            (0.56 / 0.86)(0.47 / 0.65)(0.53 / 0.72)(0.46 / 0.60)(0.56 / 0.75)(0.33 / 0.46)(0.42 / 0.63)
+static bool quad_has_iprod_lanes(unsigned nq, bool weighted)
+{
+    if (sizeof(T) == 8 && nq == 16 && weighted)
+        return false;
+    return nq % 2 == 0 && nq >= 4 && nq <= 16;
+}
+static int quad_iprod_lanes_switch(unsigned nq, unsigned nelmt, const T *in, const T *w, T *out, cudaStream_t s)
+{
+    constexpr bool D = sizeof(T) == 8;
+    switch (nq)
+    {
+#define IPL(NQ, EL)                                                                                          \
+    case NQ:                                                                                                 \
+        return launch_quad_iprod_lanes<T, NQ, EL>(nelmt, in, w, out, s);
+        IPL(4, 32)
+        IPL(6, (D ? 8 : 16))
+        IPL(8, (D ? 4 : 8))
+        IPL(10, 8)
+        IPL(12, 8)
+        IPL(14, (D ? 16 : 8))
+        IPL(16, 4)
+#undef IPL
+    default:
+        return B200FE_EUNSUPPORTED;
+    }
+}
+
 template <>
 int run_iproduct_quad<T>(Backend be, unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *w, const T *in,
                          T *out, cudaStream_t stream)
 {
-    if (be == Backend::Auto || be == Backend::Mma)
+    const bool aligned = aligned16(in) && (!w || aligned16(w)); // rows are fetched with 8- / 16-byte loads
+    if (be == Backend::Lanes && !(quad_has_iprod_lanes(nq, false) && aligned))
+        return B200FE_EUNSUPPORTED;
+    const bool lanes = be == Backend::Lanes || (be == Backend::Auto && quad_has_iprod_lanes(nq, w != nullptr) && aligned);
+    if (!lanes && (be == Backend::Auto || be == Backend::Mma))
     {
         const int rc = quad_iprod_mma_switch(nq, nelmt, b0, b1, in, w, out, stream);
         if (rc != B200FE_EUNSUPPORTED || be == Backend::Mma)
             return rc;
     }
-    else if (be != Backend::Rows)
+    else if (!lanes && be != Backend::Rows)
         return B200FE_EUNSUPPORTED;
     std::lock_guard<std::mutex> lock(g_bank_lock);
     const T *bases[2]   = {b0, b1};
     int rc = fill_basis_bank<T>(g_bank, 2, bases, (int)nq - 1, (int)nq, true, stream); // transposed
     if (rc)
         return rc;
-    rc = quad_iprod_switch(nq, nelmt, in, w, out, stream);
+    rc = lanes ? quad_iprod_lanes_switch(nq, nelmt, in, w, out, stream) : quad_iprod_switch(nq, nelmt, in, w, out, stream);
     if (rc)
         return rc;
     return release_basis_bank(g_bank, stream);

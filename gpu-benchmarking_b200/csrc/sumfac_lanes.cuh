@@ -25,13 +25,23 @@
 namespace b200fe
 {
 
+// output block of a row: as unrolled_ib (sumfac_rows.cuh), with the uniform-register budget stretched to 64 so that a
+// row of 16 doubles (IProductWRTBase nq = 16) still gets 2-wide blocks
+template <int NM, int NQ, int SIZE> constexpr int lanes_ib()
+{
+    for (int ib = 8; ib >= 2; ib /= 2)
+        if (ib <= NQ && NM * ib * (SIZE / 4) <= 64)
+            return ib;
+    return 1;
+}
+
 // NQ outputs of one row of NM register values against bank matrix BOFF, in blocks of IB outputs;
 // st(j, value) consumes output j
 template <typename T, int NM, int NQ, int BOFF, typename St>
 __device__ __forceinline__ void lanes_row(const T (&x)[NM], St st)
 {
     constexpr int PITCH = bank_pitch<T>(NQ);
-    if constexpr (unrolled_ib<NM, NQ, (int)sizeof(T)>() < 2)
+    if constexpr (lanes_ib<NM, NQ, (int)sizeof(T)>() < 2)
     {
         // very long rows (nq = 32): the basis of even a 2-wide block exceeds the uniform registers, so the
         // loop over the output blocks stays a loop (register-indexed 8-byte uniform loads, one per FMA pair)
@@ -56,7 +66,7 @@ __device__ __forceinline__ void lanes_row(const T (&x)[NM], St st)
     }
     else
     {
-        constexpr int IB = unrolled_ib<NM, NQ, (int)sizeof(T)>();
+        constexpr int IB = lanes_ib<NM, NQ, (int)sizeof(T)>();
 #pragma unroll
         for (int ib = 0; ib + IB <= NQ; ib += IB)
         {
@@ -143,35 +153,42 @@ __global__ void __launch_bounds__(QuadLanes<T, NQ, EL>::THREADS)
     }
 }
 
-// directions 0 and 1 of one plane for the IBW outputs i in [ib, ib + IBW): t1[q][i] for every q in registers
-// (the basis values of a (p, i-block) are shared by the nm rows q), then column i of t1 against B1 -> t2[j][i]
-template <typename T, int NQ, int EL, int IBW>
-__device__ __forceinline__ void hex_lanes_block(const T (&a)[(NQ - 1) * (NQ - 1)], T *dst, int ib) // t2[(j, i)] at dst[(j*NQ + i)*EL]
+// directions 0 and 1 of one plane a[NIN][NIN] for the IBW outputs i in [ib, ib + IBW): t1[q][i] for every q in registers
+// (the basis values of a (p, i-block) are shared by the NIN rows q), then column i of t1 against the second bank
+// matrix -> t2[j][i] at dst[(j*NOUT + i)*S].  BwdTrans: NIN = nm, NOUT = nq; IProductWRTBase: NIN = nq, NOUT = nm
+// with the transposed bank (common.cuh) -- the bank offsets are the same expressions in both.
+template <typename T, int NIN, int NOUT, int S, int IBW>
+__device__ __forceinline__ void plane_block(const T (&a)[NIN * NIN], T *dst, int ib)
 {
-    constexpr int NM = NQ - 1, BP = bank_pitch<T>(NQ), B0 = 0, B1 = NM * BP;
-    RowAcc<T, IBW> t1[NM];
+    constexpr int BP = bank_pitch<T>(NOUT), B0 = 0, B1 = NIN * BP;
+    RowAcc<T, IBW> t1[NIN];
 #pragma unroll
-    for (int q = 0; q < NM; ++q)
+    for (int q = 0; q < NIN; ++q)
         t1[q].zero();
 #pragma unroll
-    for (int p = 0; p < NM; ++p)
+    for (int p = 0; p < NIN; ++p)
     {
         T b[IBW];
         cbasis_load<IBW, true>(B0 + p * BP + ib, b);
 #pragma unroll
-        for (int q = 0; q < NM; ++q)
-            t1[q].fma(a[q * NM + p], b);
+        for (int q = 0; q < NIN; ++q)
+            t1[q].fma(a[q * NIN + p], b);
     }
 #pragma unroll
     for (int ii = 0; ii < IBW; ++ii)
     {
-        T x[NM];
+        T x[NIN];
 #pragma unroll
-        for (int q = 0; q < NM; ++q)
+        for (int q = 0; q < NIN; ++q)
             x[q] = t1[q].get(ii);
-        T *d = dst + (ib + ii) * EL;
-        lanes_row<T, NM, NQ, B1>(x, [&](int j, T v) { d[j * NQ * EL] = v; });
+        T *d = dst + (ib + ii) * S;
+        lanes_row<T, NIN, NOUT, B1>(x, [&](int j, T v) { d[j * NOUT * S] = v; });
     }
+}
+template <typename T, int NQ, int EL, int IBW>
+__device__ __forceinline__ void hex_lanes_block(const T (&a)[(NQ - 1) * (NQ - 1)], T *dst, int ib)
+{
+    plane_block<T, NQ - 1, NQ, EL, IBW>(a, dst, ib);
 }
 
 template <typename T, int NQ, int EL> struct HexLanes

@@ -139,3 +139,51 @@ def test_argument_errors(G):
         G.fe.iproduct("f64", (4, 4), 8, [p, 0], p, p)
     assert e.value.code == G.fe.E_INVAL
     G.fe.iproduct("f64", (4, 4, 4), 0, [p, p, p], p, p)  # empty: no-op
+
+
+IPL_QUAD = [(suf, nq) for suf in ("f64", "f32") for nq in (4, 6, 8, 10, 12, 14, 16)]
+IPL_HEX = [("f64", 4), ("f64", 6), ("f64", 8), ("f32", 4), ("f32", 6), ("f32", 8), ("f32", 10)]
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("dim,suf,nq", [(2, s, n) for s, n in IPL_QUAD] + [(3, s, n) for s, n in IPL_HEX])
+def test_lanes_kernel_forced_bit_exact(G, dim, suf, nq, weighted):
+    """sumfac_iprod_lanes.cuh, every instantiation, whole and ragged tiles; a thread fetches its own row / plane with
+    8- or 16-byte loads, so a slab that is not 16-byte aligned is refused when forced and takes the row kernel under
+    the default routing"""
+    import torch
+    dt, nm = G.NP[suf], nq - 1
+    tdt = torch.float64 if suf == "f64" else torch.float32
+    rng = np.random.default_rng(1500 + nq + dim)
+    b = [rng.standard_normal(nm * nq).astype(dt) for _ in range(dim)]
+    for nelmt in (1, 37, 1001):
+        inp = rng.standard_normal(nelmt * nq ** dim).astype(dt)
+        w = (rng.random(nelmt * nq ** dim) + 0.5).astype(dt) if weighted else None
+        want = (oracle.iproduct_quad(nq, nq, nelmt, b[0], b[1], inp, w) if dim == 2
+                else oracle.iproduct_hex(nq, nq, nq, nelmt, *b, inp, w))
+        try:
+            G.fe.set_backend("lanes")
+            got = run(G, suf, dim, nq, nelmt, b, inp, w)
+            assert G.fe.last_backend() == "iprod-lanes"
+        finally:
+            G.fe.set_backend("auto")
+        assert np.array_equal(got, want), (dim, suf, nq, nelmt, G.rel_max(got, want))
+    # misaligned input slab
+    nelmt = 37
+    inp = rng.standard_normal(nelmt * nq ** dim).astype(dt)
+    want = (oracle.iproduct_quad(nq, nq, nelmt, b[0], b[1], inp, None) if dim == 2
+            else oracle.iproduct_hex(nq, nq, nq, nelmt, *b, inp, None))
+    big_in = torch.zeros(inp.size + 4, dtype=tdt, device="cuda")
+    big_in[1:1 + inp.size] = G.dev(inp)
+    d_b = [G.dev(x) for x in b]
+    d_out = torch.full((nelmt * nm ** dim,), float("nan"), dtype=tdt, device="cuda")
+    G.fe.iproduct(suf, (nq,) * dim, nelmt, [x.data_ptr() for x in d_b], big_in.data_ptr() + inp.itemsize, d_out.data_ptr())
+    assert G.fe.last_backend() != "iprod-lanes"
+    assert np.array_equal(G.host(d_out), want)
+    try:
+        G.fe.set_backend("lanes")
+        with pytest.raises(G.fe.B200feError):
+            G.fe.iproduct(suf, (nq,) * dim, nelmt, [x.data_ptr() for x in d_b], big_in.data_ptr() + inp.itemsize,
+                          d_out.data_ptr())
+    finally:
+        G.fe.set_backend("auto")
