@@ -382,7 +382,10 @@ __global__ void __launch_bounds__(HexLanesQ<T, NQ, EL, IH>::THREADS, MINB)
 // the nq outputs of a thread go straight to global memory as runs of nq consecutive values per element.
 // One row per thread and phase, no loops, no index arithmetic beyond the prologue: the FP32 cases that the
 // general row kernel (sumfac_rows.cuh) leaves issue-bound (nq = 14: 0.66 of the roofline) are the target.
-template <typename T, int NQ, int EL> struct QuadLanesEm
+// TPC > 1: the CTA takes TPC consecutive tiles.  All their bulk copies are issued up front (TPC slots, one mbarrier
+// each), so the later tiles' loads are in flight while the first is contracted -- for the small nq, where a tile is
+// only 6-14 KB and a one-tile CTA is latency-bound.  t1 is double-buffered: one barrier per tile.
+template <typename T, int NQ, int EL, int TPC = 1> struct QuadLanesEm
 {
     static_assert(NQ % 2 == 0, "nm^2 must be odd for conflict-free lane access to the unpadded slab");
     static constexpr int NM = NQ - 1, NM2 = NM * NM, NQ2 = NQ * NQ;
@@ -390,60 +393,78 @@ template <typename T, int NQ, int EL> struct QuadLanesEm
     static constexpr int E1      = NQ + 1;  // element stride of t1 (odd)
     static constexpr int Q1      = EL * E1; // row stride of t1
     static constexpr int SIN     = (EL * NM2 * (int)sizeof(T) + 15) / 16 * 16 / (int)sizeof(T);
-    static constexpr size_t SMEM = (size_t)(SIN + NM * Q1) * sizeof(T) + 16;
+    static constexpr int S1      = (NM * Q1 * (int)sizeof(T) + 15) / 16 * 16 / (int)sizeof(T);
+    static constexpr int NBUF    = TPC > 1 ? 2 : 1;
+    static constexpr size_t SMEM = (size_t)(TPC * SIN + NBUF * S1) * sizeof(T) + 8 * ((TPC + 1) / 2 * 2);
     static_assert(THREADS <= 1024, "block size");
 };
 
-template <typename T, int NQ, int EL, int MINB = 1>
-__global__ void __launch_bounds__(QuadLanesEm<T, NQ, EL>::THREADS, MINB)
+template <typename T, int NQ, int EL, int MINB = 1, int TPC = 1>
+__global__ void __launch_bounds__(QuadLanesEm<T, NQ, EL, TPC>::THREADS, MINB)
     bwdtrans_quad_lanesem_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
 {
-    using C = QuadLanesEm<T, NQ, EL>;
+    using C = QuadLanesEm<T, NQ, EL, TPC>;
     constexpr int NM = C::NM, NM2 = C::NM2, NQ2 = C::NQ2, E1 = C::E1, Q1 = C::Q1;
     constexpr int BP = bank_pitch<T>(NQ), B0 = 0, B1 = NM * BP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *s_in       = reinterpret_cast<T *>(smem_raw);
-    T *s1         = s_in + C::SIN;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)(C::SIN + NM * Q1) * sizeof(T));
+    T *s1         = s_in + TPC * C::SIN;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)(TPC * C::SIN + C::NBUF * C::S1) * sizeof(T));
 
-    const int tid     = threadIdx.x;
-    const size_t e0   = (size_t)blockIdx.x * EL;
-    const int ne      = (nelmt - e0 < (size_t)EL) ? (int)(nelmt - e0) : EL;
+    const int tid        = threadIdx.x;
+    const unsigned tile0 = blockIdx.x * TPC;
     if (tid == 0)
     {
-        mbar_init(bar, 1);
+#pragma unroll
+        for (int t = 0; t < TPC; ++t)
+            mbar_init(bar + t, 1);
         mbar_fence_init();
     }
     __syncthreads();
     if (tid == 0)
-        ring_issue<T, EL, NM2>(s_in, bar, in, blockIdx.x, nelmt);
-    ring_wait<T, NM2>(s_in, bar, 0u, in + e0 * NM2, ne, tid);
-    grid_dependency_wait();
     {
-        const int e = tid % EL, q = tid / EL;
-        if (q < NM)
-        {
-            T x[NM];
-            const T *src = s_in + e * NM2 + q * NM;
 #pragma unroll
-            for (int p = 0; p < NM; ++p)
-                x[p] = src[p];
-            T *dst = s1 + q * Q1 + e * E1;
-            lanes_row<T, NM, NQ, B0>(x, [&](int i, T v) { dst[i] = v; });
-        }
+        for (int t = 0; t < TPC; ++t)
+            if ((size_t)(tile0 + t) * EL < nelmt)
+                ring_issue<T, EL, NM2>(s_in + t * C::SIN, bar + t, in, tile0 + t, nelmt);
     }
-    __syncthreads();
-    {
-        const int e = tid / NQ, i = tid - e * NQ;
-        T x[NM];
-        const T *src = s1 + e * E1 + i;
+    grid_dependency_wait();
 #pragma unroll
-        for (int q = 0; q < NM; ++q)
-            x[q] = src[q * Q1];
-        if (e < ne)
+    for (int t = 0; t < TPC; ++t)
+    {
+        const size_t e0 = (size_t)(tile0 + t) * EL;
+        if (e0 >= nelmt) // uniform over the CTA
+            break;
+        const int ne = (nelmt - e0 < (size_t)EL) ? (int)(nelmt - e0) : EL;
+        const T *sl  = s_in + t * C::SIN;
+        T *st1       = s1 + (t & 1) * C::S1;
+        ring_wait<T, NM2>(s_in + t * C::SIN, bar + t, 0u, in + e0 * NM2, ne, tid);
         {
-            T *dst = out + (e0 + e) * NQ2 + i;
-            lanes_row<T, NM, NQ, B1>(x, [&](int j, T v) { st_stream(dst + j * NQ, v); });
+            const int e = tid % EL, q = tid / EL;
+            if (q < NM)
+            {
+                T x[NM];
+                const T *src = sl + e * NM2 + q * NM;
+#pragma unroll
+                for (int p = 0; p < NM; ++p)
+                    x[p] = src[p];
+                T *dst = st1 + q * Q1 + e * E1;
+                lanes_row<T, NM, NQ, B0>(x, [&](int i, T v) { dst[i] = v; });
+            }
+        }
+        __syncthreads();
+        {
+            const int e = tid / NQ, i = tid - e * NQ;
+            T x[NM];
+            const T *src = st1 + e * E1 + i;
+#pragma unroll
+            for (int q = 0; q < NM; ++q)
+                x[q] = src[q * Q1];
+            if (e < ne)
+            {
+                T *dst = out + (e0 + e) * NQ2 + i;
+                lanes_row<T, NM, NQ, B1>(x, [&](int j, T v) { st_stream(dst + j * NQ, v); });
+            }
         }
     }
 }
