@@ -296,15 +296,16 @@ template <typename T, int NQ, int EL, int IH> int launch_hex_lanesq(unsigned nel
 }
 
 // ---- element-major quads, lanes style (sumfac_lanes.cuh): bulk-copied slab, one row per thread and direction
-template <typename T, int NQ, int EL> int launch_quad_lanesem(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
+template <typename T, int NQ, int EL, int TPC = 1>
+int launch_quad_lanesem(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
 {
-    using C = QuadLanesEm<T, NQ, EL>;
+    using C = QuadLanesEm<T, NQ, EL, TPC>;
     static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
-    auto kernel = bwdtrans_quad_lanesem_kernel<T, NQ, EL, 1>;
+    auto kernel = bwdtrans_quad_lanesem_kernel<T, NQ, EL, 1, TPC>;
     int rc      = opt_in_smem(kernel, C::SMEM);
     if (rc)
         return rc;
-    const unsigned grid = (nelmt + EL - 1) / EL;
+    const unsigned grid = ((nelmt + EL - 1) / EL + TPC - 1) / TPC; // TPC consecutive tiles per CTA
     B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt));
     count_launch();
     t_last_backend = "lanes-em";
