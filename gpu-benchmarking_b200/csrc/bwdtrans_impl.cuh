@@ -274,7 +274,7 @@ int launch_hex_lanes(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
     if (rc)
         return rc;
     const unsigned grid = nelmt / EL;
-    B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt, 0)); // 0: see plane_block
+    B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt));
     count_launch();
     t_last_backend = "lanes";
     return launch_status();
@@ -322,7 +322,7 @@ int launch_hex_lanesem(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
     if (rc)
         return rc;
     const unsigned grid = (nelmt + EL - 1) / EL;
-    B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt, 0)); // 0: see plane_block
+    B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt));
     count_launch();
     t_last_backend = "lanes-em";
     return launch_status();

@@ -38,7 +38,7 @@ template <int NM, int NQ, int SIZE> constexpr int lanes_ib()
 // NQ outputs of one row of NM register values against bank matrix BOFF, in blocks of IB outputs;
 // st(j, value) consumes output j
 template <typename T, int NM, int NQ, int BOFF, typename St>
-__device__ __forceinline__ void lanes_row(const T (&x)[NM], St st, int boff_rt = 0)
+__device__ __forceinline__ void lanes_row(const T (&x)[NM], St st)
 {
     constexpr int PITCH = bank_pitch<T>(NQ);
     if constexpr (lanes_ib<NM, NQ, (int)sizeof(T)>() < 2)
@@ -56,7 +56,7 @@ __device__ __forceinline__ void lanes_row(const T (&x)[NM], St st, int boff_rt =
             for (int p = 0; p < NM; ++p)
             {
                 T b[RB];
-                cbasis_load<RB, (sizeof(T) == 4)>(BOFF + boff_rt + p * PITCH + ib, b);
+                cbasis_load<RB, (sizeof(T) == 4)>(BOFF + p * PITCH + ib, b);
                 t.fma(x[p], b);
             }
 #pragma unroll
@@ -76,7 +76,7 @@ __device__ __forceinline__ void lanes_row(const T (&x)[NM], St st, int boff_rt =
             for (int p = 0; p < NM; ++p)
             {
                 T b[IB];
-                cbasis_load<IB, true>(BOFF + boff_rt + p * PITCH + ib, b);
+                cbasis_load<IB, true>(BOFF + p * PITCH + ib, b);
                 t.fma(x[p], b);
             }
 #pragma unroll
@@ -92,7 +92,7 @@ __device__ __forceinline__ void lanes_row(const T (&x)[NM], St st, int boff_rt =
             for (int p = 0; p < NM; ++p)
             {
                 T b[TAIL];
-                cbasis_load<TAIL, true>(BOFF + boff_rt + p * PITCH + (NQ - TAIL), b);
+                cbasis_load<TAIL, true>(BOFF + p * PITCH + (NQ - TAIL), b);
                 t.fma(x[p], b);
             }
 #pragma unroll
@@ -157,16 +157,8 @@ __global__ void __launch_bounds__(QuadLanes<T, NQ, EL>::THREADS)
 // (the basis values of a (p, i-block) are shared by the NIN rows q), then column i of t1 against the second bank
 // matrix -> t2[j][i] at dst[(j*NOUT + i)*S].  BwdTrans: NIN = nm, NOUT = nq; IProductWRTBase: NIN = nq, NOUT = nm
 // with the transposed bank (common.cuh) -- the bank offsets are the same expressions in both.
-// FP64 nq >= 8 only: measured 0.79 -> 0.84 (nq = 8); FP32 and the smaller nq lose (the hoisted values fit the uniform
-// registers there, and a register-indexed uniform load moves 8 bytes instead of 16)
-template <typename T, int NQ> constexpr bool kLoopVariantLoads = sizeof(T) == 8 && NQ >= 8;
-
-// `var` is 0 at run time but not to the compiler (ib * a kernel argument that is always 0): inside a rolled loop over
-// ib it keeps the second matrix's uniform loads loop-VARIANT.  Otherwise ptxas hoists all NIN*NOUT of them out of
-// the loop, spills the uniform registers into vector registers (R2UR.FILL in the loop) and the FP64 hex kernels
-// lose a CTA per SM to the extra ~50 registers.
 template <typename T, int NIN, int NOUT, int S, int IBW>
-__device__ __forceinline__ void plane_block(const T (&a)[NIN * NIN], T *dst, int ib, int var = 0)
+__device__ __forceinline__ void plane_block(const T (&a)[NIN * NIN], T *dst, int ib)
 {
     constexpr int BP = bank_pitch<T>(NOUT), B0 = 0, B1 = NIN * BP;
     RowAcc<T, IBW> t1[NIN];
@@ -190,13 +182,13 @@ __device__ __forceinline__ void plane_block(const T (&a)[NIN * NIN], T *dst, int
         for (int q = 0; q < NIN; ++q)
             x[q] = t1[q].get(ii);
         T *d = dst + (ib + ii) * S;
-        lanes_row<T, NIN, NOUT, B1>(x, [&](int j, T v) { d[j * NOUT * S] = v; }, var);
+        lanes_row<T, NIN, NOUT, B1>(x, [&](int j, T v) { d[j * NOUT * S] = v; });
     }
 }
 template <typename T, int NQ, int EL, int IBW>
-__device__ __forceinline__ void hex_lanes_block(const T (&a)[(NQ - 1) * (NQ - 1)], T *dst, int ib, int var = 0)
+__device__ __forceinline__ void hex_lanes_block(const T (&a)[(NQ - 1) * (NQ - 1)], T *dst, int ib)
 {
-    plane_block<T, NQ - 1, NQ, EL, IBW>(a, dst, ib, var);
+    plane_block<T, NQ - 1, NQ, EL, IBW>(a, dst, ib);
 }
 
 template <typename T, int NQ, int EL> struct HexLanes
@@ -215,7 +207,7 @@ template <typename T, int NQ, int EL> struct HexLanes
 
 template <typename T, int NQ, int EL, int MINB = 1>
 __global__ void __launch_bounds__(HexLanes<T, NQ, EL>::THREADS, MINB)
-    bwdtrans_hex_lanes_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt, int zero)
+    bwdtrans_hex_lanes_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
 {
     using C           = HexLanes<T, NQ, EL>;
     constexpr int NM = C::NM, NM2 = C::NM2, NQ2 = C::NQ2, NW = C::NW, IB0 = C::IB0;
@@ -244,7 +236,7 @@ __global__ void __launch_bounds__(HexLanes<T, NQ, EL>::THREADS, MINB)
         {
 #pragma unroll 1
             for (int ib = 0; ib + IB0 <= NQ; ib += IB0)
-                hex_lanes_block<T, NQ, EL, IB0>(a, dst, ib, kLoopVariantLoads<T, NQ> ? ib * zero : 0);
+                hex_lanes_block<T, NQ, EL, IB0>(a, dst, ib);
         }
         else
         {
@@ -273,8 +265,7 @@ __global__ void __launch_bounds__(HexLanes<T, NQ, EL>::THREADS, MINB)
         for (int r = 0; r < NM; ++r)
             x[r] = src[r * NQ2 * EL];
         T *dst = gout + 32 * ji;
-        lanes_row<T, NM, NQ, B2>(x, [&](int k, T v) { st_stream(dst + 32 * NQ2 * k, v); },
-                                kLoopVariantLoads<T, NQ> ? it * zero : 0);
+        lanes_row<T, NM, NQ, B2>(x, [&](int k, T v) { st_stream(dst + 32 * NQ2 * k, v); });
     }
 }
 
@@ -499,7 +490,7 @@ template <typename T, int NQ, int EL> struct HexLanesEm
 
 template <typename T, int NQ, int EL, int MINB = 1>
 __global__ void __launch_bounds__(HexLanesEm<T, NQ, EL>::THREADS, MINB)
-    bwdtrans_hex_lanesem_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt, int zero)
+    bwdtrans_hex_lanesem_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
 {
     using C = HexLanesEm<T, NQ, EL>;
     constexpr int NM = C::NM, NM2 = C::NM2, NM3 = C::NM3, NQ2 = C::NQ2, ES = C::ES, IB0 = C::IB0;
@@ -540,7 +531,7 @@ __global__ void __launch_bounds__(HexLanesEm<T, NQ, EL>::THREADS, MINB)
         {
 #pragma unroll 1
             for (int ib = 0; ib + IB0 <= NQ; ib += IB0)
-                hex_lanes_block<T, NQ, 1, IB0>(a, dst, ib, kLoopVariantLoads<T, NQ> ? ib * zero : 0);
+                hex_lanes_block<T, NQ, 1, IB0>(a, dst, ib);
         }
         else
         {
@@ -567,8 +558,7 @@ __global__ void __launch_bounds__(HexLanesEm<T, NQ, EL>::THREADS, MINB)
         if (e2 < ne)
         {
             T *dst = out + (e0 + e2) * C::NQ3 + ji;
-            lanes_row<T, NM, NQ, B2>(x, [&](int k, T v) { st_stream(dst + k * NQ2, v); },
-                                    kLoopVariantLoads<T, NQ> ? it * zero : 0);
+            lanes_row<T, NM, NQ, B2>(x, [&](int k, T v) { st_stream(dst + k * NQ2, v); });
         }
     }
 }

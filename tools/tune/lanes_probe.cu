@@ -111,8 +111,7 @@ template <typename T> struct Case
         cudaFree(ref);
         cudaFree(bad);
     }
-    template <typename K, typename... A>
-    void run(const char *name, K kernel, unsigned grid, int threads, size_t smem, A... extra)
+    template <typename K> void run(const char *name, K kernel, unsigned grid, int threads, size_t smem)
     {
         if (smem > 48 * 1024)
             CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -120,7 +119,7 @@ template <typename T> struct Case
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
         CK(cudaMemset(out, 0xff, sizeof(T) * nout));
         CK(cudaMemset(bad, 0, 8));
-        kernel<<<grid, threads, smem>>>(in, out, nelmt, extra...);
+        kernel<<<grid, threads, smem>>>(in, out, nelmt);
         CK(cudaGetLastError());
         diff_kernel<T><<<1024, 256>>>(out, ref, nout, bad);
         unsigned long long nbad = 0;
@@ -133,7 +132,7 @@ template <typename T> struct Case
         for (int r = 0; r < reps; ++r)
         {
             cudaEventRecord(e0);
-            kernel<<<grid, threads, smem>>>(in, out, nelmt, extra...);
+            kernel<<<grid, threads, smem>>>(in, out, nelmt);
             cudaEventRecord(e1);
             CK(cudaEventSynchronize(e1));
             float ms;
@@ -152,25 +151,25 @@ template <typename T> struct Case
 
 #define HP(T, NQ, EL, MB)                                                                                    \
     c.run("plane EL=" #EL " MINB=" #MB, bwdtrans_hex_lanes_kernel<T, NQ, EL, MB>, c.nelmt / EL,               \
-          HexLanes<T, NQ, EL>::THREADS, HexLanes<T, NQ, EL>::SMEM, 0);
+          HexLanes<T, NQ, EL>::THREADS, HexLanes<T, NQ, EL>::SMEM);
+#define HQ(T, NQ, EL, IH, MB)                                                                                \
+    c.run("q-outer EL=" #EL " IH=" #IH " MINB=" #MB, bwdtrans_hex_lanesq_kernel<T, NQ, EL, IH, MB>, c.nelmt / EL, \
+          HexLanesQ<T, NQ, EL, IH>::THREADS, HexLanesQ<T, NQ, EL, IH>::SMEM);
 #define QL(T, NQ, EL)                                                                                        \
     c.run("quad EL=" #EL, bwdtrans_quad_lanes_kernel<T, NQ, EL>, c.nelmt / EL, QuadLanes<T, NQ, EL>::THREADS,  \
           QuadLanes<T, NQ, EL>::SMEM);
+
+#define H3(T, NQ, EL, NWK, MB)                                                                               \
+    c.run("3-phase EL=" #EL " NWK=" #NWK " MINB=" #MB, bwdtrans_hex_lanes3_kernel<T, NQ, EL, NWK, MB>, c.nelmt / EL, \
+          HexLanes3<T, NQ, EL, NWK>::THREADS, HexLanes3<T, NQ, EL, NWK>::SMEM);
 
 int main()
 {
     printf("op,nq,dtype,_,threads,smem,ctas_per_sm,ms_best,ms_avg,gb_s,mismatches\n");
     {
-        Case<double> c;
-        c.setup(3, 8); HP(double, 8, 16, 1) HP(double, 8, 16, 3) HP(double, 8, 8, 1) HP(double, 8, 8, 5) HP(double, 8, 32, 1) c.teardown();
-        c.setup(3, 9); HP(double, 9, 16, 1) HP(double, 9, 8, 1) HP(double, 9, 8, 3) c.teardown();
-        c.setup(3, 10); HP(double, 10, 16, 1) HP(double, 10, 8, 1) HP(double, 10, 8, 2) c.teardown();
-        c.setup(3, 6); HP(double, 6, 32, 1) c.teardown();
-    }
-    {
         Case<float> c;
-        c.setup(3, 10); HP(float, 10, 16, 3) c.teardown();
-        c.setup(3, 9); HP(float, 9, 32, 1) c.teardown();
+        c.setup(3, 9); HP(float, 9, 16, 1) HP(float, 9, 16, 3) HP(float, 9, 16, 4) HP(float, 9, 32, 1) c.teardown();
+        c.setup(3, 10); HP(float, 10, 16, 1) HP(float, 10, 16, 2) HP(float, 10, 16, 3) HP(float, 10, 32, 1) c.teardown();
     }
     return 0;
 }
