@@ -212,16 +212,15 @@ static int quad_lanes_switch(unsigned nq, unsigned nelmt, const T *in, T *out, c
 // element-major lanes kernel (sumfac_lanes.cuh, "lanes-em"): even nq where it measured faster than the table's choice
 // at 64 Mi points (tools/tune/lanesem_probe.cu, profiles/r01_lanesem_probe.csv; fraction of the HBM roofline).
 // TPC = tiles per CTA (all bulk copies issued up front): pays for the small nq, whose tiles are only 3-14 KB.
-//   FP64  nq   4     6     8     10    12    14    16          FP32  nq   6     10    12    14    16
-//   EL / TPC  32/4  16/2  32/1  16/1  16/1   4/1   4/1               EL  16/8   8/4  16/1   8/1   8/1
-//   lanes-em  0.98  0.98  1.00  0.99  0.99  0.98  0.97                   0.89  0.88  0.92  0.89  0.93
-//   before    0.94  0.89  0.93  0.91  0.96  0.94  0.92                   0.85  0.85  0.85  0.66  0.82
-// (FP32 nq = 4, 8: 0.89 either way, the pipe kernel stays)
+//   FP64  nq   4     6     8     10    12    14    16      FP32  nq   4     6     8     10    12    14    16
+//   EL / TPC  32/4  16/2  32/1  16/1  16/1   4/1   4/1           EL  64/8  16/8  32/4   8/4  16/1   8/1   8/1
+//   lanes-em  0.98  0.98  1.00  0.99  0.99  0.98  0.97               0.90  0.89  0.91  0.89  0.92  0.89  0.93
+//   before    0.94  0.89  0.93  0.91  0.96  0.94  0.92               0.88  0.85  0.89  0.85  0.85  0.66  0.82
 static bool quad_has_lanesem(unsigned nq)
 {
     if (sizeof(T) == 8)
         return nq % 2 == 0 && nq >= 4 && nq <= 16;
-    return nq == 6 || nq == 10 || nq == 12 || nq == 14 || nq == 16;
+    return nq % 2 == 0 && nq >= 4 && nq <= 16;
 }
 static int quad_lanesem_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
 {
@@ -229,15 +228,11 @@ static int quad_lanesem_switch(unsigned nq, unsigned nelmt, const T *in, T *out,
     switch (nq)
     {
     case 4:
-        if constexpr (D)
-            return launch_quad_lanesem<T, 4, 32, 4>(nelmt, in, out, s);
-        break;
+        return launch_quad_lanesem<T, 4, (D ? 32 : 64), (D ? 4 : 8)>(nelmt, in, out, s);
     case 6:
         return launch_quad_lanesem<T, 6, 16, (D ? 2 : 8)>(nelmt, in, out, s);
     case 8:
-        if constexpr (D)
-            return launch_quad_lanesem<T, 8, 32>(nelmt, in, out, s);
-        break;
+        return launch_quad_lanesem<T, 8, 32, (D ? 1 : 4)>(nelmt, in, out, s);
     case 10:
         return launch_quad_lanesem<T, 10, (D ? 16 : 8), (D ? 1 : 4)>(nelmt, in, out, s);
     case 12:

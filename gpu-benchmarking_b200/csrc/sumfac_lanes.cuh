@@ -86,13 +86,16 @@ __device__ __forceinline__ void lanes_row(const T (&x)[NM], St st)
         constexpr int TAIL = NQ % IB;
         if constexpr (TAIL > 0)
         {
-            RowAcc<T, TAIL> t;
+            // FP32 with an odd number of outputs left (IProductWRTBase: nm outputs): the bank rows are padded with
+            // zeros up to a whole 16-byte vector, so the tail runs one output wider on packed FMAs and drops the last
+            constexpr int TW = (sizeof(T) == 4 && TAIL % 2 == 1 && NQ < PITCH) ? TAIL + 1 : TAIL;
+            RowAcc<T, TW> t;
             t.zero();
 #pragma unroll
             for (int p = 0; p < NM; ++p)
             {
-                T b[TAIL];
-                cbasis_load<TAIL, true>(BOFF + p * PITCH + (NQ - TAIL), b);
+                T b[TW];
+                cbasis_load<TW, true>(BOFF + p * PITCH + (NQ - TAIL), b);
                 t.fma(x[p], b);
             }
 #pragma unroll

@@ -121,9 +121,9 @@ def test_lanes_backend_where_it_has_no_instantiation(G):
         G.fe.set_backend("lanes")
         with pytest.raises(Exception):  # interleaved: nq = 4 .. 16 and 32 only
             G.run_quad("BwdTransQuadKernel_Coa", "f64", 20, 20, 32, *quad_case(G, "f64", 20, 32, 2)[:3])
-        b0, b1, inp, _ = quad_case(G, "f32", 8, 32, 1)
-        with pytest.raises(Exception):  # element-major FP32: nq = 6, 10, 12, 14, 16 only
-            G.run_quad("BwdTransQuadKernel", "f32", 8, 8, 32, b0, b1, oracle.from_coa(inp, 32, 49))
+        b0, b1, inp, _ = quad_case(G, "f32", 9, 32, 1)
+        with pytest.raises(Exception):  # element-major quads: even nq = 4 .. 16 only
+            G.run_quad("BwdTransQuadKernel", "f32", 9, 9, 32, b0, b1, oracle.from_coa(inp, 32, 64))
         b, inph, _ = hex_case(G, "f64", 8, 32, 3)
         with pytest.raises(Exception):  # element-major hexes: nq = 4, 6 (and 8, 10 in FP32) only
             G.run_hex("BwdTransHexKernel", "f64", (8, 8, 8), 32, b, inph)
@@ -131,7 +131,7 @@ def test_lanes_backend_where_it_has_no_instantiation(G):
         G.fe.set_backend("auto")
 
 
-LANES_EM = [("f64", nq) for nq in (4, 6, 8, 10, 12, 14, 16)] + [("f32", nq) for nq in (6, 10, 12, 14, 16)]
+LANES_EM = [("f64", nq) for nq in (4, 6, 8, 10, 12, 14, 16)] + [("f32", nq) for nq in (4, 6, 8, 10, 12, 14, 16)]
 
 
 @pytest.mark.parametrize("suf,nq", LANES_EM)
