@@ -51,3 +51,26 @@ def test_vector_benchmark_logs(golden, b):
     for n, cols in norms.items():
         for got, want in zip(cols, golden[f"b{b}"][n]):
             assert abs(got - want) / want < 6e-10, (b, n, got, want)
+
+
+def test_roofline_report_reads_the_committed_driver_logs():
+    """tools/roofline_report.py: parses the reference log format plus the drivers' info lines"""
+    import importlib.util
+    import io
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("roofline_report", os.path.join(root, "tools", "roofline_report.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    logs = [mod.parse(os.path.join(root, "profiles", "driver_logs", n))
+            for n in ("r01_benchmark04_nq4x4.txt", "r01_benchmark05_nq8x8x8.txt", "r01_benchmark01_outfile.txt")]
+    assert "NQ = 4, 4" in logs[0]["title"] and "NQ = 8, 8, 8" in logs[1]["title"]
+    for lg in logs[:2]:
+        assert set(lg["rows"]) == {128 << k for k in range(14)}          # the reference's sweep 128 .. 1 Mi
+        assert all(len(v[1]) == 11 for v in lg["rows"].values())         # exactly 11 numeric columns
+        assert set(lg["info"]) == set(lg["rows"])
+    assert all(len(v[1]) == 5 for v in logs[2]["rows"].values())
+    buf = io.StringIO()
+    for lg in logs:
+        mod.report(lg, buf)
+    text = buf.getvalue()
+    assert text.count("###") == 3 and "| 1048576 | GDOF/s |" in text
