@@ -107,7 +107,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.005)  # a handful of samples per 30 ms timed region; every NVML query takes a driver lock
 
     def start(self):
         if self.nv:

@@ -361,15 +361,15 @@ static int hex_iprod_mma_switch(unsigned nq, unsigned nelmt, const T *b0, const 
     return B200FE_EUNSUPPORTED;
 }
 
-// lanes-style kernel (sumfac_iprod_lanes.cuh): even nq, 16-byte aligned in / w.  Elements per CTA from
-// tools/ipl_probe.py at 64 Mi points (profiles/r01_ipl_probe.csv); fraction of the roofline unweighted / weighted,
-// row kernel in ():
-//   FP64 nq   4            6                      FP32 nq   4            6            8 (unweighted)  10
-//   EL        32           4                           EL   16           8            4               8
-//             0.66 / 0.68  0.85 / 0.87                      0.87 / 0.97  0.83 / 0.89  0.62            0.65 / 0.56
-//            (0.51 / 0.68)(0.57 / 0.71)                    (0.57 / 0.75)(0.47 / 0.66)(0.53)          (0.31 / 0.42)
-// FP64 nq = 8: 0.68 / 0.70 against 0.67 / 0.93 for the row kernel (a plane of 64 doubles plus the direction-0 block
-// leaves 2-3 CTAs of 64 threads per SM); FP32 nq = 8 weighted: 0.68 against 0.79.
+// lanes-style kernel (sumfac_iprod_lanes.cuh): even nq, 16-byte aligned in / w.  Elements per CTA and the staged
+// variant (slab through shared memory instead of per-thread plane loads) from tools/ipl_probe.py and
+// tools/tune/iprod_probe.cu at 64 Mi points (profiles/r01_ipl_probe.csv, r01_iprod_probe.csv); fraction of the roofline
+// unweighted / weighted, row kernel in ():
+//   FP64 nq   4 (staged)    6 (weighted: staged)      FP32 nq   4            6 (weighted: staged)  8 (unweighted)  10
+//   EL        16            4 / 8                          EL   64           8                     4               8
+//             0.77 / 1.06   0.89 / 1.04                         0.95 / 1.00  0.87 / 0.96           0.65            0.70 / 0.68
+//            (0.51 / 0.68) (0.57 / 0.71)                       (0.57 / 0.75)(0.47 / 0.66)         (0.53)          (0.31 / 0.42)
+// FP64 nq = 8: 0.71 / 0.71 against 0.67 / 0.93 for the row kernel; FP32 nq = 8 weighted: 0.69 against 0.79.
 static bool hex_has_iprod_lanes(unsigned nq, bool weighted)
 {
     if (sizeof(T) == 8)
@@ -382,14 +382,19 @@ static int hex_iprod_lanes_switch(unsigned nq, unsigned nelmt, const T *in, cons
     switch (nq)
     {
     case 4:
-        return launch_hex_iprod_lanes<T, 4, (D ? 32 : 16)>(nelmt, in, w, out, s);
+        if constexpr (D)
+            return launch_hex_iprod_lanes<T, 4, 16, 1, true>(nelmt, in, w, out, s);
+        else
+            return launch_hex_iprod_lanes<T, 4, 64>(nelmt, in, w, out, s);
     case 6:
+        if (w)
+            return launch_hex_iprod_lanes<T, 6, 8, 1, true>(nelmt, in, w, out, s);
         return launch_hex_iprod_lanes<T, 6, (D ? 4 : 8)>(nelmt, in, w, out, s);
     case 8:
         return launch_hex_iprod_lanes<T, 8, 4>(nelmt, in, w, out, s);
     case 10:
         if constexpr (!D)
-            return launch_hex_iprod_lanes<T, 10, 8>(nelmt, in, w, out, s);
+            return launch_hex_iprod_lanes<T, 10, 8, 3>(nelmt, in, w, out, s);
         return B200FE_EUNSUPPORTED;
     default:
         return B200FE_EUNSUPPORTED;

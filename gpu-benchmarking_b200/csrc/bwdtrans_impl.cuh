@@ -402,10 +402,10 @@ template <typename T, int NQ, int EL> int launch_quad_iprod_lanes(unsigned nelmt
     t_last_backend = "iprod-lanes";
     return launch_status();
 }
-template <typename T, int NQ, int EL, int MINB = 1>
+template <typename T, int NQ, int EL, int MINB = 1, bool STAGED = false>
 int launch_hex_iprod_lanes(unsigned nelmt, const T *in, const T *w, T *out, cudaStream_t stream)
 {
-    using C = HexIprodLanes<T, NQ, EL>;
+    using C = HexIprodLanes<T, NQ, EL, STAGED>;
     static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
     const unsigned grid = (nelmt + EL - 1) / EL;
     auto go = [&](auto kernel) -> int {
@@ -415,7 +415,8 @@ int launch_hex_iprod_lanes(unsigned nelmt, const T *in, const T *w, T *out, cuda
         B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, w, out, nelmt));
         return 0;
     };
-    int rc = w ? go(iproduct_hex_lanes_kernel<T, NQ, EL, true, MINB>) : go(iproduct_hex_lanes_kernel<T, NQ, EL, false, MINB>);
+    int rc = w ? go(iproduct_hex_lanes_kernel<T, NQ, EL, true, MINB, STAGED>)
+               : go(iproduct_hex_lanes_kernel<T, NQ, EL, false, MINB, STAGED>);
     if (rc)
         return rc;
     count_launch();

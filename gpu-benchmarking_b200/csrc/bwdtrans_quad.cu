@@ -387,16 +387,14 @@ static int quad_iprod_mma_switch(unsigned nq, unsigned nelmt, const T *b0, const
 // tools/ipl_probe.py at 64 Mi points (profiles/r01_ipl_probe.csv); fraction of the roofline unweighted / weighted,
 // row or tensor-core kernel in ():
 //   FP64 nq   4            6            8            10           12           14           16
-//   EL        32           8            4            8            8            16           4 (unweighted only)
-//             0.96 / 1.03  0.97 / 1.05  0.92 / 1.05  0.97 / 1.02  0.98 / 1.02  0.93 / 0.90  0.77 / 0.63
+//   EL        32           8            4            8            8            16           2
+//             0.96 / 1.03  0.97 / 1.05  0.92 / 1.05  0.97 / 1.02  0.98 / 1.02  0.93 / 0.90  0.81 / 0.75
 //            (0.57 / 0.85)(0.54 / 0.73)(0.90 / 1.00)(0.63 / 0.88)(0.62 / 0.88)(0.64 / 0.79)(0.69 / 0.73)
 //   FP32 EL   32           16           8            8            8            8            4
 //             0.79 / 1.00  0.85 / 1.01  0.83 / 1.01  0.86 / 0.99  0.90 / 0.99  0.82 / 0.97  0.80 / 0.93
 //            (0.56 / 0.86)(0.47 / 0.65)(0.53 / 0.72)(0.46 / 0.60)(0.56 / 0.75)(0.33 / 0.46)(0.42 / 0.63)
-static bool quad_has_iprod_lanes(unsigned nq, bool weighted)
+static bool quad_has_iprod_lanes(unsigned nq, bool)
 {
-    if (sizeof(T) == 8 && nq == 16 && weighted)
-        return false;
     return nq % 2 == 0 && nq >= 4 && nq <= 16;
 }
 static int quad_iprod_lanes_switch(unsigned nq, unsigned nelmt, const T *in, const T *w, T *out, cudaStream_t s)
@@ -413,7 +411,7 @@ static int quad_iprod_lanes_switch(unsigned nq, unsigned nelmt, const T *in, con
         IPL(10, 8)
         IPL(12, 8)
         IPL(14, (D ? 16 : 8))
-        IPL(16, 4)
+        IPL(16, (D ? 2 : 4))
 #undef IPL
     default:
         return B200FE_EUNSUPPORTED;

@@ -100,35 +100,102 @@ __global__ void __launch_bounds__(QuadIprodLanes<T, NQ, EL>::THREADS)
     }
 }
 
-template <typename T, int NQ, int EL> struct HexIprodLanes
+// STAGED: the planes of a hex are 128-512 bytes apart, so the per-thread vector loads above touch a different line in
+// every lane (nq = 8 FP32: 16 loads x 32 lines per warp for 64 lines of data) and the L1 tag rate, not HBM, sets the
+// pace (0.64-0.71 of the roofline).  The staged variant loads the CTA's slab cooperatively (consecutive threads,
+// consecutive 16-byte vectors, metric multiplied in) into shared memory with the plane stride padded by one vector
+// (bank shift 4 words per plane: the threads' own 16-byte plane reads are conflict-free) and takes the planes from
+// there.
+template <typename T, int NQ, int EL, bool STAGED = false> struct HexIprodLanes
 {
     static_assert(NQ % 2 == 0, "planes must be whole 16-byte vectors");
     static constexpr int NM = NQ - 1, NQ2 = NQ * NQ, NQ3 = NQ2 * NQ, NM2 = NM * NM, NM3 = NM2 * NM;
     static constexpr int THREADS = (EL * NQ + 31) / 32 * 32;
     static constexpr int K1      = (EL * NM2 + 30) / 32 * 32 + 1; // plane stride of u: = 1 mod 32
-    static constexpr size_t SMEM = (size_t)NQ * K1 * sizeof(T);
+    static constexpr int W       = 16 / (int)sizeof(T);
+    static constexpr int PS      = NQ2 + W;                       // padded plane stride of the staged slab
+    static constexpr int S2      = (NQ * K1 * (int)sizeof(T) + 15) / 16 * 16 / (int)sizeof(T);
+    static constexpr size_t SMEM = (size_t)(S2 + (STAGED ? EL * NQ * PS : 0)) * sizeof(T);
     static constexpr int B2      = 2 * NQ * bank_pitch<T>(NM);
     static constexpr int IB0     = sizeof(T) == 4 ? 2 : 1;
     static constexpr bool ROLLED = sizeof(T) == 8 || NQ >= 9; // see HexLanes
 };
 
-template <typename T, int NQ, int EL, bool WEIGHTED, int MINB = 1>
-__global__ void __launch_bounds__(HexIprodLanes<T, NQ, EL>::THREADS, MINB)
+template <typename T, int NQ, int EL, bool WEIGHTED, int MINB = 1, bool STAGED = false>
+__global__ void __launch_bounds__(HexIprodLanes<T, NQ, EL, STAGED>::THREADS, MINB)
     iproduct_hex_lanes_kernel(const T *__restrict__ in, const T *__restrict__ w, T *__restrict__ out, unsigned nelmt)
 {
-    using C = HexIprodLanes<T, NQ, EL>;
+    using C = HexIprodLanes<T, NQ, EL, STAGED>;
     constexpr int NM = C::NM, NQ2 = C::NQ2, NM2 = C::NM2, K1 = C::K1, IB0 = C::IB0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T *s2 = reinterpret_cast<T *>(smem_raw);
     const int tid   = threadIdx.x;
     const size_t e0 = (size_t)blockIdx.x * EL;
     const int ne    = (nelmt - e0 < (size_t)EL) ? (int)(nelmt - e0) : EL;
+    if constexpr (STAGED)
+    {
+        using V         = typename Vec16<T>::type;
+        constexpr int W = C::W, VPP = NQ2 / W; // vectors per plane
+        T *s_in         = s2 + C::S2;
+        const V *gin    = reinterpret_cast<const V *>(in + e0 * C::NQ3);
+        const V *gw     = reinterpret_cast<const V *>(w + (WEIGHTED ? e0 * C::NQ3 : 0));
+        const int nv    = ne * NQ * VPP;
+        constexpr int ITER = (EL * NQ * VPP + C::THREADS - 1) / C::THREADS;
+        V v[ITER], u[ITER];
+#pragma unroll
+        for (int it = 0; it < ITER; ++it)
+        {
+            const int c = it * C::THREADS + tid;
+            if (c < nv)
+            {
+                v[it] = ld_stream(gin + c);
+                if (WEIGHTED)
+                    u[it] = ld_stream(gw + c);
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < ITER; ++it)
+        {
+            const int c = it * C::THREADS + tid;
+            if (c < nv)
+            {
+                if (WEIGHTED)
+                {
+                    T *pv       = reinterpret_cast<T *>(&v[it]);
+                    const T *pu = reinterpret_cast<const T *>(&u[it]);
+#pragma unroll
+                    for (int k = 0; k < W; ++k)
+                        pv[k] = pv[k] * pu[k];
+                }
+                const int plane = c / VPP, off = c - plane * VPP;
+                *reinterpret_cast<V *>(s_in + plane * C::PS + off * W) = v[it];
+            }
+        }
+        __syncthreads();
+    }
     if (tid < EL * NQ)
     {
         const int e = tid / NQ, k = tid - e * NQ;
         T a[NQ2];
-        const size_t off = ((e0 + (e < ne ? e : 0)) * NQ + k) * NQ2;
-        iprod_fetch<T, NQ2, true, WEIGHTED>(a, in + off, WEIGHTED ? w + off : nullptr);
+        if constexpr (STAGED)
+        {
+            using V      = typename Vec16<T>::type;
+            const V *src = reinterpret_cast<const V *>(s2 + C::S2 + tid * C::PS);
+#pragma unroll
+            for (int c = 0; c < NQ2 / C::W; ++c)
+            {
+                const V t = src[c];
+                const T *pt = reinterpret_cast<const T *>(&t);
+#pragma unroll
+                for (int kk = 0; kk < C::W; ++kk)
+                    a[c * C::W + kk] = pt[kk];
+            }
+        }
+        else
+        {
+            const size_t off = ((e0 + (e < ne ? e : 0)) * NQ + k) * NQ2;
+            iprod_fetch<T, NQ2, true, WEIGHTED>(a, in + off, WEIGHTED ? w + off : nullptr);
+        }
         grid_dependency_wait();
         T *dst = s2 + k * K1 + e * NM2; // u[(q, p)] at dst[q*NM + p]
         if constexpr (C::ROLLED)
