@@ -328,6 +328,52 @@ def sweep_iproduct(fe, torch, peak, reps=5):
     return out
 
 
+def sweep_fused(fe, torch, reps=10):
+    """operator + sum(out^2) at ~64 Mi quadrature points: the two-pass form the reference uses after
+    every variant against the fused entry point, for one shape per kernel family that carries the epilogue"""
+    out = []
+    st = torch.cuda.current_stream().cuda_stream
+    d_scr = torch.empty(fe.sumsq_scratch_bytes(), dtype=torch.uint8, device="cuda")
+    d_res = torch.zeros(2, dtype=torch.float64, device="cuda")
+    for dim, nq, suf, tdt in ((2, 8, "f32", torch.float32), (2, 16, "f64", torch.float64), (3, 6, "f64", torch.float64),
+                              (3, 8, "f32", torch.float32), (3, 8, "f64", torch.float64)):
+        nm = nq - 1
+        nelmt = ((1 << 26) // nq ** dim) // 32 * 32
+        b = torch.from_numpy(gen_basis(nm, nq, "float64")).to(tdt).cuda()
+        d_in = torch.randn(nelmt * nm ** dim, dtype=tdt, device="cuda")
+        d_out = torch.empty(nelmt * nq ** dim, dtype=tdt, device="cuda")
+
+        def plain():
+            if dim == 2:
+                fe.bwdtrans_quad("BwdTransQuadKernel_QP_Shared", suf, nq, nq, nelmt, b.data_ptr(), b.data_ptr(),
+                                 d_in.data_ptr(), d_out.data_ptr(), stream=st)
+            else:
+                fe.bwdtrans_hex("BwdTransHexKernel_QP_Shared", suf, nq, nq, nq, nelmt, b.data_ptr(), b.data_ptr(),
+                                b.data_ptr(), d_in.data_ptr(), d_out.data_ptr(), stream=st)
+            fe.sumsq(suf, d_out.data_ptr(), d_out.numel(), d_res.data_ptr(), d_scr.data_ptr(), st)
+
+        def fused():
+            fe.bwdtrans_sumsq(suf, (nq,) * dim, nelmt, [b.data_ptr()] * dim, d_in.data_ptr(), d_out.data_ptr(),
+                              d_res.data_ptr() + 8, d_scr.data_ptr(), st)
+
+        ms = []
+        for fn in (plain, fused):
+            fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1) / reps)
+        r = d_res.cpu().numpy()
+        out.append({"op": "quad" if dim == 2 else "hex", "nq": nq, "dtype": suf, "nelmt": nelmt,
+                    "backend": fe.last_backend(), "operator_then_checksum_ms": round(ms[0], 4),
+                    "fused_ms": round(ms[1], 4), "agree": bool(abs(r[0] - r[1]) <= 1e-12 * abs(r[0]))})
+        del d_in, d_out
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -520,13 +566,14 @@ def main():
     cpu = None
     if ngpus == 1 and not args.no_cpu:
         cpu = cpu_reference_rate(sample_target_s=12.0)
-    sw = sw_ip = sw_coa = None
+    sw = sw_ip = sw_coa = sw_fused = None
     if ngpus == 1 and not args.no_sweep:
         del d_in, d_out
         torch.cuda.empty_cache()
         sw = sweep(fe, torch, peak)
         sw_ip = sweep_iproduct(fe, torch, peak)
         sw_coa = sweep_coa(fe, torch, peak)
+        sw_fused = sweep_fused(fe, torch)
 
     line = {
         "metric": METRIC, "value": value, "unit": "GDoF/s", "n_gpus": ngpus, "steps": args.steps,
@@ -540,6 +587,7 @@ def main():
         line["sweep"] = sw
         line["sweep_iproduct"] = sw_ip
         line["sweep_coa"] = sw_coa
+        line["sweep_fused_checksum"] = sw_fused
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -215,22 +215,23 @@ static bool hex_has_lanesem(unsigned nq)
 {
     return nq == 4 || nq == 6 || ((nq == 8 || nq == 10) && sizeof(T) == 4);
 }
-static int hex_lanesem_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
+static int hex_lanesem_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s, double *partials,
+                               unsigned *npartials)
 {
     constexpr bool D = sizeof(T) == 8;
     switch (nq)
     {
     case 4:
-        return launch_hex_lanesem<T, 4, (D ? 16 : 64)>(nelmt, in, out, s);
+        return launch_hex_lanesem<T, 4, (D ? 16 : 64)>(nelmt, in, out, s, partials, npartials);
     case 6:
-        return launch_hex_lanesem<T, 6, 16>(nelmt, in, out, s);
+        return launch_hex_lanesem<T, 6, 16>(nelmt, in, out, s, partials, npartials);
     case 8:
         if constexpr (!D)
-            return launch_hex_lanesem<T, 8, 16>(nelmt, in, out, s);
+            return launch_hex_lanesem<T, 8, 16>(nelmt, in, out, s, partials, npartials);
         break;
     case 10:
         if constexpr (!D)
-            return launch_hex_lanesem<T, 10, 16, 3>(nelmt, in, out, s);
+            return launch_hex_lanesem<T, 10, 16, 3>(nelmt, in, out, s, partials, npartials);
         break;
     default:
         break;
@@ -275,7 +276,7 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
             be = (nq0 < kHexLanesMinNq || (nq0 == 5 && sizeof(T) == 8)) ? Backend::Tpe // FP64 nq = 5: 0.94 against 0.88
                  : nq0 <= kHexLanesMaxNq ? Backend::Lanes
                                          : ((have & 1) ? Backend::Rows : Backend::Generic);
-        else if (hex_has_lanesem(nq0) && aligned16(in) && !partials)
+        else if (hex_has_lanesem(nq0) && aligned16(in))
             be = Backend::Lanes;
         else
             be = preferred;
@@ -314,7 +315,7 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
     else if (be == Backend::Pipe)
         rc = hex_pipe_switch(nq0, nelmt, in, out, stream);
     else if (be == Backend::Lanes)
-        rc = coa ? hex_lanes_switch(nq0, nelmt, in, out, stream) : hex_lanesem_switch(nq0, nelmt, in, out, stream);
+        rc = coa ? hex_lanes_switch(nq0, nelmt, in, out, stream) : hex_lanesem_switch(nq0, nelmt, in, out, stream, partials, npartials);
     else
         rc = hex_tpe_switch(nq0, nelmt, in, out, stream);
     if (rc)

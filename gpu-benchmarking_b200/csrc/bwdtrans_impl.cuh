@@ -35,8 +35,8 @@ template <typename K> inline int opt_in_smem(K kernel, size_t bytes)
     return 0;
 }
 
-// launch as a programmatic dependent of the kernel before it on the stream (the constant-bank fill): see
-// grid_dependency_wait() in common.cuh
+// plain stream-ordered launch with the arguments converted to the kernel's parameter types (the name is historical:
+// the operator used to be a programmatic dependent of the constant-bank fill; see common.cuh for why it no longer is)
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
                                     cudaStream_t stream, Args... args)
@@ -46,11 +46,8 @@ inline cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned grid, uns
     cfg.blockDim           = dim3(block);
     cfg.dynamicSmemBytes   = smem;
     cfg.stream             = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs                                          = attr;
-    cfg.numAttrs                                       = 1;
+    cfg.attrs              = nullptr;
+    cfg.numAttrs           = 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -297,32 +294,51 @@ template <typename T, int NQ, int EL, int IH> int launch_hex_lanesq(unsigned nel
 
 // ---- element-major quads, lanes style (sumfac_lanes.cuh): bulk-copied slab, one row per thread and direction
 template <typename T, int NQ, int EL, int TPC = 1>
-int launch_quad_lanesem(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
+int launch_quad_lanesem(unsigned nelmt, const T *in, T *out, cudaStream_t stream, double *partials = nullptr,
+                        unsigned *npartials = nullptr)
 {
     using C = QuadLanesEm<T, NQ, EL, TPC>;
     static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
-    auto kernel = bwdtrans_quad_lanesem_kernel<T, NQ, EL, 1, TPC>;
-    int rc      = opt_in_smem(kernel, C::SMEM);
+    const unsigned grid = ((nelmt + EL - 1) / EL + TPC - 1) / TPC; // TPC consecutive tiles per CTA
+    const bool fuse     = partials && npartials && grid <= kFusedPartialsMax;
+    auto go = [&](auto kernel) -> int {
+        int rc = opt_in_smem(kernel, C::SMEM);
+        if (rc)
+            return rc;
+        B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt, fuse ? partials : nullptr));
+        return 0;
+    };
+    int rc = fuse ? go(bwdtrans_quad_lanesem_kernel<T, NQ, EL, 1, TPC, true>)
+                  : go(bwdtrans_quad_lanesem_kernel<T, NQ, EL, 1, TPC, false>);
     if (rc)
         return rc;
-    const unsigned grid = ((nelmt + EL - 1) / EL + TPC - 1) / TPC; // TPC consecutive tiles per CTA
-    B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt));
+    if (fuse)
+        *npartials = grid;
     count_launch();
     t_last_backend = "lanes-em";
     return launch_status();
 }
 
 template <typename T, int NQ, int EL, int MINB = 1>
-int launch_hex_lanesem(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
+int launch_hex_lanesem(unsigned nelmt, const T *in, T *out, cudaStream_t stream, double *partials = nullptr,
+                       unsigned *npartials = nullptr)
 {
     using C = HexLanesEm<T, NQ, EL>;
     static_assert(C::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
-    auto kernel = bwdtrans_hex_lanesem_kernel<T, NQ, EL, MINB>;
-    int rc      = opt_in_smem(kernel, C::SMEM);
+    const unsigned grid = (nelmt + EL - 1) / EL;
+    const bool fuse     = partials && npartials && grid <= kFusedPartialsMax;
+    auto go = [&](auto kernel) -> int {
+        int rc = opt_in_smem(kernel, C::SMEM);
+        if (rc)
+            return rc;
+        B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt, fuse ? partials : nullptr));
+        return 0;
+    };
+    int rc = fuse ? go(bwdtrans_hex_lanesem_kernel<T, NQ, EL, MINB, true>) : go(bwdtrans_hex_lanesem_kernel<T, NQ, EL, MINB, false>);
     if (rc)
         return rc;
-    const unsigned grid = (nelmt + EL - 1) / EL;
-    B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt));
+    if (fuse)
+        *npartials = grid;
     count_launch();
     t_last_backend = "lanes-em";
     return launch_status();

@@ -222,25 +222,26 @@ static bool quad_has_lanesem(unsigned nq)
         return nq % 2 == 0 && nq >= 4 && nq <= 16;
     return nq % 2 == 0 && nq >= 4 && nq <= 16;
 }
-static int quad_lanesem_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
+static int quad_lanesem_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s, double *partials,
+                               unsigned *npartials)
 {
     constexpr bool D = sizeof(T) == 8;
     switch (nq)
     {
     case 4:
-        return launch_quad_lanesem<T, 4, (D ? 32 : 64), (D ? 4 : 8)>(nelmt, in, out, s);
+        return launch_quad_lanesem<T, 4, (D ? 32 : 64), (D ? 4 : 8)>(nelmt, in, out, s, partials, npartials);
     case 6:
-        return launch_quad_lanesem<T, 6, 16, (D ? 2 : 8)>(nelmt, in, out, s);
+        return launch_quad_lanesem<T, 6, 16, (D ? 2 : 8)>(nelmt, in, out, s, partials, npartials);
     case 8:
-        return launch_quad_lanesem<T, 8, 32, (D ? 1 : 4)>(nelmt, in, out, s);
+        return launch_quad_lanesem<T, 8, 32, (D ? 1 : 4)>(nelmt, in, out, s, partials, npartials);
     case 10:
-        return launch_quad_lanesem<T, 10, (D ? 16 : 8), (D ? 1 : 4)>(nelmt, in, out, s);
+        return launch_quad_lanesem<T, 10, (D ? 16 : 8), (D ? 1 : 4)>(nelmt, in, out, s, partials, npartials);
     case 12:
-        return launch_quad_lanesem<T, 12, 16>(nelmt, in, out, s);
+        return launch_quad_lanesem<T, 12, 16>(nelmt, in, out, s, partials, npartials);
     case 14:
-        return launch_quad_lanesem<T, 14, (D ? 4 : 8)>(nelmt, in, out, s);
+        return launch_quad_lanesem<T, 14, (D ? 4 : 8)>(nelmt, in, out, s, partials, npartials);
     case 16:
-        return launch_quad_lanesem<T, 16, (D ? 4 : 8)>(nelmt, in, out, s);
+        return launch_quad_lanesem<T, 16, (D ? 4 : 8)>(nelmt, in, out, s, partials, npartials);
     default:
         break;
     }
@@ -291,8 +292,8 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
                                        : ((have & 1) ? Backend::Rows : Backend::Generic);
         else if (nq0 == 2 && sizeof(T) == 4)
             be = Backend::Nm1; // measured: 0.81 vs 0.63 (pipe) for FP32; FP64 and hex stay on the table's choice
-        else if (quad_has_lanesem(nq0) && aligned16(in) && !partials)
-            be = Backend::Lanes; // the fused operator + checksum stays with the back-end that can fuse (mma)
+        else if (quad_has_lanesem(nq0) && aligned16(in))
+            be = Backend::Lanes;
         else
             be = preferred;
         // the bulk-copy ring needs a 16-byte aligned slab; otherwise take the plain-load twin
@@ -330,7 +331,7 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
     else if (be == Backend::Pipe)
         rc = quad_pipe_switch(nq0, nelmt, in, out, stream);
     else if (be == Backend::Lanes)
-        rc = coa ? quad_lanes_switch(nq0, nelmt, in, out, stream) : quad_lanesem_switch(nq0, nelmt, in, out, stream);
+        rc = coa ? quad_lanes_switch(nq0, nelmt, in, out, stream) : quad_lanesem_switch(nq0, nelmt, in, out, stream, partials, npartials);
     else
         rc = quad_tpe_switch(nq0, nelmt, in, out, stream);
     if (rc)

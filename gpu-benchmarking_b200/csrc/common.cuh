@@ -34,8 +34,10 @@ inline int launch_status()
 }
 
 constexpr int kSmemMax = 227 * 1024; // opt-in dynamic shared memory per CTA on sm_100
-// fused operator + checksum: one partial per resident warp of the persistent grid (148 SMs x 64 warps at most)
-constexpr unsigned kFusedPartialsMax = 16384;
+// fused operator + checksum: one partial per warp of a persistent grid (tensor-core kernels: at most 148 SMs x 64 warps)
+// or one per CTA of the one-tile-per-CTA lanes kernels (nelmt / EL of them: 262 144 at 1 Mi elements, EL = 4); a
+// launch with more partials than this runs the two-pass checksum instead.  b200fe_sumsq_scratch_bytes() = 8 x this.
+constexpr unsigned kFusedPartialsMax = 1u << 19;
 
 // ---- 16-byte vector types ----------------------------------------------------
 template <typename T> struct Vec16;
@@ -67,6 +69,24 @@ __device__ __forceinline__ double fmadd(double a, double b, double c)
 __device__ __forceinline__ float fmadd(float a, float b, float c)
 {
     return __fmaf_rn(a, b, c);
+}
+
+// sum over the CTA in a fixed order (xor-shuffle tree inside each warp, then the warps in ascending order):
+// deterministic, the result is valid in thread 0.  red: >= 32 doubles of shared memory; every thread of the CTA calls.
+__device__ __forceinline__ double cta_sum_fixed(double v, double *red)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+    if ((threadIdx.x & 31) == 0)
+        red[warp] = v;
+    __syncthreads();
+    double total = 0.0;
+    if (threadIdx.x == 0)
+        for (int k = 0; k < nwarps; ++k)
+            total += red[k];
+    return total;
 }
 
 // ---- per-device basis bank in constant memory -------------------------------------
@@ -178,17 +198,13 @@ template <typename T> constexpr int bank_pitch(int n)
     return (n + W - 1) / W * W;
 }
 
-// Programmatic dependent launch: the operator kernel that follows the fill on the stream is launched with
-// cudaLaunchAttributeProgrammaticStreamSerialization, so its CTAs are scheduled and fetch their first tiles
-// while this kernel runs; they call grid_dependency_wait() before their first constant-bank read, which
-// returns once this grid has completed and its writes are visible.  That takes the fill (and one launch
-// gap, ~4 us together: 4-6 % of an FP32 operator at 64 Mi points) off the critical path.  In a kernel that
-// was launched the ordinary way the wait returns immediately.
-__device__ __forceinline__ void grid_dependency_wait()
-{
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-
+// The operator kernel that follows the fill on the stream is an ORDINARY launch.  Launching it as a programmatic
+// dependent of the fill (cudaLaunchAttributeProgrammaticStreamSerialization + griddepcontrol.wait before the first bank
+// read) hid the fill and one launch gap (~3 us per call), but it is not safe with a constant bank: ptxas treats
+// __constant__ data as immutable and hoists the uniform loads of the basis ABOVE griddepcontrol.wait (68 of the
+// library's kernels had LDCU c[0x3][..] before ACQBULK in their SASS), so a CTA that starts while the fill is still
+// writing can multiply by the previous call's basis.  The window is about a microsecond and the symptom was one
+// wrong chunk in several thousand test calls -- found by a flaky parity test, not by inspection.
 // One tiny kernel writes the bank through the symbol's global address (constant caches are invalidated at
 // kernel boundaries, so the next kernel on the stream sees the new values).
 //   plain:       bank[(d*nm + p)*pitch(nq) + i] = B_d[p*nq + i]        (BwdTrans: contraction index p, outputs i)
@@ -197,7 +213,6 @@ template <typename T>
 __global__ void fill_bank_kernel(T *__restrict__ bank, const T *__restrict__ b0, const T *__restrict__ b1,
                                  const T *__restrict__ b2, int nb, int nm, int nq, int transposed)
 {
-    asm volatile("griddepcontrol.launch_dependents;"); // let the dependent operator kernel start its prologue now
     const int rows = transposed ? nq : nm, cols = transposed ? nm : nq, pitch = bank_pitch<T>(cols);
     for (int t = threadIdx.x; t < nb * rows * pitch; t += blockDim.x)
     {

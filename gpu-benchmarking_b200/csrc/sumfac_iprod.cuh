@@ -92,7 +92,6 @@ __global__ void __launch_bounds__(THREADS)
     const int ne    = (nelmt - e0 < (size_t)E) ? (int)(nelmt - e0) : E;
 
     iprod_tile_load<T, NQ, THREADS>(sA, in + e0 * C::NQ2, w ? w + e0 * C::NQ2 : nullptr, ne * C::NQ2, tid);
-    grid_dependency_wait();
     __syncthreads();
     // direction 0: rows (e, j) of nq values -> nm outputs p, to mid[e][p][j]
     contraction_pass<T, NQ, NM, C::B0, RS, THREADS, R, iprod_v<NQ>(), E * NQ, false>(
@@ -141,7 +140,6 @@ __global__ void __launch_bounds__(THREADS)
     const int ne    = (nelmt - e0 < (size_t)E) ? (int)(nelmt - e0) : E;
 
     iprod_tile_load<T, NQ, THREADS>(sA, in + e0 * C::NQ3, w ? w + e0 * C::NQ3 : nullptr, ne * C::NQ3, tid);
-    grid_dependency_wait();
     __syncthreads();
     // direction 0: rows (e, k, j) -> outputs p, to s1[e][p][k][j]
     contraction_pass<T, NQ, NM, C::B0, NQ * RS, THREADS, R, iprod_v<NQ>(), E * NQ2, false>(

@@ -79,7 +79,6 @@ __global__ void __launch_bounds__(QuadIprodLanes<T, NQ, EL>::THREADS)
         T x[NQ];
         const size_t off = ((e0 + (e < ne ? e : 0)) * NQ + j) * NQ; // clamp: a ragged tile computes something harmless
         iprod_fetch<T, NQ, C::VEC16, WEIGHTED>(x, in + off, WEIGHTED ? w + off : nullptr);
-        grid_dependency_wait();
         T *dst = s1 + j * J1 + e * NM;
         lanes_row<T, NQ, NM, C::B0>(x, [&](int p, T v) { dst[p] = v; });
     }
@@ -196,7 +195,6 @@ __global__ void __launch_bounds__(HexIprodLanes<T, NQ, EL, STAGED>::THREADS, MIN
             const size_t off = ((e0 + (e < ne ? e : 0)) * NQ + k) * NQ2;
             iprod_fetch<T, NQ2, true, WEIGHTED>(a, in + off, WEIGHTED ? w + off : nullptr);
         }
-        grid_dependency_wait();
         T *dst = s2 + k * K1 + e * NM2; // u[(q, p)] at dst[q*NM + p]
         if constexpr (C::ROLLED)
         {
@@ -213,8 +211,6 @@ __global__ void __launch_bounds__(HexIprodLanes<T, NQ, EL, STAGED>::THREADS, MIN
         if constexpr (NM % IB0 != 0) // nm is odd: the last output p alone
             plane_block<T, NQ, NM, 1, 1>(a, dst, NM - 1);
     }
-    else
-        grid_dependency_wait();
     __syncthreads();
 
     constexpr int ROWS = EL * NM2, ITER = (ROWS + C::THREADS - 1) / C::THREADS;

@@ -138,12 +138,9 @@ __global__ void __launch_bounds__(QuadLanes<T, NQ, EL>::THREADS)
 #pragma unroll
         for (int p = 0; p < NM; ++p)
             x[p] = ld_stream(px + 32 * p);
-        grid_dependency_wait();
         T *dst = s1 + (size_t)(w * NQ) * EL + e;
         lanes_row<T, NM, NQ, B0>(x, [&](int i, T v) { dst[i * EL] = v; });
     }
-    else
-        grid_dependency_wait();
     __syncthreads();
     {
         T x[NM];
@@ -233,7 +230,6 @@ __global__ void __launch_bounds__(HexLanes<T, NQ, EL>::THREADS, MINB)
 #pragma unroll
         for (int k = 0; k < NM2; ++k)
             a[k] = ld_stream(pa + 32 * k);
-        grid_dependency_wait();
         T *dst = s2 + (size_t)(w * NQ2) * EL + e;
         if constexpr (C::ROLLED)
         {
@@ -250,8 +246,6 @@ __global__ void __launch_bounds__(HexLanes<T, NQ, EL>::THREADS, MINB)
         if constexpr (NQ % IB0 != 0) // odd nq in FP32: the last output alone
             hex_lanes_block<T, NQ, EL, 1>(a, dst, NQ - 1);
     }
-    else
-        grid_dependency_wait();
     __syncthreads();
 
     // direction 2: rows (j, i) of t2 over r, nq outputs each straight to global
@@ -344,7 +338,6 @@ __global__ void __launch_bounds__(HexLanesQ<T, NQ, EL, IH>::THREADS, MINB)
     {
         const T *pa = gin + (size_t)r * (32 * NM2);
         T *dst      = s2 + (size_t)(r * NQ2) * EL + e;
-        grid_dependency_wait();
         if constexpr (IH == 1)
             hex_lanes_plane_q<T, NQ, EL, IH, 0>(pa, dst);
         else if constexpr (IH == 2)
@@ -355,8 +348,6 @@ __global__ void __launch_bounds__(HexLanesQ<T, NQ, EL, IH>::THREADS, MINB)
                 hex_lanes_plane_q<T, NQ, EL, IH, NI>(pa, dst);
         }
     }
-    else
-        grid_dependency_wait();
     __syncthreads();
     constexpr int ITER = (NQ2 + NW - 1) / NW;
 #pragma unroll 1
@@ -402,10 +393,14 @@ template <typename T, int NQ, int EL, int TPC = 1> struct QuadLanesEm
     static_assert(THREADS <= 1024, "block size");
 };
 
-template <typename T, int NQ, int EL, int MINB = 1, int TPC = 1>
+// SUMSQ: operator + checksum fused: every thread squares what it stores, the CTA leaves one partial
+// (fixed summation order) in partials[blockIdx.x]
+template <typename T, int NQ, int EL, int MINB = 1, int TPC = 1, bool SUMSQ = false>
 __global__ void __launch_bounds__(QuadLanesEm<T, NQ, EL, TPC>::THREADS, MINB)
-    bwdtrans_quad_lanesem_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
+    bwdtrans_quad_lanesem_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt,
+                                 double *__restrict__ partials)
 {
+    double ss = 0.0;
     using C = QuadLanesEm<T, NQ, EL, TPC>;
     constexpr int NM = C::NM, NM2 = C::NM2, NQ2 = C::NQ2, E1 = C::E1, Q1 = C::Q1;
     constexpr int BP = bank_pitch<T>(NQ), B0 = 0, B1 = NM * BP;
@@ -431,7 +426,6 @@ __global__ void __launch_bounds__(QuadLanesEm<T, NQ, EL, TPC>::THREADS, MINB)
             if ((size_t)(tile0 + t) * EL < nelmt)
                 ring_issue<T, EL, NM2>(s_in + t * C::SIN, bar + t, in, tile0 + t, nelmt);
     }
-    grid_dependency_wait();
 #pragma unroll
     for (int t = 0; t < TPC; ++t)
     {
@@ -466,9 +460,20 @@ __global__ void __launch_bounds__(QuadLanesEm<T, NQ, EL, TPC>::THREADS, MINB)
             if (e < ne)
             {
                 T *dst = out + (e0 + e) * NQ2 + i;
-                lanes_row<T, NM, NQ, B1>(x, [&](int j, T v) { st_stream(dst + j * NQ, v); });
+                lanes_row<T, NM, NQ, B1>(x, [&](int j, T v) {
+                    st_stream(dst + j * NQ, v);
+                    if (SUMSQ)
+                        ss = fma((double)v, (double)v, ss);
+                });
             }
         }
+    }
+    if constexpr (SUMSQ)
+    {
+        __shared__ double red[32];
+        const double total = cta_sum_fixed(ss, red);
+        if (tid == 0)
+            partials[blockIdx.x] = total;
     }
 }
 
@@ -491,10 +496,12 @@ template <typename T, int NQ, int EL> struct HexLanesEm
     static constexpr bool ROLLED = sizeof(T) == 8 || NQ >= 9; // see HexLanes
 };
 
-template <typename T, int NQ, int EL, int MINB = 1>
+template <typename T, int NQ, int EL, int MINB = 1, bool SUMSQ = false>
 __global__ void __launch_bounds__(HexLanesEm<T, NQ, EL>::THREADS, MINB)
-    bwdtrans_hex_lanesem_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
+    bwdtrans_hex_lanesem_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt,
+                                double *__restrict__ partials)
 {
+    double ss = 0.0;
     using C = HexLanesEm<T, NQ, EL>;
     constexpr int NM = C::NM, NM2 = C::NM2, NM3 = C::NM3, NQ2 = C::NQ2, ES = C::ES, IB0 = C::IB0;
     constexpr int BP = bank_pitch<T>(NQ), B2 = 2 * NM * BP;
@@ -526,7 +533,6 @@ __global__ void __launch_bounds__(HexLanesEm<T, NQ, EL>::THREADS, MINB)
             a[k] = src[k];
     }
     __syncthreads();
-    grid_dependency_wait();
     if (r < NM)
     {
         T *dst = s2 + e * ES + r * NQ2;
@@ -561,8 +567,19 @@ __global__ void __launch_bounds__(HexLanesEm<T, NQ, EL>::THREADS, MINB)
         if (e2 < ne)
         {
             T *dst = out + (e0 + e2) * C::NQ3 + ji;
-            lanes_row<T, NM, NQ, B2>(x, [&](int k, T v) { st_stream(dst + k * NQ2, v); });
+            lanes_row<T, NM, NQ, B2>(x, [&](int k, T v) {
+                st_stream(dst + k * NQ2, v);
+                if (SUMSQ)
+                    ss = fma((double)v, (double)v, ss);
+            });
         }
+    }
+    if constexpr (SUMSQ)
+    {
+        __shared__ double red[32];
+        const double total = cta_sum_fixed(ss, red);
+        if (tid == 0)
+            partials[blockIdx.x] = total;
     }
 }
 

@@ -537,7 +537,6 @@ __global__ void __launch_bounds__(THREADS)
     const int ne    = (nelmt - e0 < (size_t)E) ? (int)(nelmt - e0) : E;
 
     tile_load<T, THREADS, E * C::NM2>(sA, in + e0 * C::NM2, ne * C::NM2, in_vec != 0, tid);
-    grid_dependency_wait(); // the basis bank is filled by the preceding kernel (programmatic dependent launch)
     __syncthreads();
     quad_tile_compute<T, NQ, E, THREADS, R, V>(sA, sB, sA, out + e0 * C::NQ2, ne, out_vec != 0, tid);
 }
@@ -569,7 +568,6 @@ __global__ void __launch_bounds__(THREADS)
             if (t < ntiles)
                 ring_issue<T, E, C::NM2>(slot0 + s * C::SLOT, &bar[s], in, t, nelmt);
         }
-    grid_dependency_wait(); // first tiles are in flight; the basis bank is ready once the fill kernel has completed
 
     unsigned it = 0;
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it)
@@ -696,7 +694,6 @@ __global__ void __launch_bounds__(THREADS)
     const int ne    = (nelmt - e0 < (size_t)E) ? (int)(nelmt - e0) : E;
 
     tile_load<T, THREADS, E * C::NM3>(sA, in + e0 * C::NM3, ne * C::NM3, in_vec != 0, tid);
-    grid_dependency_wait(); // the basis bank is filled by the preceding kernel (programmatic dependent launch)
     __syncthreads();
     hex_dir0<T, NQ, E, THREADS, R, V>(sA, sB, ne, tid);
     __syncthreads();
@@ -731,7 +728,6 @@ __global__ void __launch_bounds__(THREADS)
             if (t < ntiles)
                 ring_issue<T, E, C::NM3>(slot0 + s * C::SLOT, &bar[s], in, t, nelmt);
         }
-    grid_dependency_wait(); // first tiles are in flight; the basis bank is ready once the fill kernel has completed
 
     unsigned it = 0;
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it)

@@ -82,7 +82,6 @@ __global__ void __launch_bounds__(THREADS)
     (void)nelmt; // nelmt % 32 == 0 is checked at the C ABI: every tile is full
 
     coa_gather<T, E, C::NM2, THREADS>(sA, gin, tid);
-    grid_dependency_wait();
     __syncthreads();
     quad_dir0<T, NQ, E, THREADS, R, V>(sA, sB, E, tid);
     __syncthreads();
@@ -116,7 +115,6 @@ __global__ void __launch_bounds__(THREADS)
     (void)nelmt;
 
     coa_gather<T, E, C::NM3, THREADS>(sA, gin, tid);
-    grid_dependency_wait();
     __syncthreads();
     hex_dir0<T, NQ, E, THREADS, R, V>(sA, sB, E, tid);
     __syncthreads();

@@ -251,3 +251,53 @@ def test_lanes_full_size_checksum_of_checksums(G, suf):
         view = d_out.reshape(nelmt // 32, nq ** dim, 32)
         d_want = G.dev(want).reshape(1, -1, 1)
         assert bool((view == d_want).all()), (dim, nq, suf)
+
+
+@pytest.mark.parametrize("case", ["quad-em-f64-8", "quad-em-f32-14", "hex-em-f32-8", "hex-em-f64-6", "quad-coa-f64-12",
+                                  "hex-coa-f32-6", "quad-em-f64-9"])
+def test_back_to_back_calls_with_alternating_bases(G, case):
+    """Every call refills the per-device constant bank and the operator kernel that follows must see the new
+    matrices.  (Regression: the operator used to be launched as a programmatic dependent of the fill; ptxas hoists the
+    uniform loads of the basis above griddepcontrol.wait, so once in a few thousand calls a CTA multiplied by the
+    previous call's basis.)  Small grids, 300 calls, the two bases alternate: a stale read cannot hide."""
+    import torch
+    kind, layout, suf, nq = case.split("-")
+    nq = int(nq)
+    dim = 2 if kind == "quad" else 3
+    dt, nm = G.NP[suf], nq - 1
+    nelmt = 64
+    rng = np.random.default_rng(4000 + nq)
+    bases = [[rnd(rng, nm * nq, dt) for _ in range(dim)] for _ in range(2)]
+    inp_em = rnd(rng, nelmt * nm ** dim, dt)
+    coa = layout == "coa"
+    inp = oracle.to_coa(inp_em, nelmt, nm ** dim) if coa else inp_em
+    want = []
+    for bs in bases:
+        w = (oracle.bwdtrans_quad(nq, nq, nelmt, *bs, inp_em) if dim == 2
+             else oracle.bwdtrans_hex(nq, nq, nq, nelmt, *bs, inp_em))
+        want.append(oracle.to_coa(w, nelmt, nq ** dim) if coa else w)
+    d_b = [[G.dev(x) for x in bs] for bs in bases]
+    d_in = G.dev(inp)
+    reps = 300
+    outs = [torch.empty(nelmt * nq ** dim, dtype=d_in.dtype, device="cuda") for _ in range(reps)]
+    st = torch.cuda.current_stream().cuda_stream
+    name = ("BwdTransQuadKernel" if dim == 2 else "BwdTransHexKernel") + ("_Coa" if coa else "_QP_Shared")
+    # a second stream keeps every SM busy meanwhile, so the one-CTA fill kernel is not the only thing scheduled
+    side = torch.cuda.Stream()
+    noise = torch.ones(64 << 20, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    for r in range(reps):
+        if r % 10 == 0:
+            with torch.cuda.stream(side):
+                noise.mul_(1.0000001)
+        b = d_b[r & 1]
+        if dim == 2:
+            G.fe.bwdtrans_quad(name, suf, nq, nq, nelmt, b[0].data_ptr(), b[1].data_ptr(), d_in.data_ptr(),
+                               outs[r].data_ptr(), stream=st)
+        else:
+            G.fe.bwdtrans_hex(name, suf, nq, nq, nq, nelmt, b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(),
+                              d_in.data_ptr(), outs[r].data_ptr(), stream=st)
+    torch.cuda.synchronize()
+    d_want = [G.dev(w) for w in want]
+    wrong = [r for r in range(reps) if not torch.equal(outs[r], d_want[r & 1])]
+    assert not wrong, (case, G.fe.last_backend(), len(wrong), wrong[:10])
