@@ -51,6 +51,25 @@ inline cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned grid, uns
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// programmatic dependent of the kernel before it on the stream (the bank fill); only for kernels whose body sits
+// behind pdl_wait() + a real call (common.cuh)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
+                              Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = dim3(grid);
+    cfg.blockDim           = dim3(block);
+    cfg.dynamicSmemBytes   = smem;
+    cfg.stream             = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs                                          = attr;
+    cfg.numAttrs                                       = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- quad ---------------------------------------------------------------------
 // resident CTAs per SM of a kernel at its block size / shared memory, cached per device
 template <typename K> inline int ctas_per_sm(K kernel, int threads, size_t smem, int *cache)
@@ -256,7 +275,7 @@ template <typename T, int NQ, int EL> int launch_quad_lanes(unsigned nelmt, cons
     if (rc)
         return rc;
     const unsigned grid = nelmt / EL; // nelmt % 32 == 0
-    B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt));
+    B200FE_CUDA_TRY(launch_pdl(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt));
     count_launch();
     t_last_backend = "lanes";
     return launch_status();
@@ -271,7 +290,7 @@ int launch_hex_lanes(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
     if (rc)
         return rc;
     const unsigned grid = nelmt / EL;
-    B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt));
+    B200FE_CUDA_TRY(launch_pdl(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt));
     count_launch();
     t_last_backend = "lanes";
     return launch_status();
@@ -286,7 +305,7 @@ template <typename T, int NQ, int EL, int IH> int launch_hex_lanesq(unsigned nel
     if (rc)
         return rc;
     const unsigned grid = nelmt / EL;
-    B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt));
+    B200FE_CUDA_TRY(launch_pdl(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt));
     count_launch();
     t_last_backend = "lanes";
     return launch_status();
@@ -305,7 +324,7 @@ int launch_quad_lanesem(unsigned nelmt, const T *in, T *out, cudaStream_t stream
         int rc = opt_in_smem(kernel, C::SMEM);
         if (rc)
             return rc;
-        B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt, fuse ? partials : nullptr));
+        B200FE_CUDA_TRY(launch_pdl(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt, fuse ? partials : nullptr));
         return 0;
     };
     int rc = fuse ? go(bwdtrans_quad_lanesem_kernel<T, NQ, EL, 1, TPC, true>)
@@ -331,7 +350,7 @@ int launch_hex_lanesem(unsigned nelmt, const T *in, T *out, cudaStream_t stream,
         int rc = opt_in_smem(kernel, C::SMEM);
         if (rc)
             return rc;
-        B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt, fuse ? partials : nullptr));
+        B200FE_CUDA_TRY(launch_pdl(kernel, grid, C::THREADS, C::SMEM, stream, in, out, nelmt, fuse ? partials : nullptr));
         return 0;
     };
     int rc = fuse ? go(bwdtrans_hex_lanesem_kernel<T, NQ, EL, MINB, true>) : go(bwdtrans_hex_lanesem_kernel<T, NQ, EL, MINB, false>);

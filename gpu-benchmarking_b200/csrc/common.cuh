@@ -198,13 +198,23 @@ template <typename T> constexpr int bank_pitch(int n)
     return (n + W - 1) / W * W;
 }
 
-// The operator kernel that follows the fill on the stream is an ORDINARY launch.  Launching it as a programmatic
-// dependent of the fill (cudaLaunchAttributeProgrammaticStreamSerialization + griddepcontrol.wait before the first bank
-// read) hid the fill and one launch gap (~3 us per call), but it is not safe with a constant bank: ptxas treats
-// __constant__ data as immutable and hoists the uniform loads of the basis ABOVE griddepcontrol.wait (68 of the
-// library's kernels had LDCU c[0x3][..] before ACQBULK in their SASS), so a CTA that starts while the fill is still
-// writing can multiply by the previous call's basis.  The window is about a microsecond and the symptom was one
-// wrong chunk in several thousand test calls -- found by a flaky parity test, not by inspection.
+// Programmatic dependent launch of the operator behind the bank fill -- the safe form.  The fill kernel triggers its
+// dependents at once, the operator kernel (cudaLaunchAttributeProgrammaticStreamSerialization) becomes resident while
+// the fill runs and executes pdl_wait() as its FIRST instruction, and everything else -- above all every read of the
+// constant bank -- lives in a __noinline__ body function called after it.  The call matters: ptxas treats
+// __constant__ data as immutable and, in an inlined kernel, hoists the uniform loads of the basis ABOVE
+// griddepcontrol.wait (68 of the library's kernels had LDCU c[0x3][..] before ACQBULK in their SASS when the wait sat
+// in the middle of the kernel), so a CTA that started while the fill was still writing multiplied by the previous
+// call's basis -- one wrong chunk in a few thousand calls on an idle GPU, every time with a busy side stream
+// (tests/test_interleaved_gpu.py::test_back_to_back_calls_with_alternating_bases).  Instructions cannot move across a
+// real call, so with this structure no bank read can precede the wait.  Kernels launched the ordinary way return
+// from the wait immediately.  Hides ~2-4 us per call (the fill and one launch gap): 2-5 % of an operator at 64 Mi
+// points.  The row / pipe / tpe / gather kernels keep the ordinary launch.
+__device__ __forceinline__ void pdl_wait()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // One tiny kernel writes the bank through the symbol's global address (constant caches are invalidated at
 // kernel boundaries, so the next kernel on the stream sees the new values).
 //   plain:       bank[(d*nm + p)*pitch(nq) + i] = B_d[p*nq + i]        (BwdTrans: contraction index p, outputs i)
@@ -213,6 +223,7 @@ template <typename T>
 __global__ void fill_bank_kernel(T *__restrict__ bank, const T *__restrict__ b0, const T *__restrict__ b1,
                                  const T *__restrict__ b2, int nb, int nm, int nq, int transposed)
 {
+    asm volatile("griddepcontrol.launch_dependents;"); // dependents that start now park in pdl_wait() until this grid is done
     const int rows = transposed ? nq : nm, cols = transposed ? nm : nq, pitch = bank_pitch<T>(cols);
     for (int t = threadIdx.x; t < nb * rows * pitch; t += blockDim.x)
     {

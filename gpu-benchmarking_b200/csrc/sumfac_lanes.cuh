@@ -115,8 +115,18 @@ template <typename T, int NQ, int EL> struct QuadLanes
 };
 
 template <typename T, int NQ, int EL>
+__device__ __noinline__ void quad_lanes_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt);
+
+template <typename T, int NQ, int EL>
 __global__ void __launch_bounds__(QuadLanes<T, NQ, EL>::THREADS)
     bwdtrans_quad_lanes_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
+{
+    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
+    quad_lanes_body<T, NQ, EL>(in, out, nelmt);
+}
+
+template <typename T, int NQ, int EL>
+__device__ __noinline__ void quad_lanes_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
 {
     using C           = QuadLanes<T, NQ, EL>;
     constexpr int NM  = C::NM;
@@ -205,9 +215,19 @@ template <typename T, int NQ, int EL> struct HexLanes
     static constexpr bool ROLLED = sizeof(T) == 8 || NQ >= 9; // (FP32 nq >= 9: 182-255 registers unrolled)
 };
 
+template <typename T, int NQ, int EL, int MINB>
+__device__ __noinline__ void hex_lanes_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt);
+
 template <typename T, int NQ, int EL, int MINB = 1>
 __global__ void __launch_bounds__(HexLanes<T, NQ, EL>::THREADS, MINB)
     bwdtrans_hex_lanes_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
+{
+    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
+    hex_lanes_body<T, NQ, EL, MINB>(in, out, nelmt);
+}
+
+template <typename T, int NQ, int EL, int MINB>
+__device__ __noinline__ void hex_lanes_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
 {
     using C           = HexLanes<T, NQ, EL>;
     constexpr int NM = C::NM, NM2 = C::NM2, NQ2 = C::NQ2, NW = C::NW, IB0 = C::IB0;
@@ -319,8 +339,18 @@ template <typename T, int NQ, int EL, int IH> struct HexLanesQ
 };
 
 template <typename T, int NQ, int EL, int IH, int MINB>
+__device__ __noinline__ void hex_lanesq_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt);
+
+template <typename T, int NQ, int EL, int IH, int MINB>
 __global__ void __launch_bounds__(HexLanesQ<T, NQ, EL, IH>::THREADS, MINB)
     bwdtrans_hex_lanesq_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
+{
+    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
+    hex_lanesq_body<T, NQ, EL, IH, MINB>(in, out, nelmt);
+}
+
+template <typename T, int NQ, int EL, int IH, int MINB>
+__device__ __noinline__ void hex_lanesq_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
 {
     using C           = HexLanesQ<T, NQ, EL, IH>;
     constexpr int NM = C::NM, NM2 = C::NM2, NQ2 = C::NQ2, NW = C::NW, NI = NQ / IH;
@@ -395,9 +425,21 @@ template <typename T, int NQ, int EL, int TPC = 1> struct QuadLanesEm
 
 // SUMSQ: operator + checksum fused: every thread squares what it stores, the CTA leaves one partial
 // (fixed summation order) in partials[blockIdx.x]
+template <typename T, int NQ, int EL, int MINB, int TPC, bool SUMSQ>
+__device__ __noinline__ void quad_lanesem_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt,
+                                 double *__restrict__ partials);
+
 template <typename T, int NQ, int EL, int MINB = 1, int TPC = 1, bool SUMSQ = false>
 __global__ void __launch_bounds__(QuadLanesEm<T, NQ, EL, TPC>::THREADS, MINB)
     bwdtrans_quad_lanesem_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt,
+                                 double *__restrict__ partials)
+{
+    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
+    quad_lanesem_body<T, NQ, EL, MINB, TPC, SUMSQ>(in, out, nelmt, partials);
+}
+
+template <typename T, int NQ, int EL, int MINB, int TPC, bool SUMSQ>
+__device__ __noinline__ void quad_lanesem_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt,
                                  double *__restrict__ partials)
 {
     double ss = 0.0;
@@ -496,9 +538,21 @@ template <typename T, int NQ, int EL> struct HexLanesEm
     static constexpr bool ROLLED = sizeof(T) == 8 || NQ >= 9; // see HexLanes
 };
 
+template <typename T, int NQ, int EL, int MINB, bool SUMSQ>
+__device__ __noinline__ void hex_lanesem_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt,
+                                double *__restrict__ partials);
+
 template <typename T, int NQ, int EL, int MINB = 1, bool SUMSQ = false>
 __global__ void __launch_bounds__(HexLanesEm<T, NQ, EL>::THREADS, MINB)
     bwdtrans_hex_lanesem_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt,
+                                double *__restrict__ partials)
+{
+    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
+    hex_lanesem_body<T, NQ, EL, MINB, SUMSQ>(in, out, nelmt, partials);
+}
+
+template <typename T, int NQ, int EL, int MINB, bool SUMSQ>
+__device__ __noinline__ void hex_lanesem_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt,
                                 double *__restrict__ partials)
 {
     double ss = 0.0;
