@@ -35,22 +35,6 @@ template <typename K> inline int opt_in_smem(K kernel, size_t bytes)
     return 0;
 }
 
-// plain stream-ordered launch with the arguments converted to the kernel's parameter types (the name is historical:
-// the operator used to be a programmatic dependent of the constant-bank fill; see common.cuh for why it no longer is)
-template <typename... KArgs, typename... Args>
-inline cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem,
-                                    cudaStream_t stream, Args... args)
-{
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim            = dim3(grid);
-    cfg.blockDim           = dim3(block);
-    cfg.dynamicSmemBytes   = smem;
-    cfg.stream             = stream;
-    cfg.attrs              = nullptr;
-    cfg.numAttrs           = 0;
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
-}
-
 // programmatic dependent of the kernel before it on the stream (the bank fill); only for kernels whose body sits
 // behind pdl_wait() + a real call (common.cuh)
 template <typename... KArgs, typename... Args>
@@ -117,7 +101,7 @@ int launch_quad_rows(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
     const unsigned grid = (nelmt + E - 1) / E;
     const int in_vec    = C::IN_VEC_OK && aligned16(in);
     const int out_vec   = C::OUT_VEC_OK && aligned16(out);
-    B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt, in_vec, out_vec));
+    B200FE_CUDA_TRY(launch_pdl(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt, in_vec, out_vec));
     count_launch();
     t_last_backend = "rows";
     return launch_status();
@@ -139,7 +123,7 @@ int launch_quad_pipe(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
     const unsigned fit    = (unsigned)(sm_count() * ctas_per_sm(kernel, THREADS, C::SMEM, occ));
     const unsigned grid   = ntiles < fit ? ntiles : fit;
     const int out_vec     = C::OUT_VEC_OK && aligned16(out);
-    B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt, ntiles, out_vec));
+    B200FE_CUDA_TRY(launch_pdl(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt, ntiles, out_vec));
     count_launch();
     t_last_backend = "pipe";
     return launch_status();
@@ -243,7 +227,7 @@ int launch_quad_rowscoa(unsigned nelmt, const T *in, T *out, cudaStream_t stream
     if (rc)
         return rc;
     const unsigned grid = nelmt / E; // nelmt % 32 == 0
-    B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt));
+    B200FE_CUDA_TRY(launch_pdl(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt));
     count_launch();
     t_last_backend = "rows-coa";
     return launch_status();
@@ -259,7 +243,7 @@ int launch_hex_rowscoa(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
     if (rc)
         return rc;
     const unsigned grid = nelmt / E;
-    B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt));
+    B200FE_CUDA_TRY(launch_pdl(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt));
     count_launch();
     t_last_backend = "rows-coa";
     return launch_status();
@@ -394,7 +378,7 @@ int launch_quad_iprod(unsigned nelmt, const T *in, const T *w, T *out, cudaStrea
     if (rc)
         return rc;
     const unsigned grid = (nelmt + E - 1) / E;
-    B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, w, out, nelmt));
+    B200FE_CUDA_TRY(launch_pdl(kernel, grid, THREADS, C::SMEM, stream, in, w, out, nelmt));
     count_launch();
     t_last_backend = "iprod-rows";
     return launch_status();
@@ -411,7 +395,7 @@ int launch_hex_iprod(unsigned nelmt, const T *in, const T *w, T *out, cudaStream
     if (rc)
         return rc;
     const unsigned grid = (nelmt + E - 1) / E;
-    B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, w, out, nelmt));
+    B200FE_CUDA_TRY(launch_pdl(kernel, grid, THREADS, C::SMEM, stream, in, w, out, nelmt));
     count_launch();
     t_last_backend = "iprod-rows";
     return launch_status();
@@ -427,7 +411,7 @@ template <typename T, int NQ, int EL> int launch_quad_iprod_lanes(unsigned nelmt
         int rc = opt_in_smem(kernel, C::SMEM);
         if (rc)
             return rc;
-        B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, w, out, nelmt));
+        B200FE_CUDA_TRY(launch_pdl(kernel, grid, C::THREADS, C::SMEM, stream, in, w, out, nelmt));
         return 0;
     };
     int rc = w ? go(iproduct_quad_lanes_kernel<T, NQ, EL, true>) : go(iproduct_quad_lanes_kernel<T, NQ, EL, false>);
@@ -447,7 +431,7 @@ int launch_hex_iprod_lanes(unsigned nelmt, const T *in, const T *w, T *out, cuda
         int rc = opt_in_smem(kernel, C::SMEM);
         if (rc)
             return rc;
-        B200FE_CUDA_TRY(launch_dependent(kernel, grid, C::THREADS, C::SMEM, stream, in, w, out, nelmt));
+        B200FE_CUDA_TRY(launch_pdl(kernel, grid, C::THREADS, C::SMEM, stream, in, w, out, nelmt));
         return 0;
     };
     int rc = w ? go(iproduct_hex_lanes_kernel<T, NQ, EL, true, MINB, STAGED>)
@@ -542,7 +526,7 @@ int launch_hex_rows(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
         return rc;
     const unsigned grid = (nelmt + E - 1) / E;
     const int in_vec    = C::IN_VEC_OK && aligned16(in);
-    B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt, in_vec));
+    B200FE_CUDA_TRY(launch_pdl(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt, in_vec));
     count_launch();
     t_last_backend = "rows";
     return launch_status();
@@ -562,7 +546,7 @@ int launch_hex_pipe(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
     const unsigned ntiles = (nelmt + E - 1) / E;
     const unsigned fit    = (unsigned)(sm_count() * ctas_per_sm(kernel, THREADS, C::SMEM, occ));
     const unsigned grid   = ntiles < fit ? ntiles : fit;
-    B200FE_CUDA_TRY(launch_dependent(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt, ntiles));
+    B200FE_CUDA_TRY(launch_pdl(kernel, grid, THREADS, C::SMEM, stream, in, out, nelmt, ntiles));
     count_launch();
     t_last_backend = "pipe";
     return launch_status();

@@ -209,7 +209,7 @@ template <typename T> constexpr int bank_pitch(int n)
 // (tests/test_interleaved_gpu.py::test_back_to_back_calls_with_alternating_bases).  Instructions cannot move across a
 // real call, so with this structure no bank read can precede the wait.  Kernels launched the ordinary way return
 // from the wait immediately.  Hides ~2-4 us per call (the fill and one launch gap): 2-5 % of an operator at 64 Mi
-// points.  The row / pipe / tpe / gather kernels keep the ordinary launch.
+// points.
 __device__ __forceinline__ void pdl_wait()
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");

@@ -64,8 +64,18 @@ template <typename T, int NQ, int EL> struct QuadIprodLanes
 };
 
 template <typename T, int NQ, int EL, bool WEIGHTED>
+__device__ __noinline__ void iproduct_quad_lanes_body(const T *__restrict__ in, const T *__restrict__ w, T *__restrict__ out, unsigned nelmt);
+
+template <typename T, int NQ, int EL, bool WEIGHTED>
 __global__ void __launch_bounds__(QuadIprodLanes<T, NQ, EL>::THREADS)
     iproduct_quad_lanes_kernel(const T *__restrict__ in, const T *__restrict__ w, T *__restrict__ out, unsigned nelmt)
+{
+    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
+    iproduct_quad_lanes_body<T, NQ, EL, WEIGHTED>(in, w, out, nelmt);
+}
+
+template <typename T, int NQ, int EL, bool WEIGHTED>
+__device__ __noinline__ void iproduct_quad_lanes_body(const T *__restrict__ in, const T *__restrict__ w, T *__restrict__ out, unsigned nelmt)
 {
     using C = QuadIprodLanes<T, NQ, EL>;
     constexpr int NM = C::NM, J1 = C::J1;
@@ -120,9 +130,19 @@ template <typename T, int NQ, int EL, bool STAGED = false> struct HexIprodLanes
     static constexpr bool ROLLED = sizeof(T) == 8 || NQ >= 9; // see HexLanes
 };
 
+template <typename T, int NQ, int EL, bool WEIGHTED, int MINB, bool STAGED>
+__device__ __noinline__ void iproduct_hex_lanes_body(const T *__restrict__ in, const T *__restrict__ w, T *__restrict__ out, unsigned nelmt);
+
 template <typename T, int NQ, int EL, bool WEIGHTED, int MINB = 1, bool STAGED = false>
 __global__ void __launch_bounds__(HexIprodLanes<T, NQ, EL, STAGED>::THREADS, MINB)
     iproduct_hex_lanes_kernel(const T *__restrict__ in, const T *__restrict__ w, T *__restrict__ out, unsigned nelmt)
+{
+    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
+    iproduct_hex_lanes_body<T, NQ, EL, WEIGHTED, MINB, STAGED>(in, w, out, nelmt);
+}
+
+template <typename T, int NQ, int EL, bool WEIGHTED, int MINB, bool STAGED>
+__device__ __noinline__ void iproduct_hex_lanes_body(const T *__restrict__ in, const T *__restrict__ w, T *__restrict__ out, unsigned nelmt)
 {
     using C = HexIprodLanes<T, NQ, EL, STAGED>;
     constexpr int NM = C::NM, NQ2 = C::NQ2, NM2 = C::NM2, K1 = C::K1, IB0 = C::IB0;

@@ -524,8 +524,18 @@ __device__ __forceinline__ void quad_tile_compute(const T *__restrict__ s_in, T 
 }
 
 template <typename T, int NQ, int E, int THREADS, int R, int V>
+__device__ __noinline__ void bwdtrans_quad_rows_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt, int in_vec, int out_vec);
+
+template <typename T, int NQ, int E, int THREADS, int R, int V>
 __global__ void __launch_bounds__(THREADS)
     bwdtrans_quad_rows_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt, int in_vec, int out_vec)
+{
+    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
+    bwdtrans_quad_rows_body<T, NQ, E, THREADS, R, V>(in, out, nelmt, in_vec, out_vec);
+}
+
+template <typename T, int NQ, int E, int THREADS, int R, int V>
+__device__ __noinline__ void bwdtrans_quad_rows_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt, int in_vec, int out_vec)
 {
     using C = QuadRows<T, NQ, E, THREADS, R, V>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -542,8 +552,20 @@ __global__ void __launch_bounds__(THREADS)
 }
 
 template <typename T, int NQ, int E, int THREADS, int R, int V>
+__device__ __noinline__ void bwdtrans_quad_pipe_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt, unsigned ntiles,
+                              int out_vec);
+
+template <typename T, int NQ, int E, int THREADS, int R, int V>
 __global__ void __launch_bounds__(THREADS)
     bwdtrans_quad_pipe_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt, unsigned ntiles,
+                              int out_vec)
+{
+    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
+    bwdtrans_quad_pipe_body<T, NQ, E, THREADS, R, V>(in, out, nelmt, ntiles, out_vec);
+}
+
+template <typename T, int NQ, int E, int THREADS, int R, int V>
+__device__ __noinline__ void bwdtrans_quad_pipe_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt, unsigned ntiles,
                               int out_vec)
 {
     using C = QuadPipe<T, NQ, E, THREADS, R, V>;
@@ -681,8 +703,18 @@ __device__ __forceinline__ void hex_dir2(const T *__restrict__ s2, T *__restrict
 }
 
 template <typename T, int NQ, int E, int THREADS, int R, int V>
+__device__ __noinline__ void bwdtrans_hex_rows_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt, int in_vec);
+
+template <typename T, int NQ, int E, int THREADS, int R, int V>
 __global__ void __launch_bounds__(THREADS)
     bwdtrans_hex_rows_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt, int in_vec)
+{
+    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
+    bwdtrans_hex_rows_body<T, NQ, E, THREADS, R, V>(in, out, nelmt, in_vec);
+}
+
+template <typename T, int NQ, int E, int THREADS, int R, int V>
+__device__ __noinline__ void bwdtrans_hex_rows_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt, int in_vec)
 {
     using C = HexRows<T, NQ, E, THREADS, R, V>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -703,8 +735,18 @@ __global__ void __launch_bounds__(THREADS)
 }
 
 template <typename T, int NQ, int E, int THREADS, int R, int V>
+__device__ __noinline__ void bwdtrans_hex_pipe_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt, unsigned ntiles);
+
+template <typename T, int NQ, int E, int THREADS, int R, int V>
 __global__ void __launch_bounds__(THREADS)
     bwdtrans_hex_pipe_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt, unsigned ntiles)
+{
+    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
+    bwdtrans_hex_pipe_body<T, NQ, E, THREADS, R, V>(in, out, nelmt, ntiles);
+}
+
+template <typename T, int NQ, int E, int THREADS, int R, int V>
+__device__ __noinline__ void bwdtrans_hex_pipe_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt, unsigned ntiles)
 {
     using C = HexPipe<T, NQ, E, THREADS, R, V>;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -66,8 +66,18 @@ __device__ __forceinline__ void coa_gather(T *__restrict__ s, const T *__restric
 
 // quad: the element-major rows kernel with the gather in front and a scatter of the staged tile behind
 template <typename T, int NQ, int E, int THREADS, int R, int V>
+__device__ __noinline__ void bwdtrans_quad_rowscoa_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt);
+
+template <typename T, int NQ, int E, int THREADS, int R, int V>
 __global__ void __launch_bounds__(THREADS)
     bwdtrans_quad_rowscoa_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
+{
+    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
+    bwdtrans_quad_rowscoa_body<T, NQ, E, THREADS, R, V>(in, out, nelmt);
+}
+
+template <typename T, int NQ, int E, int THREADS, int R, int V>
+__device__ __noinline__ void bwdtrans_quad_rowscoa_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
 {
     using C = QuadRows<T, NQ, E, THREADS, R, V>;
     static_assert(32 % E == 0, "a tile must not straddle interleave groups");
@@ -98,8 +108,18 @@ __global__ void __launch_bounds__(THREADS)
 // hex: directions 0 and 1 as in the element-major kernel; direction 2 with the rows re-indexed so that
 // consecutive lanes hold consecutive elements of the same (j, i), and stored interleaved
 template <typename T, int NQ, int E, int THREADS, int R, int V>
+__device__ __noinline__ void bwdtrans_hex_rowscoa_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt);
+
+template <typename T, int NQ, int E, int THREADS, int R, int V>
 __global__ void __launch_bounds__(THREADS)
     bwdtrans_hex_rowscoa_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
+{
+    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
+    bwdtrans_hex_rowscoa_body<T, NQ, E, THREADS, R, V>(in, out, nelmt);
+}
+
+template <typename T, int NQ, int E, int THREADS, int R, int V>
+__device__ __noinline__ void bwdtrans_hex_rowscoa_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
 {
     using C = HexRows<T, NQ, E, THREADS, R, V>;
     static_assert(32 % E == 0, "a tile must not straddle interleave groups");

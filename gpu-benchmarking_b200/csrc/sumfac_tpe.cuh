@@ -20,8 +20,18 @@ namespace b200fe
 {
 
 template <typename T, int NQ, int THREADS>
+__device__ __noinline__ void bwdtrans_quad_tpe_coa_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt);
+
+template <typename T, int NQ, int THREADS>
 __global__ void __launch_bounds__(THREADS)
     bwdtrans_quad_tpe_coa_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
+{
+    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
+    bwdtrans_quad_tpe_coa_body<T, NQ, THREADS>(in, out, nelmt);
+}
+
+template <typename T, int NQ, int THREADS>
+__device__ __noinline__ void bwdtrans_quad_tpe_coa_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
 {
     constexpr int NM = NQ - 1, NM2 = NM * NM, NQ2 = NQ * NQ;
     constexpr int BP = bank_pitch<T>(NQ), B0 = 0, B1 = NM * BP; // pitched bank rows (common.cuh)
@@ -63,8 +73,18 @@ __global__ void __launch_bounds__(THREADS)
 }
 
 template <typename T, int NQ, int THREADS>
+__device__ __noinline__ void bwdtrans_hex_tpe_coa_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt);
+
+template <typename T, int NQ, int THREADS>
 __global__ void __launch_bounds__(THREADS)
     bwdtrans_hex_tpe_coa_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
+{
+    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
+    bwdtrans_hex_tpe_coa_body<T, NQ, THREADS>(in, out, nelmt);
+}
+
+template <typename T, int NQ, int THREADS>
+__device__ __noinline__ void bwdtrans_hex_tpe_coa_body(const T *__restrict__ in, T *__restrict__ out, unsigned nelmt)
 {
     constexpr int NM = NQ - 1, NM2 = NM * NM, NM3 = NM2 * NM, NQ2 = NQ * NQ, NQ3 = NQ2 * NQ;
     constexpr int BP = bank_pitch<T>(NQ), B0 = 0, B1 = NM * BP, B2 = 2 * NM * BP;

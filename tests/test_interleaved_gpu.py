@@ -254,7 +254,8 @@ def test_lanes_full_size_checksum_of_checksums(G, suf):
 
 
 @pytest.mark.parametrize("case", ["quad-em-f64-8", "quad-em-f32-14", "hex-em-f32-8", "hex-em-f64-6", "quad-coa-f64-12",
-                                  "hex-coa-f32-6", "quad-em-f64-9"])
+                                  "hex-coa-f32-6", "quad-em-f64-9", "hex-em-f64-10", "quad-em-f32-2", "hex-em-f64-2",
+                                  "quad-coa-f32-4", "hex-coa-f64-3", "quad-coa-f64-20", "hex-coa-f64-10"])
 def test_back_to_back_calls_with_alternating_bases(G, case):
     """Every call refills the per-device constant bank and the operator kernel that follows must see the new
     matrices.  (Regression: the operator used to be launched as a programmatic dependent of the fill; ptxas hoists the
