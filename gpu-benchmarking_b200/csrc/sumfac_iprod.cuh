@@ -79,18 +79,8 @@ template <typename T, int NQ, int E> struct QuadIprodShape
 };
 
 template <typename T, int NQ, int E, int THREADS, int R>
-__device__ __noinline__ void iproduct_quad_rows_body(const T *__restrict__ in, const T *__restrict__ w, T *__restrict__ out, unsigned nelmt);
-
-template <typename T, int NQ, int E, int THREADS, int R>
 __global__ void __launch_bounds__(THREADS)
     iproduct_quad_rows_kernel(const T *__restrict__ in, const T *__restrict__ w, T *__restrict__ out, unsigned nelmt)
-{
-    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
-    iproduct_quad_rows_body<T, NQ, E, THREADS, R>(in, w, out, nelmt);
-}
-
-template <typename T, int NQ, int E, int THREADS, int R>
-__device__ __noinline__ void iproduct_quad_rows_body(const T *__restrict__ in, const T *__restrict__ w, T *__restrict__ out, unsigned nelmt)
 {
     using C = QuadIprodShape<T, NQ, E>;
     constexpr int NM = C::NM, RS = C::RS;
@@ -137,18 +127,8 @@ template <typename T, int NQ, int E> struct HexIprodShape
 };
 
 template <typename T, int NQ, int E, int THREADS, int R>
-__device__ __noinline__ void iproduct_hex_rows_body(const T *__restrict__ in, const T *__restrict__ w, T *__restrict__ out, unsigned nelmt);
-
-template <typename T, int NQ, int E, int THREADS, int R>
 __global__ void __launch_bounds__(THREADS)
     iproduct_hex_rows_kernel(const T *__restrict__ in, const T *__restrict__ w, T *__restrict__ out, unsigned nelmt)
-{
-    pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
-    iproduct_hex_rows_body<T, NQ, E, THREADS, R>(in, w, out, nelmt);
-}
-
-template <typename T, int NQ, int E, int THREADS, int R>
-__device__ __noinline__ void iproduct_hex_rows_body(const T *__restrict__ in, const T *__restrict__ w, T *__restrict__ out, unsigned nelmt)
 {
     using C = HexIprodShape<T, NQ, E>;
     constexpr int NM = C::NM, RS = C::RS, NQ2 = C::NQ2, NM2 = C::NM2;
