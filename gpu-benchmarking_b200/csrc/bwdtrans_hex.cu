@@ -209,7 +209,7 @@ static int hex_lanes_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cu
 //   EL        16    16                EL  64    16    16
 //   lanes-em 0.97  0.98                   0.91  0.91  0.90
 //   before   0.94  0.93                   0.82  0.84  0.84
-//   FP32 nq = 10, EL = 16, 3 CTAs per SM: 0.76 against 0.70
+//   FP32 nq = 10, EL = 12 (any multiple of 4 keeps the slab 16-byte aligned), 4 CTAs per SM: 0.80 against 0.70
 // (FP64 nq = 8: 0.79 against 0.92 for the tensor-core kernel; FP64 nq = 10 does not fit the register file: 0.38)
 static bool hex_has_lanesem(unsigned nq)
 {
@@ -231,7 +231,7 @@ static int hex_lanesem_switch(unsigned nq, unsigned nelmt, const T *in, T *out, 
         break;
     case 10:
         if constexpr (!D)
-            return launch_hex_lanesem<T, 10, 16, 3>(nelmt, in, out, s, partials, npartials);
+            return launch_hex_lanesem<T, 10, 12, 4>(nelmt, in, out, s, partials, npartials);
         break;
     default:
         break;

@@ -111,7 +111,8 @@ template <typename T> struct Case
         cudaFree(ref);
         cudaFree(bad);
     }
-    template <typename K> void run(const char *name, K kernel, unsigned grid, int threads, size_t smem)
+    template <typename K, typename... A>
+    void run(const char *name, K kernel, unsigned grid, int threads, size_t smem, A... extra)
     {
         if (smem > 227 * 1024)
         {
@@ -124,7 +125,7 @@ template <typename T> struct Case
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
         CK(cudaMemset(out, 0xff, sizeof(T) * nout));
         CK(cudaMemset(bad, 0, 8));
-        kernel<<<grid, threads, smem>>>(in, out, nelmt);
+        kernel<<<grid, threads, smem>>>(in, out, nelmt, extra...);
         CK(cudaGetLastError());
         diff_kernel<T><<<1024, 256>>>(out, ref, nout, bad);
         unsigned long long nbad = 0;
@@ -137,7 +138,7 @@ template <typename T> struct Case
         for (int r = 0; r < reps; ++r)
         {
             cudaEventRecord(e0);
-            kernel<<<grid, threads, smem>>>(in, out, nelmt);
+            kernel<<<grid, threads, smem>>>(in, out, nelmt, extra...);
             cudaEventRecord(e1);
             CK(cudaEventSynchronize(e1));
             float ms;
@@ -155,35 +156,27 @@ template <typename T> struct Case
 
 #define QE(T, NQ, EL, MB)                                                                                    \
     c.run("EL=" #EL "/MINB=" #MB, bwdtrans_quad_lanesem_kernel<T, NQ, EL, MB>, (c.nelmt + EL - 1) / EL,       \
-          QuadLanesEm<T, NQ, EL>::THREADS, QuadLanesEm<T, NQ, EL>::SMEM);
+          QuadLanesEm<T, NQ, EL>::THREADS, QuadLanesEm<T, NQ, EL>::SMEM, (double *)nullptr);
 
 #define HE(T, NQ, EL, MB)                                                                                    \
     c.run("EL=" #EL "/MINB=" #MB, bwdtrans_hex_lanesem_kernel<T, NQ, EL, MB>, (c.nelmt + EL - 1) / EL,        \
-          HexLanesEm<T, NQ, EL>::THREADS, HexLanesEm<T, NQ, EL>::SMEM);
+          HexLanesEm<T, NQ, EL>::THREADS, HexLanesEm<T, NQ, EL>::SMEM, (double *)nullptr);
 
 #define QT(T, NQ, EL, TPC)                                                                                   \
     c.run("EL=" #EL "/TPC=" #TPC, bwdtrans_quad_lanesem_kernel<T, NQ, EL, 1, TPC>,                            \
           ((c.nelmt + EL - 1) / EL + TPC - 1) / TPC, QuadLanesEm<T, NQ, EL, TPC>::THREADS,                    \
-          QuadLanesEm<T, NQ, EL, TPC>::SMEM);
+          QuadLanesEm<T, NQ, EL, TPC>::SMEM, (double *)nullptr);
 int main()
 {
     printf("op,nq,dtype,shape,threads,smem,ctas_per_sm,ms_best,ms_avg,gb_s,hbm_frac,mismatches\n");
     {
         Case<float> c;
-        c.setup(4); QT(float, 4, 32, 1) QT(float, 4, 32, 4) QT(float, 4, 32, 8) QT(float, 4, 64, 4) QT(float, 4, 64, 8) c.teardown();
-        c.setup(6); QT(float, 6, 32, 2) QT(float, 6, 32, 4) QT(float, 6, 32, 8) QT(float, 6, 16, 4) QT(float, 6, 16, 8) c.teardown();
-        c.setup(8); QT(float, 8, 32, 2) QT(float, 8, 32, 4) QT(float, 8, 16, 4) QT(float, 8, 16, 8) QT(float, 8, 8, 8) c.teardown();
-        c.setup(10); QT(float, 10, 16, 2) QT(float, 10, 16, 4) QT(float, 10, 8, 4) QT(float, 10, 8, 8) QT(float, 10, 32, 2) c.teardown();
-        c.setup(12); QT(float, 12, 16, 2) QT(float, 12, 16, 4) QT(float, 12, 8, 4) c.teardown();
-        c.setup(14); QT(float, 14, 8, 2) QT(float, 14, 8, 4) c.teardown();
-        c.setup(16); QT(float, 16, 8, 2) QT(float, 16, 8, 4) c.teardown();
+        c.setup(10, 3); HE(float, 10, 16, 3) HE(float, 10, 12, 1) HE(float, 10, 12, 4) HE(float, 10, 12, 5) HE(float, 10, 20, 2) HE(float, 10, 20, 3) HE(float, 10, 8, 5) HE(float, 10, 24, 2) c.teardown();
+        c.setup(8, 3); HE(float, 8, 16, 1) HE(float, 8, 12, 1) HE(float, 8, 20, 1) HE(float, 8, 24, 1) c.teardown();
     }
     {
         Case<double> c;
-        c.setup(4); QT(double, 4, 32, 4) QT(double, 4, 32, 8) QT(double, 4, 16, 8) c.teardown();
-        c.setup(6); QT(double, 6, 16, 2) QT(double, 6, 16, 4) QT(double, 6, 32, 4) c.teardown();
-        c.setup(8); QT(double, 8, 32, 2) QT(double, 8, 16, 4) c.teardown();
-        c.setup(16); QT(double, 16, 4, 2) QT(double, 16, 4, 4) c.teardown();
+        c.setup(8, 3); HE(double, 8, 16, 1) HE(double, 8, 12, 1) HE(double, 8, 4, 1) c.teardown();
     }
     return 0;
 }
