@@ -168,8 +168,13 @@ int main()
     printf("op,nq,dtype,_,threads,smem,ctas_per_sm,ms_best,ms_avg,gb_s,mismatches\n");
     {
         Case<float> c;
-        c.setup(3, 9); HP(float, 9, 16, 1) HP(float, 9, 16, 3) HP(float, 9, 16, 4) HP(float, 9, 32, 1) c.teardown();
-        c.setup(3, 10); HP(float, 10, 16, 1) HP(float, 10, 16, 2) HP(float, 10, 16, 3) HP(float, 10, 32, 1) c.teardown();
+        c.setup(3, 10); HP(float, 10, 16, 3) HP(float, 10, 8, 1) HP(float, 10, 8, 4) HP(float, 10, 8, 5) HP(float, 10, 8, 6) c.teardown();
+        c.setup(3, 8); HP(float, 8, 16, 5) HP(float, 8, 8, 1) HP(float, 8, 8, 8) c.teardown();
+        c.setup(3, 9); HP(float, 9, 32, 1) HP(float, 9, 8, 5) HP(float, 9, 16, 4) c.teardown();
+    }
+    {
+        Case<double> c;
+        c.setup(3, 8); HP(double, 8, 16, 1) HP(double, 8, 8, 1) HP(double, 8, 8, 4) c.teardown();
     }
     return 0;
 }

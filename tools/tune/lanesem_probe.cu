@@ -171,12 +171,11 @@ int main()
     printf("op,nq,dtype,shape,threads,smem,ctas_per_sm,ms_best,ms_avg,gb_s,hbm_frac,mismatches\n");
     {
         Case<float> c;
-        c.setup(10, 3); HE(float, 10, 16, 3) HE(float, 10, 12, 1) HE(float, 10, 12, 4) HE(float, 10, 12, 5) HE(float, 10, 20, 2) HE(float, 10, 20, 3) HE(float, 10, 8, 5) HE(float, 10, 24, 2) c.teardown();
-        c.setup(8, 3); HE(float, 8, 16, 1) HE(float, 8, 12, 1) HE(float, 8, 20, 1) HE(float, 8, 24, 1) c.teardown();
-    }
-    {
-        Case<double> c;
-        c.setup(8, 3); HE(double, 8, 16, 1) HE(double, 8, 12, 1) HE(double, 8, 4, 1) c.teardown();
+        c.setup(6); QT(float, 6, 16, 8) QT(float, 6, 12, 8) QT(float, 6, 24, 4) QT(float, 6, 20, 8) c.teardown();
+        c.setup(10); QT(float, 10, 8, 4) QT(float, 10, 12, 4) QT(float, 10, 12, 2) QT(float, 10, 20, 2) c.teardown();
+        c.setup(14); QT(float, 14, 8, 1) QT(float, 14, 12, 1) QT(float, 14, 4, 1) QT(float, 14, 12, 2) c.teardown();
+        c.setup(16); QT(float, 16, 8, 1) QT(float, 16, 12, 1) QT(float, 16, 4, 1) c.teardown();
+        c.setup(12); QT(float, 12, 16, 1) QT(float, 12, 12, 1) QT(float, 12, 20, 1) c.teardown();
     }
     return 0;
 }
