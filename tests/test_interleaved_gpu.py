@@ -302,3 +302,70 @@ def test_back_to_back_calls_with_alternating_bases(G, case):
     d_want = [G.dev(w) for w in want]
     wrong = [r for r in range(reps) if not torch.equal(outs[r], d_want[r & 1])]
     assert not wrong, (case, G.fe.last_backend(), len(wrong), wrong[:10])
+
+
+@pytest.mark.parametrize("dim,suf,nq", [(2, "f64", 16), (2, "f32", 14), (3, "f64", 6), (3, "f32", 8), (3, "f32", 10)])
+def test_element_major_lanes_kernels_at_baseline_size(G, dim, suf, nq):
+    """BASELINE.json's 64 Mi quadrature points through size-independent properties: identical elements give identical
+    outputs (element 0 is checked against the oracle), the operator is exactly homogeneous under a power-of-two
+    scale, and the fused checksum equals the checksum of what was stored."""
+    import torch
+    dt, nm = G.NP[suf], nq - 1
+    nelmt = (64 << 20) // nq ** dim - 7            # not a multiple of any tile size
+    rng = np.random.default_rng(5000 + nq)
+    b = [rnd(rng, nm * nq, dt) for _ in range(dim)]
+    one = rnd(rng, nm ** dim, dt)
+    want = (oracle.bwdtrans_quad(nq, nq, 1, b[0], b[1], one) if dim == 2 else oracle.bwdtrans_hex(nq, nq, nq, 1, *b, one))
+    d_b = [G.dev(x) for x in b]
+    d_in = G.dev(one).repeat(nelmt)
+    d_out = torch.empty(nelmt * nq ** dim, dtype=d_in.dtype, device="cuda")
+    d_ss = torch.zeros(1, dtype=torch.float64, device="cuda")
+    scratch = torch.empty(G.fe.sumsq_scratch_bytes(), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    G.fe.bwdtrans_sumsq(suf, (nq,) * dim, nelmt, [x.data_ptr() for x in d_b], d_in.data_ptr(), d_out.data_ptr(),
+                        d_ss.data_ptr(), scratch.data_ptr(), st)
+    assert G.fe.last_backend() == "lanes-em"
+    torch.cuda.synchronize()
+    view = d_out.reshape(nelmt, nq ** dim)
+    assert bool((view == G.dev(want).reshape(1, -1)).all())
+    ss_want = float((view[0].double() ** 2).sum()) * nelmt
+    assert abs(float(d_ss.item()) - ss_want) <= 1e-10 * ss_want
+    # homogeneity: scaling the modes by 4 scales every output by exactly 4 (no rounding in a power-of-two scale)
+    d_in.mul_(4)
+    d_out4 = torch.empty_like(d_out)
+    if dim == 2:
+        G.fe.bwdtrans_quad("BwdTransQuadKernel", suf, nq, nq, nelmt, d_b[0].data_ptr(), d_b[1].data_ptr(),
+                           d_in.data_ptr(), d_out4.data_ptr(), stream=st)
+    else:
+        G.fe.bwdtrans_hex("BwdTransHexKernel", suf, nq, nq, nq, nelmt, d_b[0].data_ptr(), d_b[1].data_ptr(),
+                          d_b[2].data_ptr(), d_in.data_ptr(), d_out4.data_ptr(), stream=st)
+    assert G.fe.last_backend() == "lanes-em"
+    assert bool(torch.equal(d_out4, d_out * 4))
+
+
+@pytest.mark.parametrize("layout,dim,suf,nq", [("em", 2, "f64", 12), ("em", 3, "f32", 8), ("coa", 2, "f32", 16),
+                                               ("coa", 3, "f64", 8)])
+def test_lanes_kernels_keep_non_finite_values_inside_their_element(G, layout, dim, suf, nq):
+    """one poisoned element (Inf modes) must not leak into its neighbours: every lane / tile slot is private"""
+    dt, nm = G.NP[suf], nq - 1
+    nelmt = 96
+    rng = np.random.default_rng(5100 + nq)
+    b = [rnd(rng, nm * nq, dt) for _ in range(dim)]
+    inp = rnd(rng, nelmt * nm ** dim, dt).reshape(nelmt, -1)
+    bad = 37
+    inp[bad] = np.inf
+    inp = inp.reshape(-1)
+    want = (oracle.bwdtrans_quad(nq, nq, nelmt, b[0], b[1], inp) if dim == 2
+            else oracle.bwdtrans_hex(nq, nq, nq, nelmt, *b, inp)).reshape(nelmt, -1)
+    coa = layout == "coa"
+    src = oracle.to_coa(inp, nelmt, nm ** dim) if coa else inp
+    if dim == 2:
+        got = G.run_quad("BwdTransQuadKernel_Coa" if coa else "BwdTransQuadKernel", suf, nq, nq, nelmt, b[0], b[1], src)
+    else:
+        got = G.run_hex("BwdTransHexKernel_Coa" if coa else "BwdTransHexKernel", suf, (nq,) * 3, nelmt, b, src)
+    assert G.fe.last_backend() == ("lanes" if coa else "lanes-em")
+    got = (oracle.from_coa(got, nelmt, nq ** dim) if coa else got).reshape(nelmt, -1)
+    ok = [e for e in range(nelmt) if e != bad]
+    assert np.isfinite(got[ok]).all()
+    assert np.array_equal(got[ok], want[ok])
+    assert not np.isfinite(got[bad]).any()
