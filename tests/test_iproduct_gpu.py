@@ -105,7 +105,7 @@ def test_fp64_backends_bit_exact_ragged_groups_and_alignment(G, backend, weighte
         assert np.array_equal(got[1:-1], want), (backend, nq, nelmt, shift, G.rel_max(got[1:-1], want))
 
 
-@pytest.mark.parametrize("dim,nq,nelmt", [(2, 8, 1048576), (3, 8, 131072)])
+@pytest.mark.parametrize("dim,nq,nelmt", [(2, 8, 1048576), (3, 8, 131072), (2, 12, 466033), (3, 6, 310689)])
 def test_adjoint_of_the_device_bwdtrans_at_baseline_size(G, dim, nq, nelmt):
     """<IProduct(u), c> == <u, BwdTrans(c)> with both operators on the device, 64 Mi quadrature points"""
     import torch
