@@ -174,7 +174,7 @@ static int hex_table_lookup(unsigned nq, Backend *preferred)
 // cap) measured with tools/tune/lanes_probe.cu at 64 Mi points (profiles/r01_lanes_probe.csv):
 //   nq            4     5     6     7     8     9    10
 //   FP64 EL      16    32    32    16    16    16     8 (q-outer, 2 slices)
-//   FP32 EL      32    16    16    16    16    32    16 (3 CTAs per SM)
+//   FP32 EL      32    16    16    16    32    32    16 (3 CTAs per SM)
 constexpr unsigned kHexLanesMinNq = 4, kHexLanesMaxNq = 10;
 static int hex_lanes_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
 {
@@ -190,7 +190,7 @@ static int hex_lanes_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cu
     case 7:
         return launch_hex_lanes<T, 7, 16, 1>(nelmt, in, out, s);
     case 8:
-        return launch_hex_lanes<T, 8, 16, D ? 1 : 5>(nelmt, in, out, s);
+        return launch_hex_lanes<T, 8, D ? 16 : 32, 1>(nelmt, in, out, s);
     case 9:
         return launch_hex_lanes<T, 9, D ? 16 : 32, 1>(nelmt, in, out, s);
     case 10:

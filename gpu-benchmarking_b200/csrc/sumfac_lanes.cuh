@@ -212,7 +212,7 @@ template <typename T, int NQ, int EL> struct HexLanes
     static constexpr int IB0 = sizeof(T) == 4 ? 2 : 1;
     // FP64: the loop over the direction-0 output blocks stays a loop.  Unrolled, ptxas computes t1 for every i
     // at once (nm*nq live doubles on top of the plane: 230 registers at nq = 8, spills at nq = 10).
-    static constexpr bool ROLLED = sizeof(T) == 8 || NQ >= 9; // (FP32 nq >= 9: 182-255 registers unrolled)
+    static constexpr bool ROLLED = sizeof(T) == 8 || NQ >= 8; // (FP32: 122 registers unrolled at nq = 8, 182-255 beyond)
 };
 
 template <typename T, int NQ, int EL, int MINB>
@@ -535,7 +535,7 @@ template <typename T, int NQ, int EL> struct HexLanesEm
     static constexpr int SBUF    = SIN > EL * ES ? SIN : EL * ES;
     static constexpr size_t SMEM = (size_t)SBUF * sizeof(T) + 16;
     static constexpr int IB0     = sizeof(T) == 4 ? 2 : 1;
-    static constexpr bool ROLLED = sizeof(T) == 8 || NQ >= 9; // see HexLanes
+    static constexpr bool ROLLED = sizeof(T) == 8 || NQ >= 8; // see HexLanes
 };
 
 template <typename T, int NQ, int EL, int MINB, bool SUMSQ>
