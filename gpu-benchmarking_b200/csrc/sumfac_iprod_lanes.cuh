@@ -127,7 +127,7 @@ template <typename T, int NQ, int EL, bool STAGED = false> struct HexIprodLanes
     static constexpr size_t SMEM = (size_t)(S2 + (STAGED ? EL * NQ * PS : 0)) * sizeof(T);
     static constexpr int B2      = 2 * NQ * bank_pitch<T>(NM);
     static constexpr int IB0     = sizeof(T) == 4 ? 2 : 1;
-    static constexpr bool ROLLED = sizeof(T) == 8 || NQ >= 9; // see HexLanes
+    static constexpr bool ROLLED = sizeof(T) == 8 || NQ >= 8; // see HexLanes
 };
 
 template <typename T, int NQ, int EL, bool WEIGHTED, int MINB, bool STAGED>

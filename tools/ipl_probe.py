@@ -1,6 +1,5 @@
 #!/usr/bin/env python
-"""IProductWRTBase: the lanes kernel (sumfac_iprod_lanes.cuh) at every tile size against the row / tensor-core
-kernels, per (operator, nq, dtype), weighted and unweighted, at ~64 Mi quadrature points through the C ABI; every
+"""IProductWRTBase: the lanes kernel (sumfac_iprod_lanes.cuh) against the row / tensor-core kernels, per (operator, nq, dtype), weighted and unweighted, at ~64 Mi quadrature points through the C ABI; every
 variant must store exactly the bits of the row kernel.
 
     python tools/ipl_probe.py > gpurun_out/ipl_probe.csv
@@ -31,12 +30,9 @@ def main():
                 y = torch.empty(nelmt * nm ** dim, dtype=tdt, device="cuda")
                 for weighted in (0, 1):
                     ref = None
-                    variants = [("rows", None), ("mma", None)] + [("lanes", el) for el in (4, 8, 16, 32)]
+                    variants = [("rows", None), ("mma", None), ("lanes", None)]  # tile sizes: tools/tune/iprod_probe.cu
                     for be, el in variants:
                         fe.set_backend(be)
-                        if el:
-                            os.environ["B200FE_IPL_EL"] = str(el)
-
                         def call():
                             fe.iproduct(suf, (nq,) * dim, nelmt, [b.data_ptr()] * dim, x.data_ptr(), y.data_ptr(),
                                         weights=wgt.data_ptr() if weighted else 0, stream=st)
