@@ -305,7 +305,7 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
     if (be == Backend::Mma) // reads the basis matrices from global memory: no constant bank, no lock
         return (have & 4) ? hex_mma_switch(nq0, nelmt, b0, b1, b2, in, out, stream, partials, npartials) : B200FE_EUNSUPPORTED;
 
-    std::lock_guard<std::mutex> lock(g_bank_lock);
+    std::lock_guard<std::mutex> lock(bank_lock_of_current_device());
     const T *bases[3]   = {b0, b1, b2};
     int rc              = fill_basis_bank<T>(g_bank, 3, bases, (int)nm0, (int)nq0, false, stream);
     if (rc)
@@ -415,7 +415,7 @@ int run_iproduct_hex<T>(Backend be, unsigned nq, unsigned nelmt, const T *b0, co
     const bool lanes = be == Backend::Lanes || (be == Backend::Auto && hex_has_iprod_lanes(nq, w != nullptr) && aligned);
     if (!lanes && be != Backend::Auto && be != Backend::Rows)
         return B200FE_EUNSUPPORTED;
-    std::lock_guard<std::mutex> lock(g_bank_lock);
+    std::lock_guard<std::mutex> lock(bank_lock_of_current_device());
     const T *bases[3]   = {b0, b1, b2};
     int rc = fill_basis_bank<T>(g_bank, 3, bases, (int)nq - 1, (int)nq, true, stream); // transposed
     if (rc)

@@ -20,8 +20,19 @@
 namespace b200fe
 {
 
-static BankGuard g_bank;       // per translation unit, like the constant bank itself
-static std::mutex g_bank_lock; // fill -> launch -> release is one critical section
+static BankGuard g_bank; // per translation unit, like the constant bank itself
+
+// fill -> launch -> release is one critical section PER DEVICE: every field of BankGuard is indexed by the device, so
+// the host threads of a multi-GPU driver (utils/multi_gpu.h: one thread per GPU) do not queue behind each other's
+// launches.  Devices the guard has no slot for share slot 0; fill_basis_bank refuses them anyway.
+static std::mutex g_bank_locks[64];
+inline std::mutex &bank_lock_of_current_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+        dev = 0;
+    return g_bank_locks[dev];
+}
 
 inline bool aligned16(const void *p)
 {

@@ -321,7 +321,7 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
     if (be == Backend::Mma) // reads the basis matrices from global memory: no constant bank, no lock
         return (have & 4) ? quad_mma_switch(nq0, nelmt, b0, b1, in, out, stream, partials, npartials) : B200FE_EUNSUPPORTED;
 
-    std::lock_guard<std::mutex> lock(g_bank_lock);
+    std::lock_guard<std::mutex> lock(bank_lock_of_current_device());
     const T *bases[2]   = {b0, b1};
     int rc              = fill_basis_bank<T>(g_bank, 2, bases, (int)nm0, (int)nq0, false, stream);
     if (rc)
@@ -435,7 +435,7 @@ int run_iproduct_quad<T>(Backend be, unsigned nq, unsigned nelmt, const T *b0, c
     }
     else if (!lanes && be != Backend::Rows)
         return B200FE_EUNSUPPORTED;
-    std::lock_guard<std::mutex> lock(g_bank_lock);
+    std::lock_guard<std::mutex> lock(bank_lock_of_current_device());
     const T *bases[2]   = {b0, b1};
     int rc = fill_basis_bank<T>(g_bank, 2, bases, (int)nq - 1, (int)nq, true, stream); // transposed
     if (rc)
