@@ -213,3 +213,30 @@ def bwdtrans_host(suf, nq, nelmt, bases_host, in_host, out_host=0):
                                   _vp(out_host), ctypes.byref(res))
     _check(name, rc)
     return res.value
+
+
+class Plan:
+    """b200fe_plan_*: the basis matrices uploaded once for many operator calls (include/b200fe.h).
+    dim 2 = quad, 3 = hex; bases: DEVICE addresses of the dim matrices (copied by the plan)."""
+
+    def __init__(self, dim, suf, nq, bases, stream=0):
+        self.dim, self.suf, self.nq = dim, suf, nq
+        self._h = ctypes.c_void_p(None)
+        b = list(bases) + [0] * (3 - len(bases))
+        _check("b200fe_plan_create",
+               lib().b200fe_plan_create(ctypes.byref(self._h), ctypes.c_int(dim), ctypes.c_int(suf == "f32"), _u(nq),
+                                        _vp(b[0]), _vp(b[1]), _vp(b[2]), _vp(stream)))
+
+    def bwdtrans(self, nelmt, inp, out, coa=False, stream=0):
+        _check("b200fe_plan_bwdtrans",
+               lib().b200fe_plan_bwdtrans(self._h, ctypes.c_int(bool(coa)), _u(nelmt), _vp(inp), _vp(out),
+                                          _vp(stream)))
+
+    def iproduct(self, nelmt, inp, out, weights=0, stream=0):
+        _check("b200fe_plan_iproduct",
+               lib().b200fe_plan_iproduct(self._h, _u(nelmt), _vp(weights), _vp(inp), _vp(out), _vp(stream)))
+
+    def destroy(self):
+        if self._h:
+            h, self._h = self._h, ctypes.c_void_p(None)
+            _check("b200fe_plan_destroy", lib().b200fe_plan_destroy(h))

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <new>
 #include <vector>
 
 #include "common.cuh"
@@ -14,6 +15,8 @@ namespace b200fe
 {
 std::atomic<unsigned long long> g_launch_count{0};
 thread_local const char *t_last_backend = "none";
+thread_local unsigned long long t_bank_tag = 0; // common.cuh: non-zero only inside a b200fe_plan_* call
+static std::atomic<unsigned long long> g_next_plan_id{1};
 static std::atomic<int> g_forced_backend{-1}; // -1: per-entry-point default
 
 static Backend pick(Backend preferred)
@@ -283,6 +286,72 @@ static int hex_sumsq_entry(unsigned nq0, unsigned nq1, unsigned nq2, unsigned ne
               : launch_sumsq<T>(out, (size_t)nelmt * nq0 * nq1 * nq2, sumsq, scratch, false, st);
 }
 
+// ---- plans: the basis matrices uploaded once for many operator calls ---------------------------
+struct Plan
+{
+    unsigned long long id = 0;
+    int dim = 0, device = -1;
+    bool f32     = false;
+    unsigned nq  = 0;
+    void *d_basis = nullptr; // dim matrices of nm * nq values, back to back (256-byte aligned each)
+    size_t stride = 0;       // bytes between matrices
+    template <typename T> const T *basis(int d) const
+    {
+        return reinterpret_cast<const T *>(static_cast<const char *>(d_basis) + (size_t)d * stride);
+    }
+};
+
+// sets the bank tag for the duration of one dispatcher call on this thread
+struct BankTagScope
+{
+    explicit BankTagScope(unsigned long long id) { t_bank_tag = id; }
+    ~BankTagScope() { t_bank_tag = 0; }
+};
+
+static int plan_check(const Plan *p, const void *in, const void *out)
+{
+    if (!p || !in || !out)
+        return B200FE_EINVAL;
+    int dev = -1;
+    B200FE_CUDA_TRY(cudaGetDevice(&dev));
+    return dev == p->device ? B200FE_OK : B200FE_EINVAL; // a plan lives on the device it was created on
+}
+
+template <typename T>
+static int plan_bwdtrans(const Plan *p, bool coa, unsigned nelmt, const T *in, T *out, cudaStream_t stream)
+{
+    if (misaligned(in) || misaligned(out))
+        return B200FE_EALIGN;
+    if (coa && (nelmt % 32u) != 0)
+        return B200FE_EINVAL;
+    if (nelmt == 0)
+        return B200FE_OK;
+    const unsigned nq = p->nq, nm = nq - 1;
+    BankTagScope scope(p->id);
+    if (p->dim == 2)
+        return run_bwdtrans_quad<T>(pick(Backend::Auto), coa, nm, nm, nq, nq, nelmt, p->basis<T>(0), p->basis<T>(1), in,
+                                    out, stream);
+    return run_bwdtrans_hex<T>(pick(Backend::Auto), coa, nm, nm, nm, nq, nq, nq, nelmt, p->basis<T>(0), p->basis<T>(1),
+                               p->basis<T>(2), in, out, stream);
+}
+
+template <typename T>
+static int plan_iproduct(const Plan *p, unsigned nelmt, const T *w, const T *in, T *out, cudaStream_t stream)
+{
+    if (misaligned(in) || misaligned(out) || (w && misaligned(w)))
+        return B200FE_EALIGN;
+    if (p->nq > (p->dim == 2 ? 32u : 16u))
+        return B200FE_EUNSUPPORTED;
+    if (nelmt == 0)
+        return B200FE_OK;
+    BankTagScope scope(p->id);
+    if (p->dim == 2)
+        return run_iproduct_quad<T>(pick(Backend::Auto), p->nq, nelmt, p->basis<T>(0), p->basis<T>(1), w, in, out,
+                                    stream);
+    return run_iproduct_hex<T>(pick(Backend::Auto), p->nq, nelmt, p->basis<T>(0), p->basis<T>(1), p->basis<T>(2), w, in,
+                               out, stream);
+}
+
 } // namespace b200fe
 
 using namespace b200fe;
@@ -516,6 +585,85 @@ IPROD_API(f32, float)
     }
 FUSED_API(f64, double)
 FUSED_API(f32, float)
+
+// ---- plans ----------------------------------------------------------------------------------
+int b200fe_plan_create(b200fe_plan **plan, int dim, int is_f32, unsigned nq, const void *basis0, const void *basis1,
+                       const void *basis2, void *stream)
+{
+    if (!plan)
+        return B200FE_EINVAL;
+    *plan = nullptr;
+    if ((dim != 2 && dim != 3) || !basis0 || !basis1 || (dim == 3 && !basis2))
+        return B200FE_EINVAL;
+    if (nq < 2 || nq > 32)
+        return B200FE_EUNSUPPORTED;
+    const size_t esize = is_f32 ? sizeof(float) : sizeof(double);
+    const void *src[3] = {basis0, basis1, basis2};
+    for (int d = 0; d < dim; ++d)
+        if (reinterpret_cast<uintptr_t>(src[d]) % esize)
+            return B200FE_EALIGN;
+    Plan *p = new (std::nothrow) Plan;
+    if (!p)
+        return (int)cudaErrorMemoryAllocation;
+    p->dim = dim;
+    p->f32 = is_f32 != 0;
+    p->nq  = nq;
+    const size_t bytes = (size_t)(nq - 1) * nq * esize;
+    p->stride          = (bytes + 255) / 256 * 256;
+    cudaError_t e      = cudaGetDevice(&p->device);
+    if (e == cudaSuccess)
+        e = cudaMalloc(&p->d_basis, p->stride * (size_t)dim);
+    for (int d = 0; d < dim && e == cudaSuccess; ++d)
+        e = cudaMemcpyAsync(static_cast<char *>(p->d_basis) + (size_t)d * p->stride, src[d], bytes,
+                            cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    // the copies are ordered before any later work on `stream` only: make the plan usable from every stream
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess)
+    {
+        cudaFree(p->d_basis);
+        delete p;
+        return (int)e;
+    }
+    p->id = g_next_plan_id.fetch_add(1, std::memory_order_relaxed);
+    *plan = reinterpret_cast<b200fe_plan *>(p);
+    return B200FE_OK;
+}
+
+int b200fe_plan_destroy(b200fe_plan *plan)
+{
+    Plan *p = reinterpret_cast<Plan *>(plan);
+    if (!p)
+        return B200FE_OK;
+    // ids are never reused, so a stale bank tag cannot match a later plan; kernels in flight read the bank
+    // (or, tensor-core back-ends, d_basis: cudaFree waits for the device)
+    const cudaError_t e = cudaFree(p->d_basis);
+    delete p;
+    return (int)e;
+}
+
+int b200fe_plan_bwdtrans(const b200fe_plan *plan, int coa, unsigned nelmt, const void *in, void *out, void *stream)
+{
+    const Plan *p = reinterpret_cast<const Plan *>(plan);
+    const int rc  = plan_check(p, in, out);
+    if (rc)
+        return rc;
+    return p->f32 ? plan_bwdtrans<float>(p, coa != 0, nelmt, (const float *)in, (float *)out, (cudaStream_t)stream)
+                  : plan_bwdtrans<double>(p, coa != 0, nelmt, (const double *)in, (double *)out, (cudaStream_t)stream);
+}
+
+int b200fe_plan_iproduct(const b200fe_plan *plan, unsigned nelmt, const void *weights, const void *in, void *out,
+                         void *stream)
+{
+    const Plan *p = reinterpret_cast<const Plan *>(plan);
+    const int rc  = plan_check(p, in, out);
+    if (rc)
+        return rc;
+    return p->f32 ? plan_iproduct<float>(p, nelmt, (const float *)weights, (const float *)in, (float *)out,
+                                         (cudaStream_t)stream)
+                  : plan_iproduct<double>(p, nelmt, (const double *)weights, (const double *)in, (double *)out,
+                                          (cudaStream_t)stream);
+}
 
 // ---- host-buffer operator ---------------------------------------------------------------
 #define HOST_API(SUF, T)                                                                                     \
