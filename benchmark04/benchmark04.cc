@@ -18,6 +18,7 @@
 //   B200FE_NELMT=a,b,..  element counts instead of the 128..1Mi sweep
 //   B200FE_DTYPE=double|float|both     B200FE_REPS=40     B200FE_CPU_REPS=2
 //   B200FE_SKIP_CPU=1  B200FE_SKIP_CUBLAS=1
+//   B200FE_PLAN=0  issue every repetition through the per-call entry points instead of a b200fe_plan
 // Lines starting with "info" carry roofline figures; postprocess.py ignores them.
 #include "../utils/bench_common.h"
 #include "../utils/cpu_reference.h"
@@ -142,11 +143,16 @@ void run_test(const unsigned nelmt, const unsigned nq0, const unsigned nq1, cons
 
     // ---- columns 6-11: the six kernel entry points ----------------------------------------------
     using A = Api<T>;
-    auto with_wsp = [&](auto fn, const T *in) {
+    const OperatorPlan plan(2, sizeof(T) == 4, nq0, nq1, 0u, d_b0.get(), d_b1.get(), nullptr);
+    auto with_wsp = [&](auto fn, const T *in, bool interleaved = false) {
+        if (plan.active())
+            return plan.bwdtrans(interleaved, nelmt, in, d_out.get());
         FE_OK(fn(nm0, nm1, (unsigned)nmTot, nq0, nq1, nelmt, d_b0.get(), d_b1.get(), in, d_wsp.get(), d_out.get(),
                  nullptr));
     };
     auto no_wsp = [&](auto fn) {
+        if (plan.active())
+            return plan.bwdtrans(false, nelmt, d_in.get(), d_out.get());
         FE_OK(fn(nm0, nm1, (unsigned)nmTot, nq0, nq1, nelmt, d_b0.get(), d_b1.get(), d_in.get(), d_out.get(), nullptr));
     };
     auto column = [&](int col, auto &&launch) {
@@ -156,7 +162,7 @@ void run_test(const unsigned nelmt, const unsigned nq0, const unsigned nq1, cons
     };
     column(5, [&] { with_wsp(A::uncoa, d_in.get()); });
     if (nelmt % 32u == 0)
-        column(6, [&] { with_wsp(A::coa, d_in_coa.get()); });
+        column(6, [&] { with_wsp(A::coa, d_in_coa.get(), true); });
     column(7, [&] { with_wsp(A::qp, d_in.get()); });
     column(8, [&] { no_wsp(A::qpsh); });
     column(9, [&] { with_wsp(A::q1d, d_in.get()); });
@@ -183,7 +189,9 @@ void run_test(const unsigned nelmt, const unsigned nq0, const unsigned nq1, cons
     std::cout << "info " << nelmt << " " << A::name << " HBM% of " << hbm_peak_gbs() << " GB/s, columns 6-11:";
     for (int c = 5; c < kCols; ++c)
         std::cout << " " << std::setprecision(4) << 100.0 * gb / secs[c] / hbm_peak_gbs();
-    std::cout << " | host threads " << host_threads() << std::endl << std::flush;
+    std::cout << " | host threads " << host_threads() << (plan.active() ? " | via b200fe_plan" : " | per-call entry points")
+              << std::endl
+              << std::flush;
 }
 
 // B200FE_NGPUS > 1: the element range is sharded over the GPUs (one host thread each); the six Cuda columns
@@ -235,11 +243,16 @@ template <typename T> void run_test_multi(MultiGpu &mg, const unsigned nelmt, co
         Checksum<T> checksum;
 
         using A = Api<T>;
-        auto with_wsp = [&](auto fn, const T *in) {
+        const OperatorPlan plan(2, sizeof(T) == 4, nq0, nq1, 0u, d_b0.get(), d_b1.get(), nullptr); // on this rank's device
+        auto with_wsp = [&](auto fn, const T *in, bool interleaved = false) {
+            if (plan.active())
+                return plan.bwdtrans(interleaved, n, in, d_out.get());
             FE_OK(fn(nm0, nm1, (unsigned)nmTot, nq0, nq1, n, d_b0.get(), d_b1.get(), in, d_wsp.get(), d_out.get(),
                      nullptr));
         };
         auto no_wsp = [&](auto fn) {
+            if (plan.active())
+                return plan.bwdtrans(false, n, d_in.get(), d_out.get());
             FE_OK(fn(nm0, nm1, (unsigned)nmTot, nq0, nq1, n, d_b0.get(), d_b1.get(), d_in.get(), d_out.get(), nullptr));
         };
         auto column = [&](int col, auto &&launch) {
@@ -259,7 +272,7 @@ template <typename T> void run_test_multi(MultiGpu &mg, const unsigned nelmt, co
         };
         column(5, [&] { with_wsp(A::uncoa, d_in.get()); });
         if (all32)
-            column(6, [&] { with_wsp(A::coa, d_in_coa.get()); });
+            column(6, [&] { with_wsp(A::coa, d_in_coa.get(), true); });
         column(7, [&] { with_wsp(A::qp, d_in.get()); });
         column(8, [&] { no_wsp(A::qpsh); });
         column(9, [&] { with_wsp(A::q1d, d_in.get()); });

@@ -135,11 +135,16 @@ void run_test(const unsigned nelmt, const unsigned nq0, const unsigned nq1, cons
     }
 
     using A = Api<T>;
-    auto with_wsp = [&](auto fn, const T *in) {
+    const OperatorPlan plan(3, sizeof(T) == 4, nq0, nq1, nq2, d_b0.get(), d_b1.get(), d_b2.get());
+    auto with_wsp = [&](auto fn, const T *in, bool interleaved = false) {
+        if (plan.active())
+            return plan.bwdtrans(interleaved, nelmt, in, d_out.get());
         FE_OK(fn(nm0, nm1, nm2, (unsigned)nmTot, nq0, nq1, nq2, nelmt, d_b0.get(), d_b1.get(), d_b2.get(), in,
                  d_wsp1.get(), d_wsp2.get(), d_out.get(), nullptr));
     };
     auto no_wsp = [&](auto fn) {
+        if (plan.active())
+            return plan.bwdtrans(false, nelmt, d_in.get(), d_out.get());
         FE_OK(fn(nm0, nm1, nm2, (unsigned)nmTot, nq0, nq1, nq2, nelmt, d_b0.get(), d_b1.get(), d_b2.get(), d_in.get(),
                  d_out.get(), nullptr));
     };
@@ -150,7 +155,7 @@ void run_test(const unsigned nelmt, const unsigned nq0, const unsigned nq1, cons
     };
     column(5, [&] { with_wsp(A::uncoa, d_in.get()); });
     if (nelmt % 32u == 0)
-        column(6, [&] { with_wsp(A::coa, d_in_coa.get()); });
+        column(6, [&] { with_wsp(A::coa, d_in_coa.get(), true); });
     column(7, [&] { with_wsp(A::qp, d_in.get()); });
     column(8, [&] { no_wsp(A::qpsh); });
     column(9, [&] { with_wsp(A::q1d, d_in.get()); });
@@ -175,7 +180,9 @@ void run_test(const unsigned nelmt, const unsigned nq0, const unsigned nq1, cons
     std::cout << "info " << nelmt << " " << A::name << " HBM% of " << hbm_peak_gbs() << " GB/s, columns 6-11:";
     for (int c = 5; c < kCols; ++c)
         std::cout << " " << std::setprecision(4) << 100.0 * gb / secs[c] / hbm_peak_gbs();
-    std::cout << " | host threads " << host_threads() << std::endl << std::flush;
+    std::cout << " | host threads " << host_threads() << (plan.active() ? " | via b200fe_plan" : " | per-call entry points")
+              << std::endl
+              << std::flush;
 }
 
 // B200FE_NGPUS > 1: the element range is sharded over the GPUs (one host thread each); the six Cuda columns
@@ -225,11 +232,16 @@ void run_test_multi(MultiGpu &mg, const unsigned nelmt, const unsigned nq0, cons
         Checksum<T> checksum;
 
         using A = Api<T>;
-        auto with_wsp = [&](auto fn, const T *in) {
+        const OperatorPlan plan(3, sizeof(T) == 4, nq0, nq1, nq2, d_b0.get(), d_b1.get(), d_b2.get()); // this rank's device
+        auto with_wsp = [&](auto fn, const T *in, bool interleaved = false) {
+            if (plan.active())
+                return plan.bwdtrans(interleaved, n, in, d_out.get());
             FE_OK(fn(nm0, nm1, nm2, (unsigned)nmTot, nq0, nq1, nq2, n, d_b0.get(), d_b1.get(), d_b2.get(), in,
                      d_wsp1.get(), d_wsp2.get(), d_out.get(), nullptr));
         };
         auto no_wsp = [&](auto fn) {
+            if (plan.active())
+                return plan.bwdtrans(false, n, d_in.get(), d_out.get());
             FE_OK(fn(nm0, nm1, nm2, (unsigned)nmTot, nq0, nq1, nq2, n, d_b0.get(), d_b1.get(), d_b2.get(), d_in.get(),
                      d_out.get(), nullptr));
         };
@@ -257,7 +269,7 @@ void run_test_multi(MultiGpu &mg, const unsigned nelmt, const unsigned nq0, cons
             all32 = all32 && ((e - b) % 32u == 0);
         }
         if (all32)
-            column(6, [&] { with_wsp(A::coa, d_in_coa.get()); });
+            column(6, [&] { with_wsp(A::coa, d_in_coa.get(), true); });
         column(7, [&] { with_wsp(A::qp, d_in.get()); });
         column(8, [&] { no_wsp(A::qpsh); });
         column(9, [&] { with_wsp(A::q1d, d_in.get()); });

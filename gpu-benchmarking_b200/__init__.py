@@ -90,6 +90,10 @@ def set_backend(name):
     _check("b200fe_set_backend", lib().b200fe_set_backend(name.encode()))
 
 
+def set_bank_fill(mode):
+    _check("b200fe_set_bank_fill", lib().b200fe_set_bank_fill(mode.encode()))
+
+
 QUAD_WSP = ("BwdTransQuadKernel", "BwdTransQuadKernel_Coa", "BwdTransQuadKernel_QP", "BwdTransQuadKernel_QP_1D")
 QUAD_NOWSP = ("BwdTransQuadKernel_QP_Shared", "BwdTransQuadKernel_QP_1D_Shared")
 HEX_WSP = ("BwdTransHexKernel", "BwdTransHexKernel_Coa", "BwdTransHexKernel_QP", "BwdTransHexKernel_QP_1D")

@@ -318,9 +318,10 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
         rc = coa ? hex_lanes_switch(nq0, nelmt, in, out, stream) : hex_lanesem_switch(nq0, nelmt, in, out, stream, partials, npartials);
     else
         rc = hex_tpe_switch(nq0, nelmt, in, out, stream);
-    if (rc)
-        return rc;
-    return release_basis_bank(g_bank, stream);
+    // the fill is enqueued: record the bank's event on the error path too, or another stream's next fill could
+    // overlap it
+    const int rel = release_basis_bank(g_bank, stream);
+    return rc ? rc : rel;
 }
 
 // ---- IProductWRTBase ---------------------------------------------------------------
@@ -421,9 +422,10 @@ int run_iproduct_hex<T>(Backend be, unsigned nq, unsigned nelmt, const T *b0, co
     if (rc)
         return rc;
     rc = lanes ? hex_iprod_lanes_switch(nq, nelmt, in, w, out, stream) : hex_iprod_switch(nq, nelmt, in, w, out, stream);
-    if (rc)
-        return rc;
-    return release_basis_bank(g_bank, stream);
+    // the fill is enqueued: record the bank's event on the error path too, or another stream's next fill could
+    // overlap it
+    const int rel = release_basis_bank(g_bank, stream);
+    return rc ? rc : rel;
 }
 
 } // namespace b200fe

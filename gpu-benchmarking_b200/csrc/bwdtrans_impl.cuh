@@ -74,8 +74,11 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned 
     cudaLaunchAttribute attr[1];
     attr[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs                                          = attr;
-    cfg.numAttrs                                       = 1;
+    if (g_bank_fill_mode.load(std::memory_order_relaxed) == 0) // "memcpy" route: plain stream order behind the copy
+    {
+        cfg.attrs    = attr;
+        cfg.numAttrs = 1;
+    }
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -334,9 +334,10 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
         rc = coa ? quad_lanes_switch(nq0, nelmt, in, out, stream) : quad_lanesem_switch(nq0, nelmt, in, out, stream, partials, npartials);
     else
         rc = quad_tpe_switch(nq0, nelmt, in, out, stream);
-    if (rc)
-        return rc;
-    return release_basis_bank(g_bank, stream);
+    // the fill is enqueued: record the bank's event on the error path too, or another stream's next fill could
+    // overlap it
+    const int rel = release_basis_bank(g_bank, stream);
+    return rc ? rc : rel;
 }
 
 // ---- IProductWRTBase ---------------------------------------------------------------
@@ -441,9 +442,10 @@ int run_iproduct_quad<T>(Backend be, unsigned nq, unsigned nelmt, const T *b0, c
     if (rc)
         return rc;
     rc = lanes ? quad_iprod_lanes_switch(nq, nelmt, in, w, out, stream) : quad_iprod_switch(nq, nelmt, in, w, out, stream);
-    if (rc)
-        return rc;
-    return release_basis_bank(g_bank, stream);
+    // the fill is enqueued: record the bank's event on the error path too, or another stream's next fill could
+    // overlap it
+    const int rel = release_basis_bank(g_bank, stream);
+    return rc ? rc : rel;
 }
 
 } // namespace b200fe

@@ -18,6 +18,7 @@ thread_local const char *t_last_backend = "none";
 thread_local unsigned long long t_bank_tag = 0; // common.cuh: non-zero only inside a b200fe_plan_* call
 static std::atomic<unsigned long long> g_next_plan_id{1};
 static std::atomic<int> g_forced_backend{-1}; // -1: per-entry-point default
+std::atomic<int> g_bank_fill_mode{0};         // common.cuh: 0 kernel + programmatic dependent launch, 1 staging + cudaMemcpyToSymbolAsync
 
 static Backend pick(Backend preferred)
 {
@@ -34,7 +35,7 @@ template <typename T>
 static int quad_entry(Backend preferred, bool coa, unsigned nm0, unsigned nm1, unsigned nmTot, unsigned nq0,
                       unsigned nq1, unsigned nelmt, const T *b0, const T *b1, const T *in, T *out, void *stream)
 {
-    if (!b0 || !b1 || !in || !out || nm0 == 0 || nm1 == 0 || nq0 == 0 || nq1 == 0 || nmTot != nm0 * nm1)
+    if (!b0 || !b1 || !in || !out || nm0 == 0 || nm1 == 0 || nq0 == 0 || nq1 == 0 || (unsigned long long)nmTot != (unsigned long long)nm0 * nm1) // 64-bit: the product may not wrap
         return B200FE_EINVAL;
     if (coa && (nelmt % 32u) != 0)
         return B200FE_EINVAL; // the interleaved layout is only defined for whole groups of 32
@@ -52,7 +53,8 @@ static int hex_entry(Backend preferred, bool coa, unsigned nm0, unsigned nm1, un
                      const T *in, T *out, void *stream)
 {
     if (!b0 || !b1 || !b2 || !in || !out || nm0 == 0 || nm1 == 0 || nm2 == 0 || nq0 == 0 || nq1 == 0 || nq2 == 0 ||
-        nmTot != nm0 * nm1 * nm2)
+        (unsigned long long)nmTot != (unsigned long long)nm0 * nm1 * nm2 || nm0 > 0xffffu || nm1 > 0xffffu ||
+        nm2 > 0xffffu) // 64-bit product of three values below 2^16: cannot wrap
         return B200FE_EINVAL;
     if (coa && (nelmt % 32u) != 0)
         return B200FE_EINVAL;
@@ -63,6 +65,13 @@ static int hex_entry(Backend preferred, bool coa, unsigned nm0, unsigned nm1, un
     return run_bwdtrans_hex<T>(pick(preferred), coa, nm0, nm1, nm2, nq0, nq1, nq2, nelmt, b0, b1, b2, in, out,
                                (cudaStream_t)stream);
 }
+
+// sets the bank tag for the duration of one dispatcher call on this thread
+struct BankTagScope
+{
+    explicit BankTagScope(unsigned long long id) { t_bank_tag = id; }
+    ~BankTagScope() { t_bank_tag = 0; }
+};
 
 // ---- host-buffer pipeline -------------------------------------------------------
 // chunk ring: H2D(in) -> BwdTrans -> sum out^2 [-> D2H(out)], one stream per slot,
@@ -97,6 +106,7 @@ struct HostPipe
                 B200FE_CUDA_TRY(cudaStreamCreateWithFlags(&stream[s], cudaStreamNonBlocking));
         if (in_bytes > in_cap || out_bytes > out_cap)
         {
+            in_cap = out_cap = 0; // a failed cudaMalloc below must not leave stale capacities over freed pointers
             for (int s = 0; s < kSlots; ++s)
             {
                 cudaFree(d_in[s]);
@@ -113,6 +123,7 @@ struct HostPipe
                 B200FE_CUDA_TRY(cudaMalloc(&d_scratch[s], sumsq_scratch_bytes()));
         if (basis_bytes > basis_cap)
         {
+            basis_cap = 0;
             cudaFree(d_basis);
             d_basis = nullptr;
             B200FE_CUDA_TRY(cudaMalloc(&d_basis, basis_bytes));
@@ -120,6 +131,7 @@ struct HostPipe
         }
         if (nchunk > sums_cap)
         {
+            sums_cap = 0;
             cudaFree(d_sums);
             cudaFreeHost(h_sums);
             d_sums = nullptr;
@@ -151,6 +163,21 @@ struct HostPipe
         d_sums  = nullptr;
         h_sums  = nullptr;
         in_cap = out_cap = basis_cap = sums_cap = 0;
+    }
+
+    // waits for everything the pipeline has in flight (error paths: chunks may still be copying from / into host memory)
+    void drain()
+    {
+        for (int s = 0; s < kSlots; ++s)
+            if (stream[s])
+                cudaStreamSynchronize(stream[s]);
+    }
+
+    // thread exit: give the streams and buffers back unless the CUDA runtime is already being torn down
+    ~HostPipe()
+    {
+        if (device >= 0 && cudaSetDevice(device) == cudaSuccess)
+            release();
     }
 };
 
@@ -201,6 +228,13 @@ static int host_pipeline(int dim, const unsigned *nq, size_t nelmt, const T *con
     }
     B200FE_CUDA_TRY(cudaStreamSynchronize(P.stream[0]));
 
+    // one bank tag for the whole call: the staged matrices do not change between chunks, so only the first chunk
+    // (per bank) pays the staging launch -- the plan mechanism of b200fe_plan_* with a throw-away id
+    BankTagScope scope(g_next_plan_id.fetch_add(1, std::memory_order_relaxed));
+    auto fail = [&](int code) {
+        P.drain(); // earlier chunks are still copying from in_host / into out_host
+        return code;
+    };
     for (size_t c = 0; c < nchunk; ++c)
     {
         const int s       = (int)(c % HostPipe::kSlots);
@@ -209,22 +243,30 @@ static int host_pipeline(int dim, const unsigned *nq, size_t nelmt, const T *con
         const unsigned ne = (unsigned)((nelmt - e0 < chunk) ? nelmt - e0 : chunk);
         T *din            = reinterpret_cast<T *>(P.d_in[s]);
         T *dout           = reinterpret_cast<T *>(P.d_out[s]);
-        B200FE_CUDA_TRY(cudaMemcpyAsync(din, in_host + e0 * nmTot, (size_t)ne * nmTot * sizeof(T),
-                                        cudaMemcpyHostToDevice, st));
+        cudaError_t ce    = cudaMemcpyAsync(din, in_host + e0 * nmTot, (size_t)ne * nmTot * sizeof(T),
+                                            cudaMemcpyHostToDevice, st);
+        if (ce != cudaSuccess)
+            return fail((int)ce);
+        // operator with the checksum in its epilogue where the back-end has one (no second pass over `out`)
+        unsigned np = 0;
         if (dim == 2)
             rc = run_bwdtrans_quad<T>(pick(Backend::Auto), false, nm[0], nm[1], nq[0], nq[1], ne, d_b[0], d_b[1], din,
-                                      dout, st);
+                                      dout, st, (double *)P.d_scratch[s], &np);
         else
             rc = run_bwdtrans_hex<T>(pick(Backend::Auto), false, nm[0], nm[1], nm[2], nq[0], nq[1], nq[2], ne, d_b[0],
-                                     d_b[1], d_b[2], din, dout, st);
+                                     d_b[1], d_b[2], din, dout, st, (double *)P.d_scratch[s], &np);
         if (rc)
-            return rc;
-        rc = launch_sumsq<T>(dout, (size_t)ne * nqTot, P.d_sums + c, P.d_scratch[s], false, st);
+            return fail(rc);
+        rc = np ? launch_sum_final((const double *)P.d_scratch[s], np, P.d_sums + c, st)
+                : launch_sumsq<T>(dout, (size_t)ne * nqTot, P.d_sums + c, P.d_scratch[s], false, st);
         if (rc)
-            return rc;
+            return fail(rc);
         if (out_host)
-            B200FE_CUDA_TRY(cudaMemcpyAsync(out_host + e0 * nqTot, dout, (size_t)ne * nqTot * sizeof(T),
-                                            cudaMemcpyDeviceToHost, st));
+        {
+            ce = cudaMemcpyAsync(out_host + e0 * nqTot, dout, (size_t)ne * nqTot * sizeof(T), cudaMemcpyDeviceToHost, st);
+            if (ce != cudaSuccess)
+                return fail((int)ce);
+        }
     }
     for (int s = 0; s < HostPipe::kSlots; ++s)
         B200FE_CUDA_TRY(cudaStreamSynchronize(P.stream[s]));
@@ -301,13 +343,6 @@ struct Plan
     }
 };
 
-// sets the bank tag for the duration of one dispatcher call on this thread
-struct BankTagScope
-{
-    explicit BankTagScope(unsigned long long id) { t_bank_tag = id; }
-    ~BankTagScope() { t_bank_tag = 0; }
-};
-
 static int plan_check(const Plan *p, const void *in, const void *out)
 {
     if (!p || !in || !out)
@@ -340,7 +375,7 @@ static int plan_iproduct(const Plan *p, unsigned nelmt, const T *w, const T *in,
 {
     if (misaligned(in) || misaligned(out) || (w && misaligned(w)))
         return B200FE_EALIGN;
-    if (p->nq > (p->dim == 2 ? 32u : 16u))
+    if (p->nq > (p->dim == 2 ? 32u : 15u)) // the hex row tables instantiate nq 2..15
         return B200FE_EUNSUPPORTED;
     if (nelmt == 0)
         return B200FE_OK;
@@ -410,6 +445,19 @@ int b200fe_set_backend(const char *name)
         g_forced_backend = (int)Backend::Lanes;
     else if (!strcmp(name, "generic"))
         g_forced_backend = (int)Backend::Generic;
+    else
+        return B200FE_EINVAL;
+    return B200FE_OK;
+}
+
+int b200fe_set_bank_fill(const char *mode)
+{
+    if (!mode)
+        return B200FE_EINVAL;
+    if (!strcmp(mode, "kernel"))
+        g_bank_fill_mode = 0;
+    else if (!strcmp(mode, "memcpy"))
+        g_bank_fill_mode = 1;
     else
         return B200FE_EINVAL;
     return B200FE_OK;
@@ -559,7 +607,7 @@ size_t b200fe_sumsq_scratch_bytes(void)
         if (misaligned(basis0) || misaligned(basis1) || misaligned(basis2) || misaligned(in) ||              \
             misaligned(out) || (weights && misaligned(weights)))                                             \
             return B200FE_EALIGN;                                                                            \
-        if (nq0 != nq1 || nq1 != nq2 || nm0 + 1 != nq0 || nm1 + 1 != nq1 || nm2 + 1 != nq2 || nq0 > 16)      \
+        if (nq0 != nq1 || nq1 != nq2 || nm0 + 1 != nq0 || nm1 + 1 != nq1 || nm2 + 1 != nq2 || nq0 > 15)      \
             return B200FE_EUNSUPPORTED;                                                                      \
         if (nelmt == 0)                                                                                      \
             return B200FE_OK;                                                                                \

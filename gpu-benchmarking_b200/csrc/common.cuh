@@ -186,6 +186,7 @@ struct BankGuard
     cudaStream_t last[64] = {};
     bool used[64]         = {};
     void *bank[64]        = {}; // global address of this translation unit's constant bank, per device
+    void *stage[64]       = {}; // "memcpy" fill route only: global staging copy of the bank, per device
     unsigned long long tag[64] = {}; // whose matrices the bank holds (0 = an anonymous per-call fill)
 };
 
@@ -193,6 +194,13 @@ struct BankGuard
 // + transposed.  A fill whose tag is already resident is skipped -- the plan's matrices are immutable device
 // copies, so equal tags mean equal bank contents.  0 on every other path: those always refill.
 extern thread_local unsigned long long t_bank_tag;
+
+// How the bank is rewritten (b200fe_set_bank_fill): 0 = "kernel" (default): the fill kernel stores through the
+// symbol's global address and the operator starts as its programmatic dependent -- fastest, and guarded by the
+// mandatory SASS scan tools/check_sass.py; 1 = "memcpy": the fill kernel writes a global staging buffer and
+// cudaMemcpyToSymbolAsync (device to device) moves it into the bank -- only documented CUDA behaviour (constant
+// memory written by the runtime, ordinary stream order), ~3 us more stream time per per-call operator.
+extern std::atomic<int> g_bank_fill_mode;
 
 // Bank layout: matrix d occupies rows [d*nrows, (d+1)*nrows) of `pitch` values each, pitch = the row length
 // rounded up to a whole 16-byte vector (bank_pitch), so that every row -- and every block of 2 / 4 consecutive
@@ -266,10 +274,32 @@ inline int fill_basis_bank(BankGuard &g, int nb, const T *const *basis, int nm, 
     if (tag && g.tag[dev] == tag)
         return 0; // this plan's matrices are resident (its fill is ordered before us by the event wait above)
     g.tag[dev] = 0;
-    fill_bank_kernel<T><<<1, 256, 0, stream>>>(static_cast<T *>(g.bank[dev]), basis[0], nb > 1 ? basis[1] : basis[0],
-                                               nb > 2 ? basis[2] : basis[0], nb, nm, nq, transposed ? 1 : 0);
-    count_launch();
-    const int rc = launch_status();
+    int rc;
+    if (g_bank_fill_mode.load(std::memory_order_relaxed) == 1)
+    {
+        if (!g.stage[dev])
+            B200FE_CUDA_TRY(cudaMalloc(&g.stage[dev], kBasisBankElems * sizeof(T)));
+        fill_bank_kernel<T><<<1, 256, 0, stream>>>(static_cast<T *>(g.stage[dev]), basis[0], nb > 1 ? basis[1] : basis[0],
+                                                   nb > 2 ? basis[2] : basis[0], nb, nm, nq, transposed ? 1 : 0);
+        count_launch();
+        rc = launch_status();
+        const size_t bytes = (size_t)nb * rows * bank_pitch<T>(cols) * sizeof(T);
+        if (rc == 0)
+        {
+            if (std::is_same<T, double>::value)
+                rc = (int)cudaMemcpyToSymbolAsync(c_basis_f64, g.stage[dev], bytes, 0, cudaMemcpyDeviceToDevice, stream);
+            else
+                rc = (int)cudaMemcpyToSymbolAsync(c_basis_f32, g.stage[dev], bytes, 0, cudaMemcpyDeviceToDevice, stream);
+        }
+    }
+    else
+    {
+        fill_bank_kernel<T><<<1, 256, 0, stream>>>(static_cast<T *>(g.bank[dev]), basis[0],
+                                                   nb > 1 ? basis[1] : basis[0], nb > 2 ? basis[2] : basis[0], nb, nm, nq,
+                                                   transposed ? 1 : 0);
+        count_launch();
+        rc = launch_status();
+    }
     if (rc == 0)
         g.tag[dev] = tag;
     return rc;

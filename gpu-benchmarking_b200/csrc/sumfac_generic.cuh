@@ -125,7 +125,10 @@ template <typename T>
 inline int launch_quad_generic(unsigned nm0, unsigned nm1, unsigned nq0, unsigned nq1, unsigned nelmt, const T *b0,
                                const T *b1, const T *in, T *out, bool coa, cudaStream_t stream)
 {
-    const size_t smem = (size_t)(nm0 * nq0 + nm1 * nq1 + nm0 * nm1 + nq0 * nm1) * sizeof(T);
+    // 64-bit products: caller-supplied shapes must not wrap into something that passes the check
+    if (nm0 > 0xffffu || nm1 > 0xffffu || nq0 > 0xffffu || nq1 > 0xffffu)
+        return B200FE_EUNSUPPORTED;
+    const size_t smem = ((size_t)nm0 * nq0 + (size_t)nm1 * nq1 + (size_t)nm0 * nm1 + (size_t)nq0 * nm1) * sizeof(T);
     if (smem > (size_t)kSmemMax)
         return B200FE_EUNSUPPORTED;
     B200FE_CUDA_TRY(cudaFuncSetAttribute(bwdtrans_quad_generic_kernel<T>,
@@ -144,8 +147,10 @@ inline int launch_hex_generic(unsigned nm0, unsigned nm1, unsigned nm2, unsigned
                               unsigned nelmt, const T *b0, const T *b1, const T *b2, const T *in, T *out, bool coa,
                               cudaStream_t stream)
 {
-    const size_t smem = (size_t)(nm0 * nq0 + nm1 * nq1 + nm2 * nq2 + nm0 * nm1 * nm2 + nq0 * nm1 * nm2 +
-                                 nq0 * nq1 * nm2) *
+    if (nm0 > 0x3ffu || nm1 > 0x3ffu || nm2 > 0x3ffu || nq0 > 0x3ffu || nq1 > 0x3ffu || nq2 > 0x3ffu)
+        return B200FE_EUNSUPPORTED; // below 2^10 each: no 64-bit product of three can wrap, and nothing larger fits
+    const size_t smem = ((size_t)nm0 * nq0 + (size_t)nm1 * nq1 + (size_t)nm2 * nq2 + (size_t)nm0 * nm1 * nm2 +
+                         (size_t)nq0 * nm1 * nm2 + (size_t)nq0 * nq1 * nm2) *
                         sizeof(T);
     if (smem > (size_t)kSmemMax)
         return B200FE_EUNSUPPORTED;

@@ -413,14 +413,15 @@ template <typename T, int NQ, int EL, int TPC = 1> struct QuadLanesEm
 {
     static_assert(NQ % 2 == 0, "nm^2 must be odd for conflict-free lane access to the unpadded slab");
     static constexpr int NM = NQ - 1, NM2 = NM * NM, NQ2 = NQ * NQ;
-    static constexpr int THREADS = EL * NQ;
+    static constexpr int WORK    = EL * NQ;                // threads with a row to contract
+    static constexpr int THREADS = (WORK + 31) / 32 * 32;  // whole warps: cta_sum_fixed shuffles over full warps
     static constexpr int E1      = NQ + 1;  // element stride of t1 (odd)
     static constexpr int Q1      = EL * E1; // row stride of t1
     static constexpr int SIN     = (EL * NM2 * (int)sizeof(T) + 15) / 16 * 16 / (int)sizeof(T);
     static constexpr int S1      = (NM * Q1 * (int)sizeof(T) + 15) / 16 * 16 / (int)sizeof(T);
     static constexpr int NBUF    = TPC > 1 ? 2 : 1;
     static constexpr size_t SMEM = (size_t)(TPC * SIN + NBUF * S1) * sizeof(T) + 8 * ((TPC + 1) / 2 * 2);
-    static_assert(THREADS <= 1024, "block size");
+    static_assert(THREADS <= 1024 && THREADS % 32 == 0, "block size: whole warps");
 };
 
 // SUMSQ: operator + checksum fused: every thread squares what it stores, the CTA leaves one partial
@@ -496,10 +497,13 @@ __device__ __noinline__ void quad_lanesem_body(const T *__restrict__ in, T *__re
             const int e = tid / NQ, i = tid - e * NQ;
             T x[NM];
             const T *src = st1 + e * E1 + i;
+            if (tid < C::WORK) // the threads that pad the last warp own no row: they only take part in the barriers
+            {
 #pragma unroll
-            for (int q = 0; q < NM; ++q)
-                x[q] = src[q * Q1];
-            if (e < ne)
+                for (int q = 0; q < NM; ++q)
+                    x[q] = src[q * Q1];
+            }
+            if (tid < C::WORK && e < ne)
             {
                 T *dst = out + (e0 + e) * NQ2 + i;
                 lanes_row<T, NM, NQ, B1>(x, [&](int j, T v) {

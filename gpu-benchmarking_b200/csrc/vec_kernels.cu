@@ -11,6 +11,7 @@
 // run.
 #include <type_traits>
 
+#include "../../utils/cuda_vectors.h"
 #include "common.cuh"
 #include "vec_kernels.h"
 
@@ -46,43 +47,21 @@ template <typename A, int THREADS> __device__ __forceinline__ A block_sum(A v)
     return total;
 }
 
-// component-wise vector accumulation, the device-side counterpart of the
-// reference's float4/double2 operators (utils/cuda_vectors.h:7-141)
-__device__ __forceinline__ void sq_acc(double2 &a, const double2 v)
+// component-wise vector accumulation through the float4 / double2 operators of utils/cuda_vectors.h -- the shared
+// device header of the 1-D kernels, as in the reference (utils/cuda_vectors.h:7-141; its kernels use `+=`(vec, vec)
+// and `*`(vec, vec): benchmark01.cc:32,43, benchmark02.cc:29,38, benchmark03.cc:31,43).  nvcc contracts the
+// inlined `a += u * v` into one fused multiply-add per component, the arithmetic of the reference kernels.
+template <typename V> __device__ __forceinline__ void sq_acc(V &a, const V v)
 {
-    a.x = fmadd(v.x, v.x, a.x);
-    a.y = fmadd(v.y, v.y, a.y);
+    a += v * v;
 }
-__device__ __forceinline__ void sq_acc(float4 &a, const float4 v)
+template <typename V> __device__ __forceinline__ void dot_acc(V &a, const V u, const V v)
 {
-    a.x = fmadd(v.x, v.x, a.x);
-    a.y = fmadd(v.y, v.y, a.y);
-    a.z = fmadd(v.z, v.z, a.z);
-    a.w = fmadd(v.w, v.w, a.w);
+    a += u * v;
 }
-__device__ __forceinline__ void dot_acc(double2 &a, const double2 u, const double2 v)
+template <typename V> __device__ __forceinline__ void add_acc(V &a, const V v)
 {
-    a.x = fmadd(u.x, v.x, a.x);
-    a.y = fmadd(u.y, v.y, a.y);
-}
-__device__ __forceinline__ void dot_acc(float4 &a, const float4 u, const float4 v)
-{
-    a.x = fmadd(u.x, v.x, a.x);
-    a.y = fmadd(u.y, v.y, a.y);
-    a.z = fmadd(u.z, v.z, a.z);
-    a.w = fmadd(u.w, v.w, a.w);
-}
-__device__ __forceinline__ void add_acc(double2 &a, const double2 v)
-{
-    a.x += v.x;
-    a.y += v.y;
-}
-__device__ __forceinline__ void add_acc(float4 &a, const float4 v)
-{
-    a.x += v.x;
-    a.y += v.y;
-    a.z += v.z;
-    a.w += v.w;
+    a += v;
 }
 __device__ __forceinline__ double hsum(const double2 v)
 {
@@ -116,8 +95,8 @@ __global__ void __launch_bounds__(kRedThreads)
     constexpr int W = Vec16<T>::W;
     const unsigned n      = end - begin;
     const T *x            = data + begin;
-    const unsigned rank   = blockIdx.x * kRedThreads + threadIdx.x;
-    const unsigned stride = gridDim.x * kRedThreads;
+    const size_t rank   = (size_t)blockIdx.x * kRedThreads + threadIdx.x; // 64-bit: t += k*stride must not wrap
+    const size_t stride = (size_t)gridDim.x * kRedThreads;
     T v                   = T(0);
 
     if (VL)
@@ -125,7 +104,7 @@ __global__ void __launch_bounds__(kRedThreads)
         const unsigned nv = n / W;
         const V *xv       = reinterpret_cast<const V *>(x);
         V acc0 = vzero<V>(), acc1 = vzero<V>(), acc2 = vzero<V>(), acc3 = vzero<V>();
-        unsigned t = rank;
+        size_t t = rank;
         for (; t + 3 * (size_t)stride < nv; t += 4 * stride)
         {
             const V a = ld_stream(xv + t), b = ld_stream(xv + t + stride), c = ld_stream(xv + t + 2 * stride),
@@ -167,7 +146,7 @@ __global__ void __launch_bounds__(kRedThreads)
     else
     {
         T a0 = T(0), a1 = T(0), a2 = T(0), a3 = T(0);
-        unsigned t = rank;
+        size_t t = rank;
         for (; t + 3 * (size_t)stride < n; t += 4 * stride)
         {
             const T a = ld_stream(x + t), b = ld_stream(x + t + stride), c = ld_stream(x + t + 2 * stride),
@@ -203,9 +182,10 @@ __global__ void set_data_kernel(T *__restrict__ data, unsigned n, int mode)
     //   mode 1: i % 8 + (0.4 + 3e-5 * (i % 100721)), the HOST generator of benchmark02.cc:143
     //           (g++: every operation rounded separately);
     //   mode 2: the mode-0 formula as the HOST computes it in benchmark02.cc:142 (no contraction).
-    const unsigned stride = gridDim.x * blockDim.x;
-    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i64 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i64 < n; i64 += stride)
     {
+        const unsigned i = (unsigned)i64; // the generators are defined on unsigned (benchmark01.cc:176-178)
         double v;
         if (mode == 1)
             v = __dadd_rn((double)(i % 8u), __dadd_rn(0.4, __dmul_rn(0.00003, (double)(i % 100721u))));
@@ -214,8 +194,6 @@ __global__ void set_data_kernel(T *__restrict__ data, unsigned n, int mode)
         else
             v = __dadd_rn((double)(i % 13u), __fma_rn(0.00001, (double)(i % 100191u), 0.2));
         data[i] = (T)v;
-        if (i + stride < i)
-            break; // unsigned wrap guard for n close to 2^32
     }
 }
 
@@ -230,14 +208,14 @@ __global__ void __launch_bounds__(256) add_vector_kernel(T *__restrict__ x, cons
     const unsigned n      = end - begin;
     T *xs                 = x + begin;
     const T *ys           = y + begin;
-    const unsigned rank   = blockIdx.x * 256u + threadIdx.x;
-    const unsigned stride = gridDim.x * 256u;
+    const size_t rank   = (size_t)blockIdx.x * 256u + threadIdx.x; // 64-bit: t += k*stride must not wrap
+    const size_t stride = (size_t)gridDim.x * 256u;
     if (VL)
     {
         const unsigned nv = n / W;
         V *xv             = reinterpret_cast<V *>(xs);
         const V *yv       = reinterpret_cast<const V *>(ys);
-        unsigned t        = rank;
+        size_t t          = rank;
         for (; t + (size_t)stride < nv; t += 2 * stride)
         {
             V a = ld_stream(xv + t), c = ld_stream(xv + t + stride);
@@ -261,7 +239,7 @@ __global__ void __launch_bounds__(256) add_vector_kernel(T *__restrict__ x, cons
     }
     else
     {
-        unsigned t = rank;
+        size_t t = rank;
         for (; t + 3 * (size_t)stride < n; t += 4 * stride)
         {
             const T a = ld_stream(xs + t), b = ld_stream(xs + t + stride), c = ld_stream(xs + t + 2 * stride),

@@ -25,6 +25,18 @@
  *     different devices; calls on one device from several streams are
  *     serialised with events where they share the per-device basis bank.
  *
+ * Numerical contract.  Every back-end but one accumulates each output over p, then q, then r in ascending order
+ * from 0 with fused multiply-adds -- the arithmetic nvcc generates for every reference variant
+ * (benchmark04.cc:55-59, benchmark05.cc:65-69) -- and is BIT-IDENTICAL to the reference kernels (FP64 and FP32).
+ * The exception is the FP32 tensor-core route (3xTF32 split; default for quad FP32 nq = 32): its products are
+ * formed from TF32 halves and summed in the tensor core's order, so it agrees with the reference to rounding:
+ *     |out - exact| <= 1e-5 * (|B1|^T |B0|^T |in|)   for every single output (component-wise; measured 2-3e-6),
+ * which implies the norm-wise bound max|out - ref| <= 1e-5 * max|ref| of the north star, but NOT a bound relative
+ * to an individual output that is itself the result of heavy cancellation (no floating-point dot product offers
+ * that; the reference's own FFMA chain satisfies the same component-wise bound with a smaller constant).
+ * b200fe_set_backend("rows") selects the bit-exact FP32 path where that matters more than speed.
+ * IProductWRTBase has no counterpart in the reference: its oracle is PARITY-UNPINNED (adjoint identity only).
+ *
  * Data layouts:  nm = nq - 1 modes per direction.
  *   element-major  in[e*nmTot + (r*nm1 + q)*nm0 + p]   out[e*nqTot + (k*nq1 + j)*nq0 + i]
  *   interleaved    x[(e/32)*32*len + 32*idx + e%32]    (idx = in-element index above)
@@ -335,6 +347,14 @@ int b200fe_bwdtrans_hex_host_f32(unsigned nq0, unsigned nq1, unsigned nq2, size_
  * B200FE_EUNSUPPORTED where the forced back-end has no instantiation.  Used by the tuner and the parity tests to
  * exercise every back-end through the same C ABI. */
 int b200fe_set_backend(const char *name);
+/* How the per-device constant bank that holds the basis matrices is rewritten before an operator call:
+ *   "kernel" (default)  a one-CTA kernel stores through the symbol's global address and the operator starts as its
+ *                       programmatic dependent (griddepcontrol.wait first, bank reads only behind a real call; the
+ *                       build fails if the shipped SASS of any kernel violates that: tools/check_sass.py);
+ *   "memcpy"            the kernel fills a staging buffer and cudaMemcpyToSymbolAsync copies it into the bank: only
+ *                       documented CUDA behaviour, ~3 us more stream time per per-call operator (plans skip the
+ *                       fill either way).  Results are bit-identical.  Process-wide; returns 0 or B200FE_EINVAL. */
+int b200fe_set_bank_fill(const char *mode);
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

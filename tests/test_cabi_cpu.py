@@ -60,37 +60,16 @@ def test_sass_is_sm100_only():
 def test_no_kernel_reads_the_constant_bank_before_its_dependency_wait():
     """Kernels launched as programmatic dependents of the constant-bank fill must not touch the bank (SASS c[0x3][..])
     before griddepcontrol.wait (SASS ACQBULK).  ptxas hoists constant loads above the wait in an inlined kernel --
-    that was a real stale-basis race -- so those kernels wait first and CALL a non-inlined body; this checks the
-    shipped SASS for it."""
-    import shutil
-    import subprocess
+    that was a real stale-basis race -- so those kernels wait first and CALL a non-inlined body.  tools/check_sass.py
+    checks the shipped SASS for it; the same scan is a mandatory step of __graft_entry__.build()."""
+    import importlib.util
     import pytest
-    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
-    if not os.path.exists(exe):
+    spec = importlib.util.spec_from_file_location("check_sass", os.path.join(fe.ROOT, "tools", "check_sass.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    try:
+        waits, bad = mod.scan(fe.LIB_PATH)
+    except FileNotFoundError:
         pytest.skip("cuobjdump not available")
-    so = os.path.join(os.path.dirname(os.path.abspath(b200fe_loader.__file__)), "gpu-benchmarking_b200", "libb200fe.so")
-    sass = subprocess.run([exe, "-sass", so], capture_output=True, text=True, check=True).stdout
-    fn, idx, state, waits, bad = None, 0, {}, 0, []
-    for line in sass.splitlines():
-        m = re.match(r"\s+Function : (\S+)", line)
-        if m:
-            fn, idx = m.group(1), 0
-            state[fn] = {"acq": None, "call": None, "bank": None}
-            continue
-        if fn and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
-            idx += 1
-            st = state[fn]
-            if "ACQBULK" in line and st["acq"] is None:
-                st["acq"] = idx
-            if "CALL" in line and st["call"] is None:
-                st["call"] = idx
-            if "c[0x3]" in line and st["bank"] is None:
-                st["bank"] = idx
-    for fn, st in state.items():
-        if st["acq"] is None:
-            continue
-        waits += 1
-        if st["acq"] > 8 or st["call"] is None or (st["bank"] is not None and st["bank"] < st["call"]):
-            bad.append((fn, st))
     assert waits >= 40, waits          # the lanes kernels are there
     assert not bad, bad[:5]

@@ -43,8 +43,11 @@ def norms(lines, key):
     return {l.split()[1]: [float(v) for v in l.split()[3:]] for l in lines if l.startswith(key) and " norm:" in l}
 
 
-def test_benchmark04_cli_log_format_and_golden_norms(golden):
-    lines = run("benchmark04", (4, 4), B200FE_NELMT="128,4096", B200FE_REPS=3, B200FE_CPU_REPS=1)
+@pytest.mark.parametrize("plan", [1, 0])
+def test_benchmark04_cli_log_format_and_golden_norms(golden, plan):
+    """plan = 1 (default): every repetition through a b200fe_plan; plan = 0: the per-call entry points"""
+    lines = run("benchmark04", (4, 4), B200FE_NELMT="128,4096", B200FE_REPS=3, B200FE_CPU_REPS=1, B200FE_PLAN=plan)
+    assert any(l.startswith("info") and ("via b200fe_plan" if plan else "per-call entry points") in l for l in lines)
     assert lines[1].startswith("Benchmark04 : BwdTrans (2D)")
     xs, ys, title = postprocess_parse(lines, "nelmt", "DOF/s", 11)
     assert xs == [128.0, 4096.0] and len(title) == 1 and "NQ = 4, 4" in title[0]
@@ -62,8 +65,10 @@ def test_benchmark04_default_arguments_are_8_8():
     assert any("NQ = 8, 8" in l for l in lines)
 
 
-def test_benchmark05_log_format_and_golden_norms(golden):
-    lines = run("benchmark05", (4, 4, 4), B200FE_NELMT="128,1024", B200FE_REPS=3, B200FE_CPU_REPS=1)
+@pytest.mark.parametrize("plan", [1, 0])
+def test_benchmark05_log_format_and_golden_norms(golden, plan):
+    lines = run("benchmark05", (4, 4, 4), B200FE_NELMT="128,1024", B200FE_REPS=3, B200FE_CPU_REPS=1, B200FE_PLAN=plan)
+    assert any(l.startswith("info") and ("via b200fe_plan" if plan else "per-call entry points") in l for l in lines)
     xs, ys, title = postprocess_parse(lines, "nelmt", "DOF/s", 11)
     assert xs == [128.0, 1024.0] and "NQ = 4, 4, 4" in title[0]
     for n, cols in norms(lines, "nelmt").items():
@@ -92,3 +97,40 @@ def test_benchmark01_03_log_format_and_golden_norms(golden, binary, key, tol):
         assert len(cols) == 5
         for got, want in zip(cols, golden[key][n]):
             assert abs(got - want) / want < tol, (binary, n, cols)
+
+
+@pytest.mark.parametrize("bench,orders,fmt", [("benchmark04", (2, 4, 6, 8, 10, 12, 14, 16, 32), "nq{0}x{0}.log"),
+                                              ("benchmark05", (2, 4, 6, 8, 10), "nq{0}x{0}x{0}.log")])
+def test_reference_run_sh_unmodified_drives_the_built_binaries(golden, bench, orders, fmt, tmp_path):
+    """The reference's run.sh, byte for byte (tests/test_driver_logs_cpu.py pins its hash): `cd build/`, the nq loop,
+    CUDA_VISIBLE_DEVICES=1, `&> ../nq*.log` (benchmark04/run.sh:3-8).  It pins device 1, so this needs a box with at
+    least two GPUs (gpurun --gpus 2); every log then goes through the parser half of postprocess.py."""
+    import shutil
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("run.sh pins CUDA_VISIBLE_DEVICES=1: needs >= 2 GPUs")
+    exe = os.path.join(ROOT, bench, "build", bench)
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", ROOT, "drivers"])
+    # a scratch copy of the benchmark directory layout run.sh expects: ./run.sh, ./build/<binary>, logs land in ./
+    work = tmp_path / bench
+    (work / "build").mkdir(parents=True)
+    shutil.copy2(os.path.join(ROOT, bench, "run.sh"), work / "run.sh")
+    os.symlink(exe, work / "build" / bench)
+    e = dict(os.environ)
+    e.update({"B200FE_NELMT": "128,4096", "B200FE_REPS": "3", "B200FE_CPU_REPS": "1"})  # env knobs pass through run.sh
+    e.pop("CUDA_VISIBLE_DEVICES", None)
+    p = subprocess.run(["bash", "run.sh"], cwd=work, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+    assert p.returncode == 0, p.stdout.decode()[-2000:]
+    assert p.stdout.decode().split() == [f"nq={n}" for n in orders]
+    kind = "quad" if bench == "benchmark04" else "hex"
+    for nq in orders:
+        lines = (work / fmt.format(nq)).read_text().splitlines()
+        xs, ys, title = postprocess_parse(lines, "nelmt", "DOF/s", 11)
+        assert xs == [128.0, 4096.0] and len(title) == 1 and f"NQ = {nq}, {nq}" in title[0], lines[-5:]
+        assert all(v > 0 and math.isfinite(v) for y in ys for v in y)
+        for n, cols in norms(lines, "nelmt").items():
+            ref = golden[kind][str(nq)][n]
+            for c, (got, want) in enumerate(zip(cols, ref)):
+                want = ref[0] if (kind == "hex" and c == 6) else want
+                assert abs(got - want) / want < 6e-10, (nq, n, c, got, want)

@@ -181,3 +181,30 @@ def test_plan_argument_errors(G):
     finally:
         plan.destroy()
     plan.destroy()                                                      # idempotent on the wrapper
+
+
+@pytest.mark.parametrize("suf", ["f64", "f32"])
+def test_documented_bank_fill_route_is_bit_identical(G, suf):
+    """b200fe_set_bank_fill("memcpy"): the basis reaches the constant bank through cudaMemcpyToSymbolAsync instead of
+    the fill kernel's stores + programmatic dependent launch (include/b200fe.h).  Same kernels, same bits -- with two
+    different bases alternating, so a stale bank would show."""
+    rng = np.random.default_rng(77)
+    dt = G.NP[suf]
+    cases = [("quad", 4, 4096), ("quad", 10, 2048), ("hex", 6, 1024)]
+    try:
+        for mode in ("memcpy", "kernel"):
+            G.fe.set_bank_fill(mode)
+            for op, nq, nelmt in cases:
+                nm, dim = nq - 1, 2 if op == "quad" else 3
+                for rep in range(3):
+                    b = [rng.standard_normal(nm * nq).astype(dt) for _ in range(dim)]
+                    inp = rng.standard_normal(nelmt * nm ** dim).astype(dt)
+                    if op == "quad":
+                        got = G.run_quad("BwdTransQuadKernel_QP_Shared", suf, nq, nq, nelmt, b[0], b[1], inp)
+                        want = oracle.bwdtrans_quad(nq, nq, nelmt, b[0], b[1], inp)
+                    else:
+                        got = G.run_hex("BwdTransHexKernel_QP_Shared", suf, (nq,) * 3, nelmt, b, inp)
+                        want = oracle.bwdtrans_hex(nq, nq, nq, nelmt, b[0], b[1], b[2], inp)
+                    assert np.array_equal(got, want), (mode, op, nq, rep, G.fe.last_backend())
+    finally:
+        G.fe.set_bank_fill("kernel")

@@ -188,6 +188,38 @@ template <typename T> struct Checksum
     }
 };
 
+// The drivers' repetition loops go through a b200fe_plan: the basis matrices are handed over ONCE per run_test -- where
+// the reference uploads them once (benchmark04.cc:890-905, benchmark05.cc:1237-1259) -- and the 40 repetitions of
+// every column reuse them, so a repetition is one kernel launch instead of staging launch + kernel.  Same kernels,
+// same bits as the per-call entry points (tests/test_plan_gpu.py).  Only for the shapes plans cover (equal nq per
+// direction, nm = nq - 1, nq <= 32); B200FE_PLAN=0 keeps every column on the per-call entry points.
+class OperatorPlan
+{
+public:
+    OperatorPlan(int dim, bool is_f32, unsigned nq0, unsigned nq1, unsigned nq2, const void *b0, const void *b1,
+                 const void *b2)
+    {
+        const bool regular = nq0 == nq1 && (dim == 2 || nq1 == nq2) && nq0 >= 2u && nq0 <= 32u;
+        if (regular && env_long("B200FE_PLAN", 1) != 0)
+            FE_OK(b200fe_plan_create(&m_plan, dim, is_f32 ? 1 : 0, nq0, b0, b1, dim == 3 ? b2 : nullptr, nullptr));
+    }
+    OperatorPlan(const OperatorPlan &)            = delete;
+    OperatorPlan &operator=(const OperatorPlan &) = delete;
+    ~OperatorPlan()
+    {
+        if (m_plan)
+            b200fe_plan_destroy(m_plan);
+    }
+    bool active() const { return m_plan != nullptr; }
+    void bwdtrans(bool coa, unsigned nelmt, const void *in, void *out) const
+    {
+        FE_OK(b200fe_plan_bwdtrans(m_plan, coa ? 1 : 0, nelmt, in, out, nullptr));
+    }
+
+private:
+    b200fe_plan *m_plan = nullptr;
+};
+
 template <typename T> double host_sumsq(const std::vector<T> &v)
 {
     long double s = 0.0L;
