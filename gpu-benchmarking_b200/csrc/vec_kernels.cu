@@ -199,60 +199,59 @@ __global__ void set_data_kernel(T *__restrict__ data, unsigned n, int mode)
 
 // ---- benchmark02 --------------------------------------------------------------------
 
+// One chunk of kAddThreads * U items per CTA, no persistent loop: on this B200 a read-modify-write stream runs at
+// 7.1-7.2 TB/s launched this way against 6.3-6.6 TB/s for the same body in a persistent grid-stride loop
+// (tools/ubench/stream_add.cu -> profiles/r02_ubench_stream_add.txt; 1024 threads, one 16-byte vector per thread and
+// array measured best) -- the CTAs of a one-shot grid drift apart in phase, so reads and writes of different CTAs mix
+// instead of arriving in waves.  n < 2^32, so the grid (n / 16-byte vectors / 1024 <= 2^21 CTAs) never needs a loop;
+// two CTAs per SM (<= 32 registers) keep 2048 threads' loads in flight.
+constexpr int kAddThreads = 1024;
 template <typename T, bool VL>
-__global__ void __launch_bounds__(256) add_vector_kernel(T *__restrict__ x, const T *__restrict__ y, unsigned begin,
-                                                         unsigned end)
+__global__ void __launch_bounds__(kAddThreads, 2) add_vector_kernel(T *__restrict__ x, const T *__restrict__ y, unsigned begin,
+                                                                 unsigned end)
 {
     using V         = typename Vec16<T>::type;
     constexpr int W = Vec16<T>::W;
-    const unsigned n      = end - begin;
-    T *xs                 = x + begin;
-    const T *ys           = y + begin;
-    const size_t rank   = (size_t)blockIdx.x * 256u + threadIdx.x; // 64-bit: t += k*stride must not wrap
-    const size_t stride = (size_t)gridDim.x * 256u;
+    const unsigned n = end - begin;
+    T *xs            = x + begin;
+    const T *ys      = y + begin;
     if (VL)
     {
-        const unsigned nv = n / W;
-        V *xv             = reinterpret_cast<V *>(xs);
-        const V *yv       = reinterpret_cast<const V *>(ys);
-        size_t t          = rank;
-        for (; t + (size_t)stride < nv; t += 2 * stride)
+        const size_t nv = n / W;
+        V *xv           = reinterpret_cast<V *>(xs);
+        const V *yv     = reinterpret_cast<const V *>(ys);
+        const size_t rank = (size_t)blockIdx.x * kAddThreads + threadIdx.x;
+        if (rank < nv)
         {
-            V a = ld_stream(xv + t), c = ld_stream(xv + t + stride);
-            const V b = ld_stream(yv + t), d = ld_stream(yv + t + stride);
-            add_acc(a, b);
-            add_acc(c, d);
-            st_stream(xv + t, a);
-            st_stream(xv + t + stride, c);
-        }
-        for (; t < nv; t += stride)
-        {
-            V a = ld_stream(xv + t);
-            add_acc(a, ld_stream(yv + t));
-            st_stream(xv + t, a);
+            V a = ld_stream(xv + rank);
+            add_acc(a, ld_stream(yv + rank));
+            st_stream(xv + rank, a);
         }
         if (rank < n % W)
         {
-            const unsigned id = n - 1u - rank; // benchmark02.cc:50-57
+            const unsigned id = n - 1u - (unsigned)rank; // benchmark02.cc:50-57
             xs[id] += ys[id];
         }
     }
     else
     {
-        size_t t = rank;
-        for (; t + 3 * (size_t)stride < n; t += 4 * stride)
+        constexpr int U    = 4; // scalars per thread, kAddThreads apart inside the CTA's chunk (coalesced)
+        const size_t chunk = (size_t)kAddThreads * U;
         {
-            const T a = ld_stream(xs + t), b = ld_stream(xs + t + stride), c = ld_stream(xs + t + 2 * stride),
-                    d = ld_stream(xs + t + 3 * stride);
-            const T e = ld_stream(ys + t), f = ld_stream(ys + t + stride), g = ld_stream(ys + t + 2 * stride),
-                    h = ld_stream(ys + t + 3 * stride);
-            st_stream(xs + t, a + e);
-            st_stream(xs + t + stride, b + f);
-            st_stream(xs + t + 2 * stride, c + g);
-            st_stream(xs + t + 3 * stride, d + h);
+            const size_t t0 = (size_t)blockIdx.x * chunk + threadIdx.x;
+            T a[U], b[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (t0 + (size_t)u * kAddThreads < n)
+                {
+                    a[u] = ld_stream(xs + t0 + (size_t)u * kAddThreads);
+                    b[u] = ld_stream(ys + t0 + (size_t)u * kAddThreads);
+                }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (t0 + (size_t)u * kAddThreads < n)
+                    st_stream(xs + t0 + (size_t)u * kAddThreads, a[u] + b[u]);
         }
-        for (; t < n; t += stride)
-            st_stream(xs + t, ld_stream(xs + t) + ld_stream(ys + t));
     }
 }
 
@@ -447,14 +446,13 @@ template <typename T> int launch_add_vector(T *x, const T *y, unsigned begin, un
     if (vl && (((reinterpret_cast<uintptr_t>(x + begin) | reinterpret_cast<uintptr_t>(y + begin)) & 15u) != 0))
         vl = false;
     const unsigned n    = end - begin;
-    const unsigned work = vl ? n / W : n;
-    // ~2 vectors (or 4 scalars) per thread per trip, at most 16 CTAs of 256 threads per SM
-    const unsigned per  = vl ? 2u : 4u;
-    const unsigned grid = clampu((work + 256u * per - 1) / (256u * per), 1u, 148u * 16u);
+    // one 16-byte vector (or 4 scalars) per thread, one chunk per CTA (see add_vector_kernel)
+    const size_t work   = vl ? (size_t)(n / W) : ((size_t)n + 3) / 4;
+    const unsigned grid = (unsigned)((work + kAddThreads - 1) / kAddThreads);
     if (vl)
-        add_vector_kernel<T, true><<<grid, 256, 0, s>>>(x, y, begin, end);
+        add_vector_kernel<T, true><<<grid < 1u ? 1u : grid, kAddThreads, 0, s>>>(x, y, begin, end);
     else
-        add_vector_kernel<T, false><<<grid, 256, 0, s>>>(x, y, begin, end);
+        add_vector_kernel<T, false><<<grid < 1u ? 1u : grid, kAddThreads, 0, s>>>(x, y, begin, end);
     count_launch();
     return launch_status();
 }
@@ -469,7 +467,7 @@ template <typename T> int launch_matvec(unsigned N, unsigned M, const T *A, cons
         vl = false;
     const bool warp_rows = N <= 2048u;
     const unsigned rows  = warp_rows ? 8u : 1u;
-    const unsigned grid  = clampu((M + rows - 1) / rows, 1u, 148u * 8u);
+    const unsigned grid  = clampu((M + rows - 1) / rows, 1u, 148u * 8u); // persistent: one row (group) per CTA up to the reference's 65535 measured 3-9 % slower
 #define MV(VL_, LANES_) matvec_kernel<T, VL_, LANES_><<<grid, 256, 0, s>>>(N, M, A, x, y)
     if (vl && warp_rows)
         MV(true, 32);
