@@ -293,6 +293,8 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
         t_last_backend = "generic";
         return launch_hex_generic<T>(nm0, nm1, nm2, nq0, nq1, nq2, nelmt, b0, b1, b2, in, out, coa, stream);
     }
+    if (be == Backend::Umma)
+        return B200FE_EUNSUPPORTED; // quad FP32 nq = 32 only
     if (!regular || ((be == Backend::Pipe || be == Backend::Mma || be == Backend::Nm1) && coa) ||
         (be == Backend::Tpe && !coa) || (be == Backend::Rows && !(have & 1)))
         return B200FE_EUNSUPPORTED;

@@ -2,6 +2,9 @@
 // Included by bwdtrans_{quad,hex}_{f64,f32}.cu with B200FE_T / B200FE_TAG set.
 #pragma once
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "dispatch.h"
@@ -16,6 +19,7 @@
 #include "sumfac_lanes.cuh"
 #include "sumfac_rows_coa.cuh"
 #include "sumfac_tpe.cuh"
+#include "sumfac_umma.cuh"
 
 namespace b200fe
 {
@@ -219,6 +223,60 @@ int launch_quad_mma(unsigned nelmt, const float *b0, const float *b1, const floa
     count_launch();
     t_last_backend = "mma";
     return launch_status();
+}
+
+// FP32 quad nq = 32 on tcgen05 (sumfac_umma.cuh): one persistent CTA per SM, 4 elements per tile; `in` 16-byte aligned
+inline int launch_quad_umma(unsigned nelmt, const float *b0, const float *b1, const float *in, float *out, cudaStream_t stream,
+                            double *partials = nullptr, unsigned *npartials = nullptr)
+{
+    static_assert(umma::SMEM <= (size_t)kSmemMax, "stages do not fit shared memory");
+    auto kernel    = umma::bwdtrans_quad32_umma_kernel<false>;
+    auto kernel_ss = umma::bwdtrans_quad32_umma_kernel<true>;
+    int rc         = opt_in_smem(kernel, umma::SMEM);
+    if (!rc && partials)
+        rc = opt_in_smem(kernel_ss, umma::SMEM);
+    if (rc)
+        return rc;
+    const unsigned ntiles = (nelmt + umma::TILE_E - 1) / umma::TILE_E;
+    const unsigned fit    = (unsigned)sm_count();
+    const unsigned grid   = ntiles < fit ? ntiles : fit;
+    if (partials && npartials)
+    {
+        kernel_ss<<<grid, umma::THREADS, umma::SMEM, stream>>>(b0, b1, in, out, nelmt, ntiles, partials, nullptr);
+        *npartials = grid * 4;
+    }
+    else if (getenv("B200FE_UMMA_PROF")) // development: per-role wait / busy cycles of CTA 0 (tools/umma_check.py)
+    {
+        auto kp = umma::bwdtrans_quad32_umma_kernel<false, true>;
+        rc      = opt_in_smem(kp, umma::SMEM);
+        if (rc)
+            return rc;
+        unsigned long long *prof = nullptr, h[40] = {};
+        cudaMalloc(&prof, sizeof(h));
+        cudaMemsetAsync(prof, 0, sizeof(h), stream);
+        kp<<<grid, umma::THREADS, umma::SMEM, stream>>>(b0, b1, in, out, nelmt, ntiles, nullptr, prof);
+        cudaMemcpyAsync(h, prof, sizeof(h), cudaMemcpyDeviceToHost, stream);
+        cudaStreamSynchronize(stream);
+        cudaFree(prof);
+        const char *role[5] = {"convert ", "epilog0 ", "epilog1 ", "producer", "mma     "};
+        const unsigned my = (ntiles + grid - 1) / grid;
+        for (int r = 0; r < 5; ++r)
+            fprintf(stderr, "umma prof %s per tile (%u tiles):%8.0f %8.0f %8.0f %8.0f %8.0f %8.0f clk\n", role[r], my,
+                    (double)h[r * 8] / my, (double)h[r * 8 + 1] / my, (double)h[r * 8 + 2] / my, (double)h[r * 8 + 3] / my,
+                    (double)h[r * 8 + 4] / my, (double)h[r * 8 + 5] / my);
+        fprintf(stderr, "umma prof producer loop: %llu clk in %llu ns = %.0f MHz\n", h[3 * 8 + 4], h[3 * 8 + 5],
+                1e3 * (double)h[3 * 8 + 4] / (double)h[3 * 8 + 5]);
+    }
+    else
+        kernel<<<grid, umma::THREADS, umma::SMEM, stream>>>(b0, b1, in, out, nelmt, ntiles, nullptr, nullptr);
+    count_launch();
+    t_last_backend = "umma";
+    return launch_status();
+}
+inline int launch_quad_umma(unsigned, const double *, const double *, const double *, double *, cudaStream_t, double * = nullptr,
+                            unsigned * = nullptr)
+{
+    return B200FE_EUNSUPPORTED; // tcgen05 has no FP64 kind: DMMA (sumfac_mma.cuh) is the FP64 tensor path
 }
 
 // ---- interleaved layout through the rows passes.  E is a power of two dividing 32 with E*sizeof(T) >= 32 bytes

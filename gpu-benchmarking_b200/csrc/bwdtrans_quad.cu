@@ -294,6 +294,8 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
             be = Backend::Nm1; // measured: 0.81 vs 0.63 (pipe) for FP32; FP64 and hex stay on the table's choice
         else if (quad_has_lanesem(nq0) && aligned16(in))
             be = Backend::Lanes;
+        else if (nq0 == 32 && sizeof(T) == 4 && aligned16(in))
+            be = Backend::Umma; // tcgen05 kind::tf32 (sumfac_umma.cuh); a misaligned `in` stays on the warp-level path
         else
             be = preferred;
         // the bulk-copy ring needs a 16-byte aligned slab; otherwise take the plain-load twin
@@ -309,7 +311,7 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
         t_last_backend = "generic";
         return launch_quad_generic<T>(nm0, nm1, nq0, nq1, nelmt, b0, b1, in, out, coa, stream);
     }
-    if (!regular || ((be == Backend::Pipe || be == Backend::Mma || be == Backend::Nm1) && coa) ||
+    if (!regular || ((be == Backend::Pipe || be == Backend::Mma || be == Backend::Nm1 || be == Backend::Umma) && coa) ||
         (be == Backend::Tpe && !coa) || (be == Backend::Rows && !(have & 1)))
         return B200FE_EUNSUPPORTED;
     if (be == Backend::Lanes && !coa && (!quad_has_lanesem(nq0) || !aligned16(in)))
@@ -318,6 +320,10 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
         return B200FE_EUNSUPPORTED;
     if (be == Backend::Nm1)
         return (nq0 == 2 && !coa) ? launch_nm1<T, 2>(nelmt, b0, b1, b1, in, out, stream) : B200FE_EUNSUPPORTED;
+    if (be == Backend::Umma)
+        return (nq0 == 32 && sizeof(T) == 4 && !coa && aligned16(in))
+                   ? launch_quad_umma(nelmt, b0, b1, in, out, stream, partials, npartials)
+                   : B200FE_EUNSUPPORTED;
     if (be == Backend::Mma) // reads the basis matrices from global memory: no constant bank, no lock
         return (have & 4) ? quad_mma_switch(nq0, nelmt, b0, b1, in, out, stream, partials, npartials) : B200FE_EUNSUPPORTED;
 

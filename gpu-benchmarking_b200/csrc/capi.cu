@@ -445,6 +445,8 @@ int b200fe_set_backend(const char *name)
         g_forced_backend = (int)Backend::Lanes;
     else if (!strcmp(name, "generic"))
         g_forced_backend = (int)Backend::Generic;
+    else if (!strcmp(name, "umma"))
+        g_forced_backend = (int)Backend::Umma;
     else
         return B200FE_EINVAL;
     return B200FE_OK;

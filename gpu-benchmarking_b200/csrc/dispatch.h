@@ -18,6 +18,7 @@ enum class Backend : int
     Lanes   = 7, // lanes = elements, an element's planes / rows split over the warps of a CTA (interleaved layout;
                  // element-major even-nq quads through a bulk-copied slab: "lanes-em")
     Mma     = 5, // FP64 tensor cores (DMMA m8n8k4), one element group per warp, bulk (TMA) fed (quad, even nq)
+    Umma    = 8, // FP32 quad nq = 32 on tcgen05.mma kind::tf32 (3xTF32 split, accumulators in TMEM): sumfac_umma.cuh
 };
 
 // element-major unless coa; return 0 / cudaError_t / negative B200FE_E*

@@ -48,7 +48,7 @@ def test_quad_every_nq_bit_exact(G, suf, nq):
         inp = rnd(rng, nelmt * nm * nm, dt)
         want = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp, use_fma=True)
         got = G.run_quad("BwdTransQuadKernel_QP_Shared", suf, nq, nq, nelmt, b0, b1, inp)
-        assert G.fe.last_backend() in ("rows", "pipe", "mma", "nm1", "lanes-em")
+        assert G.fe.last_backend() in ("rows", "pipe", "mma", "umma", "nm1", "lanes-em")
         G.assert_parity(got, want, suf, (nq, nelmt))
         plain = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp, use_fma=False)
         assert G.rel_max(got, plain) < G.TOL[suf]
@@ -489,7 +489,8 @@ def test_fused_operator_and_checksum(G, suf, dim, nq, nelmt):
         plain = G.run_hex("BwdTransHexKernel_QP_Shared", suf, (nq,) * 3, nelmt, b, inp)
     # the plain call may take another back-end (lanes-em cannot fuse); every back-end but the FP32 tensor-core one
     # is bit-identical, so the fused kernel must store exactly what the plain one does
-    if suf == "f32" and "mma" in (backend, G.fe.last_backend()) and backend != G.fe.last_backend():
+    tensor32 = {"mma", "umma"} & {backend, G.fe.last_backend()}
+    if suf == "f32" and tensor32 and backend != G.fe.last_backend():
         assert G.rel_max(results[0][0], plain) < G.TOL["f32"]
     else:
         assert np.array_equal(results[0][0], plain)

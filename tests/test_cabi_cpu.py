@@ -73,3 +73,16 @@ def test_no_kernel_reads_the_constant_bank_before_its_dependency_wait():
         pytest.skip("cuobjdump not available")
     assert waits >= 40, waits          # the lanes kernels are there
     assert not bad, bad[:5]
+
+
+def test_the_library_carries_blackwell_tensor_core_code():
+    """SASS evidence of the tcgen05 path (csrc/sumfac_umma.cuh): UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st,
+    UBLKCP = bulk (TMA) copies; DMMA = the FP64 tensor path (tcgen05 has no f64 kind)"""
+    import subprocess
+    import pytest
+    exe = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", fe.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    for op in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "DMMA", "UTCBAR"):
+        assert sass.count(op) > 0, op

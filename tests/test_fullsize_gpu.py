@@ -122,10 +122,11 @@ def test_quad_nq4_full_size_element_dependent_bit_exact(G, ref):
     assert np.array_equal(d_out.cpu().numpy(), oracle.to_coa(want, nelmt, nq * nq))
 
 
-@pytest.mark.parametrize("nq", [16, 32])
+@pytest.mark.parametrize("nq,backend", [(16, "mma"), (32, "mma"), (32, "umma")])
 @pytest.mark.parametrize("kind", ["random", "cancelling"])
-def test_fp32_tensor_core_route_componentwise_bound(G, nq, kind):
-    """quad FP32 on the tensor cores (3xTF32 split): |got - want| <= 1e-5 * (|B1|^T |B0|^T |in|) for EVERY output"""
+def test_fp32_tensor_core_route_componentwise_bound(G, nq, backend, kind):
+    """quad FP32 on the tensor cores (3xTF32 split; "mma": warp-level mma.sync, "umma": tcgen05 + TMEM, the default at
+    nq = 32): |got - want| <= 1e-5 * (|B1|^T |B0|^T |in|) for EVERY output"""
     nm, nelmt = nq - 1, 4096
     rng = np.random.default_rng(3200 + nq)
     b0 = rng.standard_normal(nm * nq).astype(np.float32)
@@ -136,10 +137,10 @@ def test_fp32_tensor_core_route_componentwise_bound(G, nq, kind):
         b0 = oracle.gen_basis(nm, nq, np.float32)
         b1 = b0.copy()
         inp = oracle.gen_in(nelmt, nm * nm, np.float32) * (1.0 + 1e-3 * rng.standard_normal(nelmt * nm * nm)).astype(np.float32)
-    G.fe.set_backend("mma")
+    G.fe.set_backend(backend)
     try:
         got = G.run_quad("BwdTransQuadKernel_QP_Shared", "f32", nq, nq, nelmt, b0, b1, inp)
-        assert G.fe.last_backend() in ("mma", "umma")
+        assert G.fe.last_backend() == backend
     finally:
         G.fe.set_backend("auto")
     # exact-ish reference and the componentwise scale, both in double
