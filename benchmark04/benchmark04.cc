@@ -18,6 +18,7 @@
 //   B200FE_NELMT=a,b,..  element counts instead of the 128..1Mi sweep
 //   B200FE_DTYPE=double|float|both     B200FE_REPS=40     B200FE_CPU_REPS=2
 //   B200FE_SKIP_CPU=1  B200FE_SKIP_CUBLAS=1
+//   B200FE_COL5=gemm  column 5 = the GEMM formulation on the library's own kernels (b200fe_gemm_bwdtrans_*) instead of cuBLAS
 //   B200FE_PLAN=0  issue every repetition through the per-call entry points instead of a b200fe_plan
 // Lines starting with "info" carry roofline figures; postprocess.py ignores them.
 #include "../utils/bench_common.h"
@@ -139,6 +140,21 @@ void run_test(const unsigned nelmt, const unsigned nq0, const unsigned nq1, cons
         });
         sumsq[4] = checksum(d_out.get(), d_out.size());
         CUBLAS_OK(cublasDestroy(handle));
+    }
+    // B200FE_COL5=gemm: the same GEMM factorisation (intermediate in global memory) on the library's own kernels
+    // instead of cuBLAS -- a cuBLAS-free column 5
+    if (env_str("B200FE_COL5", "cublas") == "gemm")
+    {
+        d_out.zero();
+        secs[4] = time_min(reps, [&] {
+            if constexpr (std::is_same<T, double>::value)
+                FE_OK(b200fe_gemm_bwdtrans_quad_f64(nm0, nm1, nq0, nq1, nelmt, d_b0.get(), d_b1.get(), d_in.get(),
+                                                    d_wsp.get(), d_out.get(), nullptr));
+            else
+                FE_OK(b200fe_gemm_bwdtrans_quad_f32(nm0, nm1, nq0, nq1, nelmt, d_b0.get(), d_b1.get(), d_in.get(),
+                                                    d_wsp.get(), d_out.get(), nullptr));
+        });
+        sumsq[4] = checksum(d_out.get(), d_out.size());
     }
 
     // ---- columns 6-11: the six kernel entry points ----------------------------------------------

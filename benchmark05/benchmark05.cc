@@ -133,6 +133,21 @@ void run_test(const unsigned nelmt, const unsigned nq0, const unsigned nq1, cons
         sumsq[4] = checksum(d_out.get(), d_out.size());
         CUBLAS_OK(cublasDestroy(handle));
     }
+    // B200FE_COL5=gemm: the same GEMM factorisation (intermediates in global memory) on the library's own kernels
+    // instead of cuBLAS -- a cuBLAS-free column 5
+    if (env_str("B200FE_COL5", "cublas") == "gemm")
+    {
+        d_out.zero();
+        secs[4] = time_min(reps, [&] {
+            if constexpr (std::is_same<T, double>::value)
+                FE_OK(b200fe_gemm_bwdtrans_hex_f64(nm0, nm1, nm2, nq0, nq1, nq2, nelmt, d_b0.get(), d_b1.get(), d_b2.get(),
+                                                   d_in.get(), d_wsp1.get(), d_wsp2.get(), d_out.get(), nullptr));
+            else
+                FE_OK(b200fe_gemm_bwdtrans_hex_f32(nm0, nm1, nm2, nq0, nq1, nq2, nelmt, d_b0.get(), d_b1.get(), d_b2.get(),
+                                                   d_in.get(), d_wsp1.get(), d_wsp2.get(), d_out.get(), nullptr));
+        });
+        sumsq[4] = checksum(d_out.get(), d_out.size());
+    }
 
     using A = Api<T>;
     const OperatorPlan plan(3, sizeof(T) == 4, nq0, nq1, nq2, d_b0.get(), d_b1.get(), d_b2.get());

@@ -166,6 +166,29 @@ def compute_matvec(suf, N, M, A, x, y, vl, stream=0):
     _check(name, getattr(lib(), name)(_u(N), _u(M), _vp(A), _vp(x), _vp(y), ctypes.c_int(int(vl)), _vp(stream)))
 
 
+def gemm_bwdtrans(suf, nq, nelmt, bases, inp, out, wsp, stream=0, nm=None):
+    """BwdTrans in its GEMM formulation (b200fe_gemm_bwdtrans_*); nq: tuple of 2 or 3; wsp: 1 (quad) or 2 (hex) DEVICE
+    scratch addresses"""
+    nm = [n - 1 for n in nq] if nm is None else list(nm)
+    if len(nq) == 2:
+        name = f"b200fe_gemm_bwdtrans_quad_{suf}"
+        rc = getattr(lib(), name)(_u(nm[0]), _u(nm[1]), _u(nq[0]), _u(nq[1]), _u(nelmt), _vp(bases[0]), _vp(bases[1]),
+                                  _vp(inp), _vp(wsp[0]), _vp(out), _vp(stream))
+    else:
+        name = f"b200fe_gemm_bwdtrans_hex_{suf}"
+        rc = getattr(lib(), name)(_u(nm[0]), _u(nm[1]), _u(nm[2]), _u(nq[0]), _u(nq[1]), _u(nq[2]), _u(nelmt),
+                                  _vp(bases[0]), _vp(bases[1]), _vp(bases[2]), _vp(inp), _vp(wsp[0]), _vp(wsp[1]), _vp(out),
+                                  _vp(stream))
+    _check(name, rc)
+
+
+def matvec_batched(suf, M, N, batch, A, strideA, x, stridex, y, stridey, stream=0):
+    name = f"b200fe_matvec_batched_{suf}"
+    z = ctypes.c_size_t
+    _check(name, getattr(lib(), name)(_u(M), _u(N), z(int(batch)), _vp(A), z(int(strideA)), _vp(x), z(int(stridex)), _vp(y),
+                                      z(int(stridey)), _vp(stream)))
+
+
 def sumsq_scratch_bytes():
     return int(lib().b200fe_sumsq_scratch_bytes())
 

@@ -576,6 +576,39 @@ HEX_NOWSP(BwdTransHexKernel_QP_1D_Shared, f32, float, Backend::Auto)
 VEC_API(f64, double)
 VEC_API(f32, float)
 
+// ---- GEMM formulation and batched small mat-vec (gemm_form.cu) -------------------------------
+#define GEMM_API(SUF, T)                                                                                     \
+    int b200fe_gemm_bwdtrans_quad_##SUF(unsigned nm0, unsigned nm1, unsigned nq0, unsigned nq1,              \
+                                        unsigned nelmt, const T *basis0, const T *basis1, const T *in,       \
+                                        T *wsp, T *out, void *stream)                                        \
+    {                                                                                                        \
+        if (misaligned(basis0) || misaligned(basis1) || misaligned(in) || misaligned(wsp) || misaligned(out)) \
+            return B200FE_EALIGN;                                                                            \
+        return launch_gemm_bwdtrans_quad<T>(nm0, nm1, nq0, nq1, nelmt, basis0, basis1, in, wsp, out,         \
+                                            (cudaStream_t)stream);                                           \
+    }                                                                                                        \
+    int b200fe_gemm_bwdtrans_hex_##SUF(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nq0,               \
+                                       unsigned nq1, unsigned nq2, unsigned nelmt, const T *basis0,          \
+                                       const T *basis1, const T *basis2, const T *in, T *wsp1, T *wsp2,      \
+                                       T *out, void *stream)                                                 \
+    {                                                                                                        \
+        if (misaligned(basis0) || misaligned(basis1) || misaligned(basis2) || misaligned(in) ||              \
+            misaligned(wsp1) || misaligned(wsp2) || misaligned(out))                                         \
+            return B200FE_EALIGN;                                                                            \
+        return launch_gemm_bwdtrans_hex<T>(nm0, nm1, nm2, nq0, nq1, nq2, nelmt, basis0, basis1, basis2, in,  \
+                                           wsp1, wsp2, out, (cudaStream_t)stream);                           \
+    }                                                                                                        \
+    int b200fe_matvec_batched_##SUF(unsigned M, unsigned N, size_t batch, const T *A, size_t strideA,        \
+                                    const T *x, size_t stridex, T *y, size_t stridey, void *stream)          \
+    {                                                                                                        \
+        if (misaligned(A) || misaligned(x) || misaligned(y))                                                 \
+            return B200FE_EALIGN;                                                                            \
+        return launch_matvec_batched<T>(M, N, batch, A, strideA, x, stridex, y, stridey,                     \
+                                        (cudaStream_t)stream);                                               \
+    }
+GEMM_API(f64, double)
+GEMM_API(f32, float)
+
 size_t b200fe_sumsq_scratch_bytes(void)
 {
     return sumsq_scratch_bytes();

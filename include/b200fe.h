@@ -293,6 +293,38 @@ int b200fe_IProductWRTBaseHex_f32(unsigned nm0, unsigned nm1, unsigned nm2, unsi
                                   const float *basis2, const float *weights, const float *in, float *out,
                                   void *stream);
 
+/* ---- GEMM formulation and batched small mat-vec (extension) ----
+ * b200fe_gemm_bwdtrans_*: BwdTrans as one contraction per pass with the intermediates in GLOBAL memory -- the
+ * factorisation the reference hands to cuBLAS for its "cuBLAS" log column (benchmark04.cc:804-820:
+ * gemm(N,N, nq0, nm1*nelmt, nm0) + gemmStridedBatched(N,T, nq0, nq1, nm1); benchmark05.cc:1128-1153) -- on this
+ * library's own kernels: a cuBLAS-free comparator for column 5 (drivers: B200FE_COL5=gemm) that shows what NOT
+ * fusing the passes costs.  Directions run 0 -> 1 -> 2 and every output is accumulated in ascending index order with
+ * fused multiply-adds: bit-identical to the BwdTrans entry points (cuBLAS agrees to rounding only).  Element-major
+ * layouts; any nm, nq <= 1024 (quad) / 256 (hex) whose basis + tile fit shared memory.
+ *   quad  wsp:  nelmt*nq0*nm1 values                     hex  wsp1: nelmt*nq0*nm1*nm2,  wsp2: nelmt*nq0*nq1*nm2 */
+int b200fe_gemm_bwdtrans_quad_f64(unsigned nm0, unsigned nm1, unsigned nq0, unsigned nq1, unsigned nelmt,
+                                  const double *basis0, const double *basis1, const double *in, double *wsp,
+                                  double *out, void *stream);
+int b200fe_gemm_bwdtrans_quad_f32(unsigned nm0, unsigned nm1, unsigned nq0, unsigned nq1, unsigned nelmt,
+                                  const float *basis0, const float *basis1, const float *in, float *wsp, float *out,
+                                  void *stream);
+int b200fe_gemm_bwdtrans_hex_f64(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nq0, unsigned nq1, unsigned nq2,
+                                 unsigned nelmt, const double *basis0, const double *basis1, const double *basis2,
+                                 const double *in, double *wsp1, double *wsp2, double *out, void *stream);
+int b200fe_gemm_bwdtrans_hex_f32(unsigned nm0, unsigned nm1, unsigned nm2, unsigned nq0, unsigned nq1, unsigned nq2,
+                                 unsigned nelmt, const float *basis0, const float *basis1, const float *basis2,
+                                 const float *in, float *wsp1, float *wsp2, float *out, void *stream);
+/* Batched small dense mat-vec, benchmark03's operator (compute_matvec, benchmark03/benchmark03.cc:80-104) for many
+ * small matrices in one launch:  y_b[i] = sum_j A_b[i*N + j] x_b[j],  b < batch.  Row-major M x N matrices strideA
+ * values apart (0: the same matrix for every b), vectors stridex / stridey values apart.  Sums in ascending j with
+ * fused multiply-adds (deterministic).  One matrix + vector must fit a CTA's shared memory (M*(N+1)+N values);
+ * larger matrices are b200fe_compute_matvec_*'s job and return B200FE_EUNSUPPORTED here.  Not in the reference
+ * (its benchmark03 multiplies one large matrix): parity is against the oracle's own restatement. */
+int b200fe_matvec_batched_f64(unsigned M, unsigned N, size_t batch, const double *A, size_t strideA, const double *x,
+                              size_t stridex, double *y, size_t stridey, void *stream);
+int b200fe_matvec_batched_f32(unsigned M, unsigned N, size_t batch, const float *A, size_t strideA, const float *x,
+                              size_t stridex, float *y, size_t stridey, void *stream);
+
 /* ---- plans: basis matrices uploaded once for many calls (extension) ----------------
  * The reference passes basis0/1/2 to every launch (benchmark04.cc:912-1001,
  * benchmark05.cc:1262-1385) and its kernels re-read them per CTA; the entry points

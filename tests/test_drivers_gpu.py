@@ -134,3 +134,16 @@ def test_reference_run_sh_unmodified_drives_the_built_binaries(golden, bench, or
             for c, (got, want) in enumerate(zip(cols, ref)):
                 want = ref[0] if (kind == "hex" and c == 6) else want
                 assert abs(got - want) / want < 6e-10, (nq, n, c, got, want)
+
+
+def test_column5_without_cublas(golden):
+    """B200FE_COL5=gemm: column 5 from b200fe_gemm_bwdtrans_* (same factorisation as the reference's cuBLAS calls,
+    benchmark04.cc:804-820 / benchmark05.cc:1128-1153), golden norms as every other column"""
+    for binary, args, kind, key in (("benchmark04", (8, 8), "quad", "8"), ("benchmark05", (6, 6, 6), "hex", "6")):
+        lines = run(binary, args, B200FE_NELMT="128,2048", B200FE_REPS=3, B200FE_SKIP_CPU=1, B200FE_SKIP_CUBLAS=1,
+                    B200FE_COL5="gemm")
+        xs, ys, _ = postprocess_parse(lines, "nelmt", "DOF/s", 11)
+        assert all(y[4] > 0 and math.isfinite(y[4]) for y in ys)
+        for n, cols in norms(lines, "nelmt").items():
+            want = golden[kind][key][n][0]
+            assert abs(cols[4] - want) / want < 6e-10, (binary, n, cols[4], want)
