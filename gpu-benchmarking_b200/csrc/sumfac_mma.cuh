@@ -58,12 +58,18 @@ constexpr int mma_mid_stride(int nq)
 // pass_data_rows: A = data.  nrows rows of NM values, row r at src + r*NM (contiguous rows: the raw
 // element-major slab), contracted with the basis fragments fragB[ks][nt]; output (row, i) to
 // dst + row*DS + i (shared memory).  MB m-tiles (8 rows each) share every B fragment.
-template <int NQ, int DS, int MB>
+// SWZ (NQ == 8 only): the destination rows are unpadded (DS == 8) and column i of row `row` is stored at
+// i ^ (4 * ((row >> 1) & 1)): the double2 stores of a quarter warp (2 consecutive rows x 4 column pairs) and the scalar
+// loads of the next pass's B fragments (4 consecutive rows x 4 columns per half warp) are both bank-conflict free, which
+// no padding achieves (stride 12 served the loads and left the stores 2-way conflicted), and the tile is a third smaller.
+template <int NQ, int DS, int MB, bool SWZ = false>
 __device__ __forceinline__ void mma_pass_data_rows(const double *__restrict__ src, const double *__restrict__ fragB,
                                                    double *__restrict__ dst, int nrows, int lane)
 {
     constexpr int NM = NQ - 1, KS = (NM + 3) / 4, NT = (NQ + 7) / 8;
+    static_assert(!SWZ || (NQ == 8 && DS == 8), "the swizzle is defined for 8-wide unpadded rows");
     const int r = lane >> 2, c = lane & 3;
+    const int cs = SWZ ? ((2 * c) ^ (4 * ((r >> 1) & 1))) : 2 * c; // 8 * tile + r keeps bit 1 of the row
 #pragma unroll 1
     for (int mt = 0; mt * 8 < nrows; mt += MB)
     {
@@ -104,7 +110,7 @@ __device__ __forceinline__ void mma_pass_data_rows(const double *__restrict__ sr
             const int row = (mt + m) * 8 + r;
             if (row < nrows)
             {
-                double *mp = dst + row * DS + 2 * c;
+                double *mp = dst + row * DS + cs;
 #pragma unroll
                 for (int n = 0; n < NT; ++n)
                     if (8 * n + 2 * c < NQ)
@@ -118,12 +124,13 @@ __device__ __forceinline__ void mma_pass_data_rows(const double *__restrict__ sr
 // data is the B operand: column n of ncols decomposes as (g, w) = (n / W, n % W) and its K values lie
 // STRIDE apart: src + (g*NM + k)*STRIDE + w.  Output (m, n) goes to dst + g*DG + m*DM + w, i.e. each
 // lane holds two values adjacent in w: one 16-byte store, to shared memory or (streaming) to global.
-template <int NQ, int W, int STRIDE, int DG, int DM, int NB, bool TO_GLOBAL, bool SUMSQ = false>
+template <int NQ, int W, int STRIDE, int DG, int DM, int NB, bool TO_GLOBAL, bool SUMSQ = false, bool SWZ_SRC = false>
 __device__ __forceinline__ void mma_pass_basis_rows(const double *__restrict__ src, const double *__restrict__ fragA,
                                                     double *__restrict__ dst, int ncols, bool vec, int lane, double &ss)
 {
     constexpr int NM = NQ - 1, KS = (NM + 3) / 4, MT = (NQ + 7) / 8;
     static_assert(W % 2 == 0, "outputs are paired along w");
+    static_assert(!SWZ_SRC || (W == 8 && STRIDE == 8), "the swizzled source has 8-wide unpadded rows");
     const int r = lane >> 2, c = lane & 3;
 #pragma unroll 1
     for (int nt = 0; nt * 8 < ncols; nt += NB)
@@ -137,6 +144,8 @@ __device__ __forceinline__ void mma_pass_basis_rows(const double *__restrict__ s
             const int nc = n < ncols ? n : ncols - 1;
             const int g = nc / W, w = nc - g * W;
             bp[t] = src + (g * NM + c) * STRIDE + w;
+            if (SWZ_SRC) // row g*NM + c + 4*ks: bit 1 of the row index picks the column half (4*ks keeps bit 1 only for even ks)
+                bp[t] = src + (g * NM + c) * STRIDE; // the column is added per k step below
 #pragma unroll
             for (int m = 0; m < MT; ++m)
                 acc[m][t][0] = acc[m][t][1] = 0.0;
@@ -151,10 +160,18 @@ __device__ __forceinline__ void mma_pass_basis_rows(const double *__restrict__ s
 #pragma unroll
             for (int t = 0; t < NB; ++t)
             {
+                int col = 0;
+                if (SWZ_SRC)
+                {
+                    const int n  = (nt + t) * 8 + r;
+                    const int nc = n < ncols ? n : ncols - 1;
+                    const int g = nc / W, w = nc - g * W, row = g * NM + c + 4 * ks;
+                    col = w ^ (4 * ((row >> 1) & 1));
+                }
                 if (4 * ks + 3 < NM)
-                    b[t] = bp[t][4 * ks * STRIDE];
+                    b[t] = bp[t][4 * ks * STRIDE + col];
                 else
-                    b[t] = (4 * ks + c < NM) ? bp[t][4 * ks * STRIDE] : 0.0; // rows >= nm do not exist
+                    b[t] = (4 * ks + c < NM) ? bp[t][4 * ks * STRIDE + col] : 0.0; // rows >= nm do not exist
             }
 #pragma unroll
             for (int m = 0; m < MT; ++m)
@@ -210,16 +227,17 @@ __device__ __forceinline__ void dmma884_ordered(double (&c)[2], double a, double
                  : "d"(a), "d"(b));
 }
 
-template <int NQ, int DS, int MB, int NROWS>
+template <int NQ, int DS, int MB, int NROWS, bool SWZ = false>
 __device__ __forceinline__ void mma_pass_data_rows_full(const double *__restrict__ src,
                                                         const double *__restrict__ fragB, double *__restrict__ dst,
                                                         int lane)
 {
     constexpr int NM = NQ - 1, KS = (NM + 3) / 4, NT = (NQ + 7) / 8, MT = (NROWS + 7) / 8;
     constexpr int NBLK = (MT + MB - 1) / MB;
+    static_assert(!SWZ || (NQ == 8 && DS == 8), "the swizzle is defined for 8-wide unpadded rows");
     const int r = lane >> 2, c = lane & 3;
     const double *abase = src + r * NM + c;   // row (8*mt + r), column c
-    double *dbase       = dst + r * DS + 2 * c;
+    double *dbase       = dst + r * DS + (SWZ ? ((2 * c) ^ (4 * ((r >> 1) & 1))) : 2 * c);
     const bool kpad     = c >= NM - 4 * (KS - 1); // this lane's column of the last k step is padding
 
     double b[KS][NT]; // the basis fragments are the same for every block: loaded once per pass
@@ -284,7 +302,8 @@ __device__ __forceinline__ void mma_pass_data_rows_full(const double *__restrict
 
 // needs NCOLS % 8 == 0.  A tile of 8 columns may straddle two groups when W % 8 != 0: the lanes past
 // the group boundary then add one compile-time constant to their address (a predicated add per tile).
-template <int NQ, int W, int STRIDE, int DG, int DM, int NB, bool TO_GLOBAL, bool VEC, int NCOLS, bool SUMSQ = false>
+template <int NQ, int W, int STRIDE, int DG, int DM, int NB, bool TO_GLOBAL, bool VEC, int NCOLS, bool SUMSQ = false,
+          bool SWZ_SRC = false>
 __device__ __forceinline__ void mma_pass_basis_rows_full(const double *__restrict__ src,
                                                          const double *__restrict__ fragA, double *__restrict__ dst,
                                                          int lane, double &ss)
@@ -292,8 +311,14 @@ __device__ __forceinline__ void mma_pass_basis_rows_full(const double *__restric
     constexpr int NM = NQ - 1, KS = (NM + 3) / 4, MT = (NQ + 7) / 8, NTT = NCOLS / 8;
     constexpr int NBLK = (NTT + NB - 1) / NB;
     static_assert(W % 2 == 0 && NCOLS % 8 == 0, "whole tiles, outputs paired along w");
+    static_assert(!SWZ_SRC || (W == 8 && STRIDE == 8), "the swizzled source has 8-wide unpadded rows");
     const int r = lane >> 2, c = lane & 3;
     const double *bbase = src + c * STRIDE + r;    // k row c, column r of tile 0
+    // swizzled source: this lane's k row is (compile-time base) + c and bit 1 of the row index picks the column half:
+    // one per-lane base address for each residue of the compile-time base modulo 4
+    const int t0 = (c >> 1) & 1, t1 = ((c + 1) >> 1) & 1;
+    const double *bbs[4] = {src + c * STRIDE + (r ^ (4 * t0)), src + c * STRIDE + (r ^ (4 * t1)),
+                            src + c * STRIDE + (r ^ (4 * (t0 ^ 1))), src + c * STRIDE + (r ^ (4 * (t1 ^ 1)))};
     double *dbase       = dst + r * DM + 2 * c;    // output row r, column pair c
     const bool kpad     = c >= NM - 4 * (KS - 1);
 
@@ -316,6 +341,8 @@ __device__ __forceinline__ void mma_pass_basis_rows_full(const double *__restric
 #pragma unroll
                 for (int ks = 0; ks < KS; ++ks)
                 {
+                    if (SWZ_SRC) // W == 8: a tile never straddles groups
+                        bb = bbs[(g * NM + 4 * ks) & 3];
                     if (4 * ks + 3 < NM)
                         dstB[t][ks] = bb[(g * NM + 4 * ks) * STRIDE + w0];
                     else
@@ -371,16 +398,17 @@ __device__ __forceinline__ void mma_pass_basis_rows_full(const double *__restric
 }
 
 // dispatch: unrolled twin for a full group where the shape allows it, generic loops otherwise
-template <int NQ, int DS, int MB, int NROWS>
+template <int NQ, int DS, int MB, int NROWS, bool SWZ = false>
 __device__ __forceinline__ void mma_dir_data(const double *__restrict__ src, const double *__restrict__ fragB,
                                              double *__restrict__ dst, int nrows, int lane)
 {
     if (nrows == NROWS)
-        mma_pass_data_rows_full<NQ, DS, MB, NROWS>(src, fragB, dst, lane);
+        mma_pass_data_rows_full<NQ, DS, MB, NROWS, SWZ>(src, fragB, dst, lane);
     else
-        mma_pass_data_rows<NQ, DS, MB>(src, fragB, dst, nrows, lane);
+        mma_pass_data_rows<NQ, DS, MB, SWZ>(src, fragB, dst, nrows, lane);
 }
-template <int NQ, int W, int STRIDE, int DG, int DM, int NB, bool TO_GLOBAL, int NCOLS, bool SUMSQ = false>
+template <int NQ, int W, int STRIDE, int DG, int DM, int NB, bool TO_GLOBAL, int NCOLS, bool SUMSQ = false,
+          bool SWZ_SRC = false>
 __device__ __forceinline__ void mma_dir_basis(const double *__restrict__ src, const double *__restrict__ fragA,
                                               double *__restrict__ dst, int ncols, bool vec, int lane, double &ss)
 {
@@ -389,15 +417,15 @@ __device__ __forceinline__ void mma_dir_basis(const double *__restrict__ src, co
         if (ncols == NCOLS)
         {
             if (vec)
-                mma_pass_basis_rows_full<NQ, W, STRIDE, DG, DM, NB, TO_GLOBAL, true, NCOLS, SUMSQ>(src, fragA, dst, lane,
-                                                                                                ss);
+                mma_pass_basis_rows_full<NQ, W, STRIDE, DG, DM, NB, TO_GLOBAL, true, NCOLS, SUMSQ, SWZ_SRC>(src, fragA, dst,
+                                                                                                         lane, ss);
             else
-                mma_pass_basis_rows_full<NQ, W, STRIDE, DG, DM, NB, TO_GLOBAL, false, NCOLS, SUMSQ>(src, fragA, dst, lane,
-                                                                                                 ss);
+                mma_pass_basis_rows_full<NQ, W, STRIDE, DG, DM, NB, TO_GLOBAL, false, NCOLS, SUMSQ, SWZ_SRC>(src, fragA, dst,
+                                                                                                          lane, ss);
             return;
         }
     }
-    mma_pass_basis_rows<NQ, W, STRIDE, DG, DM, NB, TO_GLOBAL, SUMSQ>(src, fragA, dst, ncols, vec, lane, ss);
+    mma_pass_basis_rows<NQ, W, STRIDE, DG, DM, NB, TO_GLOBAL, SUMSQ, SWZ_SRC>(src, fragA, dst, ncols, vec, lane, ss);
 }
 
 // this warp's share of the fused checksum -> partials[global warp index] (xor-shuffle: fixed order)
@@ -572,7 +600,8 @@ template <int NQ, int G, int WARPS, int MB0, int NB> struct HexMma
     static constexpr int NQ3  = NQ2 * NQ;
     static constexpr int KS   = (NM + 3) / 4;
     static constexpr int NT   = (NQ + 7) / 8;
-    static constexpr int S1   = mma_mid_stride(NQ); // s1[(e,r,q)][i]
+    static constexpr bool SWZ = NQ == 8;             // 8-wide rows: unpadded + XOR swizzle instead of padding (mma_pass_data_rows)
+    static constexpr int S1   = SWZ ? NQ : mma_mid_stride(NQ); // s1[(e,r,q)][i]
     static constexpr int S2   = mma_s2_stride(NQ);  // s2[(e,r)][j*nq + i]
     static constexpr int SLOT = (G * NM3 + 1 + 3 + 1) / 2 * 2;
     static constexpr int MID1 = G * NM2 * S1;
@@ -632,12 +661,13 @@ __global__ void __launch_bounds__(WARPS * 32)
             parity ^= 1u;
         }
         // direction 0: s1[(e,r,q)][i] = sum_p in[(e,r,q)][p] B0[p][i]
-        mma_dir_data<NQ, C::S1, MB0, G * C::NM2>(s_in, frag0, s1, ne * C::NM2, lane);
+        mma_dir_data<NQ, C::S1, MB0, G * C::NM2, C::SWZ>(s_in, frag0, s1, ne * C::NM2, lane);
         __syncwarp();
         if (g + nw < ngroups)
             by_bar = mma_fetch_group<G, C::NM3>(slot, bar, in, g + nw, nelmt, lane);
         // direction 1: s2[(e,r)][j][i] = sum_q B1[q][j] s1[(e,r)][q][i]
-        mma_dir_basis<NQ, NQ, C::S1, C::S2, NQ, NB, false, G * NM * NQ>(s1, frag1, s2, ne * NM * NQ, true, lane, ss);
+        mma_dir_basis<NQ, NQ, C::S1, C::S2, NQ, NB, false, G * NM * NQ, false, C::SWZ>(s1, frag1, s2, ne * NM * NQ, true, lane,
+                                                                                      ss);
         __syncwarp();
         // direction 2: out[e][k][(j,i)] = sum_r B2[r][k] s2[e][r][(j,i)]
         mma_dir_basis<NQ, C::NQ2, C::S2, C::NQ3, C::NQ2, NB, true, G * C::NQ2, SUMSQ>(
