@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "dispatch.h"
 #include "sumfac_generic.cuh"
@@ -226,9 +227,15 @@ int launch_quad_mma(unsigned nelmt, const float *b0, const float *b1, const floa
 }
 
 // FP32 quad nq = 32 on tcgen05 (sumfac_umma.cuh): one persistent CTA per SM, 4 elements per tile; `in` 16-byte aligned
-inline int launch_quad_umma(unsigned nelmt, const float *b0, const float *b1, const float *in, float *out, cudaStream_t stream,
-                            double *partials = nullptr, unsigned *npartials = nullptr)
+// (a template so that the kernels are instantiated only in the translation unit that calls it with float)
+template <typename T>
+int launch_quad_umma(unsigned nelmt, const T *b0, const T *b1, const T *in, T *out, cudaStream_t stream,
+                     double *partials = nullptr, unsigned *npartials = nullptr)
 {
+    if constexpr (!std::is_same<T, float>::value)
+        return B200FE_EUNSUPPORTED; // tcgen05 has no FP64 kind: DMMA (sumfac_mma.cuh) is the FP64 tensor path
+    else
+    {
     static_assert(umma::SMEM <= (size_t)kSmemMax, "stages do not fit shared memory");
     auto kernel    = umma::bwdtrans_quad32_umma_kernel<false>;
     auto kernel_ss = umma::bwdtrans_quad32_umma_kernel<true>;
@@ -272,11 +279,7 @@ inline int launch_quad_umma(unsigned nelmt, const float *b0, const float *b1, co
     count_launch();
     t_last_backend = "umma";
     return launch_status();
-}
-inline int launch_quad_umma(unsigned, const double *, const double *, const double *, double *, cudaStream_t, double * = nullptr,
-                            unsigned * = nullptr)
-{
-    return B200FE_EUNSUPPORTED; // tcgen05 has no FP64 kind: DMMA (sumfac_mma.cuh) is the FP64 tensor path
+    }
 }
 
 // ---- interleaved layout through the rows passes.  E is a power of two dividing 32 with E*sizeof(T) >= 32 bytes

@@ -322,7 +322,7 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
         return (nq0 == 2 && !coa) ? launch_nm1<T, 2>(nelmt, b0, b1, b1, in, out, stream) : B200FE_EUNSUPPORTED;
     if (be == Backend::Umma)
         return (nq0 == 32 && sizeof(T) == 4 && !coa && aligned16(in))
-                   ? launch_quad_umma(nelmt, b0, b1, in, out, stream, partials, npartials)
+                   ? launch_quad_umma<T>(nelmt, b0, b1, in, out, stream, partials, npartials)
                    : B200FE_EUNSUPPORTED;
     if (be == Backend::Mma) // reads the basis matrices from global memory: no constant bank, no lock
         return (have & 4) ? quad_mma_switch(nq0, nelmt, b0, b1, in, out, stream, partials, npartials) : B200FE_EUNSUPPORTED;
