@@ -203,6 +203,26 @@ static int hex_lanes_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cu
     }
 }
 
+// interleaved layout, coa-pipe back-end (sumfac_coapipe.cuh): FP64 at the nq where a plane of the element no longer
+// fits the registers of a lanes worker.  tools/tune/lanes_probe.cu at 64 Mi points (profiles/r02_coa_probe.csv):
+//   nq = 10   lanes (q-outer) 0.49   coa-pipe 0.72 (16 elements per tile = whole 128-byte lines, 50 workers, 1 CTA / SM)
+//   nq =  8   lanes (planes)  0.81   coa-pipe 0.87 ( 8 elements per tile, 32 workers, 3 CTAs / SM)
+static bool hex_has_coapipe(unsigned nq)
+{
+    return sizeof(T) == 8 && (nq == 8 || nq == 10);
+}
+static int hex_coapipe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cudaStream_t s)
+{
+    if constexpr (sizeof(T) == 8)
+    {
+        if (nq == 10)
+            return launch_hex_coapipe<T, 10, 16, 50, 1>(nelmt, in, out, s);
+        if (nq == 8)
+            return launch_hex_coapipe<T, 8, 8, 32, 2>(nelmt, in, out, s);
+    }
+    return B200FE_EUNSUPPORTED;
+}
+
 // element-major lanes kernel (sumfac_lanes.cuh, "lanes-em"): even nq where it measured faster than the table's choice
 // at 64 Mi points (tools/tune/lanesem_probe.cu, profiles/r01_lanesem_probe.csv; fraction of the HBM roofline):
 //   FP64  nq   4     6          FP32  nq   4     6     8
@@ -274,6 +294,7 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
             be = Backend::Generic;
         else if (coa)
             be = (nq0 < kHexLanesMinNq || (nq0 == 5 && sizeof(T) == 8)) ? Backend::Tpe // FP64 nq = 5: 0.94 against 0.88
+                 : hex_has_coapipe(nq0)  ? Backend::Pipe
                  : nq0 <= kHexLanesMaxNq ? Backend::Lanes
                                          : ((have & 1) ? Backend::Rows : Backend::Generic);
         else if (hex_has_lanesem(nq0) && aligned16(in))
@@ -281,8 +302,10 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
         else
             be = preferred;
         // the bulk-copy ring needs a 16-byte aligned slab; otherwise take the plain-load twin
-        if (be == Backend::Pipe && (!(have & 2) || !aligned16(in)))
+        if (be == Backend::Pipe && !coa && (!(have & 2) || !aligned16(in)))
             be = (have & 1) ? Backend::Rows : Backend::Generic;
+        if (be == Backend::Pipe && coa && !aligned16(in)) // 16-byte cp.async chunks
+            be = Backend::Lanes;
         if (be == Backend::Mma && !(have & 4))
             be = (have & 1) ? Backend::Rows : Backend::Generic;
         if (be == Backend::Rows && !(have & 1))
@@ -295,12 +318,14 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
     }
     if (be == Backend::Umma)
         return B200FE_EUNSUPPORTED; // quad FP32 nq = 32 only
-    if (!regular || ((be == Backend::Pipe || be == Backend::Mma || be == Backend::Nm1) && coa) ||
-        (be == Backend::Tpe && !coa) || (be == Backend::Rows && !(have & 1)))
+    if (!regular || ((be == Backend::Mma || be == Backend::Nm1) && coa) || (be == Backend::Tpe && !coa) ||
+        (be == Backend::Rows && !(have & 1)))
+        return B200FE_EUNSUPPORTED;
+    if (be == Backend::Pipe && coa && (!hex_has_coapipe(nq0) || !aligned16(in)))
         return B200FE_EUNSUPPORTED;
     if (be == Backend::Lanes && !coa && (!hex_has_lanesem(nq0) || !aligned16(in)))
         return B200FE_EUNSUPPORTED; // the bulk copy of the slab needs a 16-byte aligned `in`
-    if (be == Backend::Pipe && (!(have & 2) || !aligned16(in)))
+    if (be == Backend::Pipe && !coa && (!(have & 2) || !aligned16(in)))
         return B200FE_EUNSUPPORTED;
     if (be == Backend::Nm1)
         return (nq0 == 2 && !coa) ? launch_nm1<T, 3>(nelmt, b0, b1, b2, in, out, stream) : B200FE_EUNSUPPORTED;
@@ -315,7 +340,7 @@ int run_bwdtrans_hex<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsign
     if (be == Backend::Rows)
         rc = coa ? hex_rowscoa_switch(nq0, nelmt, in, out, stream) : hex_rows_switch(nq0, nelmt, in, out, stream);
     else if (be == Backend::Pipe)
-        rc = hex_pipe_switch(nq0, nelmt, in, out, stream);
+        rc = coa ? hex_coapipe_switch(nq0, nelmt, in, out, stream) : hex_pipe_switch(nq0, nelmt, in, out, stream);
     else if (be == Backend::Lanes)
         rc = coa ? hex_lanes_switch(nq0, nelmt, in, out, stream) : hex_lanesem_switch(nq0, nelmt, in, out, stream, partials, npartials);
     else

@@ -18,6 +18,8 @@
 #include "sumfac_nm1.cuh"
 #include "sumfac_rows.cuh"
 #include "sumfac_lanes.cuh"
+#include "sumfac_coapipe.cuh"
+#include "sumfac_coamma.cuh"
 #include "sumfac_rows_coa.cuh"
 #include "sumfac_tpe.cuh"
 #include "sumfac_umma.cuh"
@@ -382,6 +384,52 @@ template <typename T, int NQ, int EL, int IH> int launch_hex_lanesq(unsigned nel
     count_launch();
     t_last_backend = "lanes";
     return launch_status();
+}
+
+// ---- interleaved layout at the largest nq (sumfac_coapipe.cuh, sumfac_coamma.cuh): persistent CTAs, cp.async gather
+template <typename T, int NQ, int EL, int NW, int MINB>
+int launch_hex_coapipe(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
+{
+    using C = HexCoaPipe<T, NQ, EL, NW>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "slot + work region do not fit shared memory");
+    static int occ[64] = {};
+    auto kernel        = bwdtrans_hex_coapipe_kernel<T, NQ, EL, NW, MINB>;
+    int rc             = opt_in_smem(kernel, C::SMEM);
+    if (rc)
+        return rc;
+    const unsigned ntiles = nelmt / EL; // nelmt % 32 == 0 is checked at the C ABI: every tile is full
+    const unsigned fit    = (unsigned)(sm_count() * ctas_per_sm(kernel, C::THREADS, C::SMEM, occ));
+    const unsigned grid   = ntiles < fit ? ntiles : fit;
+    B200FE_CUDA_TRY(launch_pdl(kernel, grid, C::THREADS, C::SMEM, stream, in, out, ntiles));
+    count_launch();
+    t_last_backend = "coa-pipe";
+    return launch_status();
+}
+
+// FP64 quads on the tensor cores with M = elements; reads the basis matrices from global memory (no bank fill)
+template <int NQ, int WARPS>
+int launch_quad_coamma(unsigned nelmt, const double *b0, const double *b1, const double *in, double *out,
+                       cudaStream_t stream)
+{
+    using C = QuadCoaMma<NQ, WARPS>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "region does not fit shared memory");
+    static int occ[64] = {};
+    auto kernel        = bwdtrans_quad_coamma_kernel<NQ, WARPS, 1>;
+    int rc             = opt_in_smem(kernel, C::SMEM);
+    if (rc)
+        return rc;
+    const unsigned ntiles = nelmt / C::EL;
+    const unsigned fit    = (unsigned)(sm_count() * ctas_per_sm(kernel, C::THREADS, C::SMEM, occ));
+    const unsigned grid   = ntiles < fit ? ntiles : fit;
+    kernel<<<grid, C::THREADS, C::SMEM, stream>>>(b0, b1, in, out, ntiles);
+    count_launch();
+    t_last_backend = "coa-mma";
+    return launch_status();
+}
+template <int NQ, int WARPS>
+int launch_quad_coamma(unsigned, const float *, const float *, const float *, float *, cudaStream_t)
+{
+    return B200FE_EUNSUPPORTED; // FP64 only (DMMA)
 }
 
 // ---- element-major quads, lanes style (sumfac_lanes.cuh): bulk-copied slab, one row per thread and direction

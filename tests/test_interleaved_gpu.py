@@ -63,9 +63,10 @@ def test_quad_lanes_backend_bit_exact(G, suf, nq):
     finally:
         G.fe.set_backend("auto")
     assert np.array_equal(oracle.from_coa(got, nelmt, nq * nq), want_em)
-    # the default routing: lanes, except FP32 nq <= 6 where the thread-per-element kernel measured faster
+    # the default routing: lanes, except FP32 nq <= 6 where the thread-per-element kernel measured faster and FP64
+    # nq = 32 on the tensor cores (tests/test_coa_large_nq_gpu.py)
     got = G.run_quad("BwdTransQuadKernel_Coa", suf, nq, nq, nelmt, b0, b1, inp)
-    assert G.fe.last_backend() == ("tpe" if suf == "f32" and nq <= 6 else "lanes")
+    assert G.fe.last_backend() == ("tpe" if suf == "f32" and nq <= 6 else "coa-mma" if suf == "f64" and nq == 32 else "lanes")
     assert np.array_equal(oracle.from_coa(got, nelmt, nq * nq), want_em)
 
 
@@ -82,7 +83,7 @@ def test_hex_lanes_backend_bit_exact(G, suf, nq):
         G.fe.set_backend("auto")
     assert np.array_equal(oracle.from_coa(got, nelmt, nq ** 3), want_em)
     got = G.run_hex("BwdTransHexKernel_Coa", suf, (nq, nq, nq), nelmt, b, inp)
-    assert G.fe.last_backend() == ("tpe" if suf == "f64" and nq == 5 else "lanes")
+    assert G.fe.last_backend() == ("tpe" if suf == "f64" and nq == 5 else "coa-pipe" if suf == "f64" and nq in (8, 10) else "lanes")
     assert np.array_equal(oracle.from_coa(got, nelmt, nq ** 3), want_em)
 
 
@@ -245,7 +246,7 @@ def test_lanes_full_size_checksum_of_checksums(G, suf):
             want = oracle.bwdtrans_hex(nq, nq, nq, 1, *b, one)
             G.fe.bwdtrans_hex("BwdTransHexKernel_Coa", suf, nq, nq, nq, nelmt, d_b[0].data_ptr(), d_b[1].data_ptr(),
                               d_b[2].data_ptr(), d_in.data_ptr(), d_out.data_ptr(), stream=st)
-        assert G.fe.last_backend() == "lanes"
+        assert G.fe.last_backend() == ("coa-pipe" if (dim, nq, suf) == (3, 8, "f64") else "lanes")
         torch.cuda.synchronize()
         # out_coa[g][m][e] == want[m] for every g, e
         view = d_out.reshape(nelmt // 32, nq ** dim, 32)
@@ -344,7 +345,7 @@ def test_element_major_lanes_kernels_at_baseline_size(G, dim, suf, nq):
 
 
 @pytest.mark.parametrize("layout,dim,suf,nq", [("em", 2, "f64", 12), ("em", 3, "f32", 8), ("coa", 2, "f32", 16),
-                                               ("coa", 3, "f64", 8)])
+                                               ("coa", 3, "f64", 7)])  # (coa FP64 nq = 8: test_coa_large_nq_gpu.py)
 def test_lanes_kernels_keep_non_finite_values_inside_their_element(G, layout, dim, suf, nq):
     """one poisoned element (Inf modes) must not leak into its neighbours: every lane / tile slot is private"""
     dt, nm = G.NP[suf], nq - 1

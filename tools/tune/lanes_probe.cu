@@ -7,12 +7,16 @@
 
 #include "../../gpu-benchmarking_b200/csrc/sumfac_generic.cuh"
 #include "../../gpu-benchmarking_b200/csrc/sumfac_lanes.cuh"
+#include "../../gpu-benchmarking_b200/csrc/sumfac_coapipe.cuh"
+#include "../../gpu-benchmarking_b200/csrc/sumfac_coamma.cuh"
 
 using namespace b200fe;
 namespace b200fe
 {
 std::atomic<unsigned long long> g_launch_count{0};
 thread_local const char *t_last_backend = "";
+thread_local unsigned long long t_bank_tag = 0;
+std::atomic<int> g_bank_fill_mode{0};
 }
 
 #define CK(x)                                                                                                \
@@ -113,13 +117,20 @@ template <typename T> struct Case
     }
     template <typename K> void run(const char *name, K kernel, unsigned grid, int threads, size_t smem)
     {
+        run_args(name, kernel, grid, threads, smem, in, out, nelmt);
+    }
+    // any kernel signature: the arguments are passed through
+    template <typename K, typename... A> void run_args(const char *name, K kernel, unsigned grid, int threads, size_t smem, A... args)
+    {
         if (smem > 48 * 1024)
             CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem);
+        if (grid == 0) // persistent kernels: one wave
+            grid = 148 * (occ > 0 ? occ : 1);
         CK(cudaMemset(out, 0xff, sizeof(T) * nout));
         CK(cudaMemset(bad, 0, 8));
-        kernel<<<grid, threads, smem>>>(in, out, nelmt);
+        kernel<<<grid, threads, smem>>>(args...);
         CK(cudaGetLastError());
         diff_kernel<T><<<1024, 256>>>(out, ref, nout, bad);
         unsigned long long nbad = 0;
@@ -132,7 +143,7 @@ template <typename T> struct Case
         for (int r = 0; r < reps; ++r)
         {
             cudaEventRecord(e0);
-            kernel<<<grid, threads, smem>>>(in, out, nelmt);
+            kernel<<<grid, threads, smem>>>(args...);
             cudaEventRecord(e1);
             CK(cudaEventSynchronize(e1));
             float ms;
@@ -159,13 +170,57 @@ template <typename T> struct Case
     c.run("quad EL=" #EL, bwdtrans_quad_lanes_kernel<T, NQ, EL>, c.nelmt / EL, QuadLanes<T, NQ, EL>::THREADS,  \
           QuadLanes<T, NQ, EL>::SMEM);
 
-#define H3(T, NQ, EL, NWK, MB)                                                                               \
-    c.run("3-phase EL=" #EL " NWK=" #NWK " MINB=" #MB, bwdtrans_hex_lanes3_kernel<T, NQ, EL, NWK, MB>, c.nelmt / EL, \
-          HexLanes3<T, NQ, EL, NWK>::THREADS, HexLanes3<T, NQ, EL, NWK>::SMEM);
 
-int main()
+// coa-pipe (sumfac_coapipe.cuh): persistent (grid 0 = one wave of resident CTAs)
+#define CP(T, NQ, EL, NW, MB)                                                                                \
+    c.run_args("coa-pipe EL=" #EL " NW=" #NW " MINB=" #MB, bwdtrans_hex_coapipe_kernel<T, NQ, EL, NW, MB>, 0u,  \
+               HexCoaPipe<T, NQ, EL, NW>::THREADS, HexCoaPipe<T, NQ, EL, NW>::SMEM, (const T *)c.in, c.out, c.nelmt / EL);
+#define CM(NQ, WARPS, RB)                                                                                    \
+    c.run_args("coa-mma WARPS=" #WARPS " RB=" #RB, bwdtrans_quad_coamma_kernel<NQ, WARPS, RB>, 0u, WARPS * 32, \
+               QuadCoaMma<NQ, WARPS>::SMEM, (const double *)c.b[0], (const double *)c.b[1], (const double *)c.in, c.out, c.nelmt / 8);
+
+int main(int argc, char **argv)
 {
+    const int which = argc > 1 ? atoi(argv[1]) : 0;
     printf("op,nq,dtype,_,threads,smem,ctas_per_sm,ms_best,ms_avg,gb_s,mismatches\n");
+    if (which == 1)
+    {
+        {
+            Case<double> c;
+            c.setup(3, 10);
+            HQ(double, 10, 8, 2, 1)
+            CP(double, 10, 8, 34, 2) CP(double, 10, 8, 50, 2) CP(double, 10, 8, 52, 2) CP(double, 10, 8, 46, 2) CP(double, 10, 8, 41, 2) CP(double, 10, 8, 27, 2)
+            CP(double, 10, 16, 50, 1) CP(double, 10, 16, 25, 1)
+            c.teardown();
+            c.setup(3, 8);
+            HP(double, 8, 16, 1)
+            CP(double, 8, 8, 32, 2) CP(double, 8, 8, 32, 4) CP(double, 8, 8, 22, 4) CP(double, 8, 8, 16, 4) CP(double, 8, 16, 32, 2)
+            c.teardown();
+            c.setup(2, 32);
+            QL(double, 32, 16)
+            CM(32, 8, 1) CM(32, 6, 1) CM(32, 4, 1) CM(32, 12, 1) CM(32, 8, 2) CM(32, 4, 2)
+            c.teardown();
+        }
+        {
+            Case<float> c;
+            c.setup(3, 10);
+            HP(float, 10, 16, 3)
+            CP(float, 10, 16, 25, 2) CP(float, 10, 16, 50, 1) CP(float, 10, 16, 34, 2) CP(float, 10, 32, 25, 1) CP(float, 10, 32, 17, 1)
+            c.teardown();
+        }
+        return 0;
+    }
+    if (which == 2) // ncu targets
+    {
+        Case<double> c;
+        c.setup(3, 10);
+        CP(double, 10, 8, 50, 2)
+        c.teardown();
+        c.setup(2, 32);
+        CM(32, 8, 2)
+        c.teardown();
+        return 0;
+    }
     {
         Case<float> c;
         c.setup(3, 10); HP(float, 10, 16, 3) HP(float, 10, 8, 1) HP(float, 10, 8, 4) HP(float, 10, 8, 5) HP(float, 10, 8, 6) c.teardown();
