@@ -414,7 +414,7 @@ int launch_quad_coamma(unsigned nelmt, const double *b0, const double *b1, const
     using C = QuadCoaMma<NQ, WARPS>;
     static_assert(C::SMEM <= (size_t)kSmemMax, "region does not fit shared memory");
     static int occ[64] = {};
-    auto kernel        = bwdtrans_quad_coamma_kernel<NQ, WARPS, 1>;
+    auto kernel        = bwdtrans_quad_coamma_kernel<NQ, WARPS>;
     int rc             = opt_in_smem(kernel, C::SMEM);
     if (rc)
         return rc;

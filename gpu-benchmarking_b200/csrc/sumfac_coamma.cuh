@@ -13,16 +13,22 @@
 // nq with zeros in the basis fragments (3 % waste at nq = 32, none in N), and nothing is ever transposed.
 //
 //   gather  the tile [idx][8 e] (64-byte runs, 256 bytes apart) by 16-byte cp.async copies into ONE region of
-//           nm rows x nq units (a unit = one index of the 8 elements = 64 bytes): row q of the input (nm units)
+//           nq rows x nq units (a unit = one index of the 8 elements = 64 bytes): row q of the input (nm units)
 //           at units [nq*q, nq*q + nm)
 //   dir 0   a warp takes rows q, q + WARPS, ...: KS A fragments from its row (lanes (e, p)), KS x NT DMMAs against the
-//           B0 fragments held in registers, and t1[q][.][e] (nq units) goes back IN PLACE over the row it came from --
-//           the row belongs to that warp alone, so direction 0 needs no barrier at all
-//   dir 1   a warp takes columns i: A fragments from t1 (lanes (e, q)), B1 fragments in registers, results straight
-//           to global memory: each store instruction writes four whole 64-byte runs
-// 63.5 KB per tile + 16 KB of basis fragments: two CTAs per SM whose gather / contract phases overlap (a first version
-// with a two-slot ring and one CTA per SM left the tensor pipe idle through every gather issue, fragment reload and
-// barrier: 65 % DMMA utilisation, 0.45 of the roofline).
+//           B0 fragments, and t1[q][.][e] (nq units) goes back IN PLACE over the row it came from -- the row belongs
+//           to that warp alone, so direction 0 needs no barrier at all
+//   dir 1   a warp takes columns i: A fragments from t1 (lanes (e, q)), B1 fragments, results straight to global
+//           memory: each store instruction writes four whole 64-byte runs
+// Both basis matrices live in registers, as fragments, for the whole kernel, and every warp runs its rows (columns) as
+// a three-stage software pipeline -- A fragments of row k+1 loaded, DMMAs of row k issued, results of row k-1 stored --
+// on two alternating fragment / accumulator sets, so the tensor pipe sees one uninterrupted DMMA stream per warp.
+// 255 registers: 4 warps per CTA, two CTAs per SM (64 KB each) whose gather / contract phases overlap.
+// Measured at 65 536 elements (tools/tune/lanes_probe.cu, profiles/r02_coa_probe.csv): 0.55 of the HBM roofline =
+// 29 TFLOP/s = 79 % of the FP64 tensor peak (the ceiling at that peak is 0.70; the element-major DMMA kernel holds
+// 0.60; the lanes kernel this replaces 0.29).  Steps on the way: two-slot ring + fragments reloaded from shared
+// memory at every phase change, one CTA per SM: 0.45 (tensor pipe idle through every gather issue, reload and barrier);
+// the swizzles below: 0.46; in-place rows, two CTAs per SM: 0.50; registers + pipeline: 0.55.
 // Bank conflicts.  An 8-byte access is served a half warp at a time: fragment rows 0-3 (4 elements = 32 bytes) x the 4
 // fragment columns, which therefore have to fall into the four 32-byte quarters of a 128-byte bank window.  The tile's
 // unit is 64 bytes (index u, 8 elements), so consecutive u alternate between the two halves and a two-bit swizzle does
@@ -37,6 +43,7 @@
 
 #include "sumfac_coapipe.cuh"
 #include "sumfac_mma.cuh"
+#include "sumfac_mma32.cuh"
 
 namespace b200fe
 {
@@ -46,15 +53,14 @@ template <int NQ, int WARPS> struct QuadCoaMma
     static_assert(NQ % 8 == 0, "whole n tiles");
     static constexpr int EL = 8, NM = NQ - 1, NM2 = NM * NM, NQ2 = NQ * NQ;
     static constexpr int KS = (NM + 3) / 4, NT = NQ / 8;
-    static constexpr int S1   = NM * NQ * EL;   // the region: input rows pitched to nq units, then t1 in place (doubles)
-    static constexpr int FRAG = KS * NT * 32;   // one basis matrix in fragment order
-    static constexpr size_t SMEM = (size_t)(S1 + 2 * FRAG) * sizeof(double);
+    static constexpr int S1 = NQ * NQ * EL; // the region: nm rows of nq units + one spare row (the zero-selected k padding of direction 1 reads it)
+    static constexpr size_t SMEM = (size_t)S1 * sizeof(double);
     static constexpr int THREADS = WARPS * 32;
     static constexpr int PER = 32 / EL;
+    static constexpr int ROWS = (NM + WARPS - 1) / WARPS, COLS = (NQ + WARPS - 1) / WARPS; // per warp
 };
 
-// RB rows (columns) per warp at once: RB * NT independent accumulator chains in flight
-template <int NQ, int WARPS, int RB = 1>
+template <int NQ, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 2)
     bwdtrans_quad_coamma_kernel(const double *__restrict__ b0, const double *__restrict__ b1,
                                 const double *__restrict__ in, double *__restrict__ out, unsigned ntiles)
@@ -62,21 +68,23 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
     using C = QuadCoaMma<NQ, WARPS>;
     constexpr int NM = C::NM, NM2 = C::NM2, KS = C::KS, NT = C::NT, EL = C::EL, PER = C::PER;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *s1    = reinterpret_cast<double *>(smem_raw);
-    double *fb0   = s1 + C::S1; // (also what the zero-selected reads past the end of t1 land in)
-    double *fb1   = fb0 + C::FRAG;
+    double *s1 = reinterpret_cast<double *>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r = lane >> 2, c = lane & 3; // fragment row (element) / column
 
-    // basis fragments: B[k = 4 ks + c][n = 8 nt + r], zero where k is padding
-    for (int f = tid; f < C::FRAG; f += C::THREADS)
-    {
-        const int l = f & 31, t = f >> 5, ks = t / NT, nt = t - ks * NT;
-        const int k = 4 * ks + (l & 3), n = 8 * nt + (l >> 2);
-        fb0[f] = k < NM ? b0[k * NQ + n] : 0.0;
-        fb1[f] = k < NM ? b1[k * NQ + n] : 0.0;
-    }
+    // basis fragments B[k = 4 ks + c][n = 8 nt + r], zero where k is padding: in registers from here on
+    double f0[KS][NT], f1[KS][NT];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+        {
+            const int k = 4 * ks + c;
+            f0[ks][n]   = k < NM ? b0[k * NQ + 8 * n + r] : 0.0;
+            f1[ks][n]   = k < NM ? b1[k * NQ + 8 * n + r] : 0.0;
+        }
+    const bool kpad = 4 * (KS - 1) + c >= NM; // this lane's column of the last k step is padding
 
     auto issue = [&](unsigned tile) {
         const unsigned group = tile / PER, l0 = (tile % PER) * EL;
@@ -89,8 +97,241 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
         }
         cp_async_commit();
     };
+    auto load_a = [&](double (&a)[KS], const double *ap, int stride) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+            a[ks] = ap[ks * stride];
+        if (kpad)
+            a[KS - 1] = 0.0; // the padded column must not contribute, whatever lies there (Inf, NaN)
+    };
+    auto mma_row = [&](double (&acc)[NT][2], const double (&a)[KS], const double (&f)[KS][NT]) {
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+            acc[n][0] = acc[n][1] = 0.0;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+                dmma884_ordered(acc[n], a[ks], f[ks][n]);
+    };
+    // A fragments of row q (direction 0): u = nq*q + 4 ks + c, bit 1 of u is that of c
+    auto row_ptr = [&](int q) { return s1 + (q * NQ + c) * EL + (r ^ (2 * (c & 2))); };
+    // t1[q][i = 8 n + 2 c + h]: u = 32 q + i -- bit 1 = c & 1, bit 2 = c >> 1, bit 5 = q & 1, bit 6 = q >> 1 & 1
+    auto store_row = [&](int q, const double (&acc)[NT][2]) {
+        const int sw = (c ^ q) & 1, er = r ^ (4 * (((c >> 1) ^ (q >> 1)) & 1));
+        double *d0   = s1 + (q * NQ + 2 * c + sw) * EL + er;
+        double *d1   = s1 + (q * NQ + 2 * c + (sw ^ 1)) * EL + er;
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+        {
+            d0[8 * n * EL] = acc[n][0];
+            d1[8 * n * EL] = acc[n][1];
+        }
+    };
+    // A fragments of column i (direction 1): u = 32 (4 ks + c) + i -- bit 1 = i >> 1, bit 2 = i >> 2, bit 5 = c & 1, bit 6 = c >> 1
+    auto col_ptr = [&](int i) {
+        return s1 + (c * NQ + (i ^ (((i >> 1) ^ c) & 1))) * EL + (r ^ (4 * (((i >> 2) ^ (c >> 1)) & 1)));
+    };
 
-    const bool kpad = 4 * (KS - 1) + c >= NM; // this lane's column of the last k step is padding
+#pragma unroll 1
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+    {
+        __syncthreads(); // every warp has left direction 1 of the previous tile
+        issue(tile);
+        cp_async_wait<0>();
+        __syncthreads();
+
+        // direction 0: rows q = warp + k*WARPS, in place (a row belongs to one warp)
+        {
+            double a[2][KS], acc[2][NT][2];
+            load_a(a[0], row_ptr(warp), 4 * EL);
+#pragma unroll
+            for (int k = 0; k < C::ROWS; ++k)
+            {
+                const int q = warp + k * WARPS;
+                if (k + 1 < C::ROWS && q + WARPS < NM)
+                    load_a(a[(k + 1) & 1], row_ptr(q + WARPS), 4 * EL);
+                if (q < NM)
+                    mma_row(acc[k & 1], a[k & 1], f0);
+                if (k > 0)
+                    store_row(q - WARPS, acc[(k - 1) & 1]);
+            }
+            if (warp + (C::ROWS - 1) * WARPS < NM)
+                store_row(warp + (C::ROWS - 1) * WARPS, acc[(C::ROWS - 1) & 1]);
+        }
+        __syncthreads();
+
+        // direction 1: columns i = warp + k*WARPS, straight to global
+        {
+            const unsigned group = tile / PER, l0 = (tile % PER) * EL;
+            double *gout         = out + (size_t)group * 32 * C::NQ2 + l0 + r;
+            auto store_col = [&](int i, const double (&acc)[NT][2]) {
+                double *dst = gout + (size_t)32 * ((2 * c) * NQ + i); // j = 8 n + 2 c + h
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+                {
+                    st_stream(dst + (size_t)32 * NQ * (8 * n), acc[n][0]);
+                    st_stream(dst + (size_t)32 * NQ * (8 * n + 1), acc[n][1]);
+                }
+            };
+            double a[2][KS], acc[2][NT][2];
+            load_a(a[0], col_ptr(warp), 4 * NQ * EL);
+#pragma unroll
+            for (int k = 0; k < C::COLS; ++k)
+            {
+                const int i = warp + k * WARPS;
+                if (k + 1 < C::COLS && i + WARPS < NQ)
+                    load_a(a[(k + 1) & 1], col_ptr(i + WARPS), 4 * NQ * EL);
+                if (i < NQ)
+                    mma_row(acc[k & 1], a[k & 1], f1);
+                if (k > 0)
+                    store_col(i - WARPS, acc[(k - 1) & 1]);
+            }
+            if (warp + (C::COLS - 1) * WARPS < NQ)
+                store_col(warp + (C::COLS - 1) * WARPS, acc[(C::COLS - 1) & 1]);
+        }
+    }
+}
+
+// ---- FP32 twin: the same formulation on the warp-level TF32 tensor-core path with the 3xTF32 split ---------------
+// (mma.sync.m16n8k8.tf32 = SASS HMMA.1688.F32.TF32, FP32 accumulate; split and error analysis: sumfac_mma32.cuh).
+// FP32 nq = 32 needs 103 TFLOP/s at the HBM roofline against 72 TFLOP/s of FFMA peak: the lanes kernel (rolled FFMA2
+// loop) holds 0.33 of the roofline; three HMMAs per product give 93 TFLOP/s of FP32-equivalent peak.
+// M = 16 elements: a tile is 16 consecutive elements of an interleave group, the unit (one index of the tile) is again
+// 64 bytes, so region, gather and the two-bit swizzles are those of the FP64 kernel with 8-float quarters.  A lane's A
+// fragment is (e = g, g + 8) x (k = t, t + 4): four 4-byte loads per k step, each conflict-free across the warp.  The
+// data is split on the fly (3 ALU instructions per value), the basis once per CTA into a fragment area in shared
+// memory ([ks][n][lane] x {hi b0, hi b1, lo b0, lo b1}: one 16-byte load per fragment, reloaded per direction).
+// Measured (tools/tune/lanes_probe.cu): 0.48 of the roofline, HMMA pipe 59 % busy (profiles/r02_ncu_quad32_f32_coamma.txt);
+// issuing two rows' chains interleaved instead of prefetching the next row was slower (0.45).
+// Not bit-identical to the reference's FFMA chain: held to the component-wise 1e-5 bound of include/b200fe.h like the
+// element-major tensor-core kernels (measured 7e-7 of the largest output); b200fe_set_backend("lanes") keeps the
+// bit-exact kernel.
+template <int NQ, int WARPS> struct QuadCoaMma32
+{
+    static_assert(NQ % 8 == 0, "whole n tiles and k steps");
+    static constexpr int EL = 16, NM = NQ - 1, NM2 = NM * NM, NQ2 = NQ * NQ;
+    static constexpr int KS = NQ / 8, NT = NQ / 8;
+    static constexpr int S1   = NQ * NQ * EL;       // floats: nm rows of nq units + one spare row
+    static constexpr int FRAG = KS * NT * 32 * 4;   // words per basis matrix
+    static constexpr size_t SMEM = (size_t)(S1 + 2 * FRAG) * sizeof(float);
+    static constexpr int THREADS = WARPS * 32;
+    static constexpr int PER = 32 / EL;
+    static constexpr int ROWS = (NM + WARPS - 1) / WARPS, COLS = (NQ + WARPS - 1) / WARPS; // per warp
+};
+
+template <int NQ, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2)
+    bwdtrans_quad_coamma32_kernel(const float *__restrict__ b0, const float *__restrict__ b1,
+                                  const float *__restrict__ in, float *__restrict__ out, unsigned ntiles)
+{
+    using C = QuadCoaMma32<NQ, WARPS>;
+    constexpr int NM = C::NM, NM2 = C::NM2, KS = C::KS, NT = C::NT, EL = C::EL, PER = C::PER;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s1     = reinterpret_cast<float *>(smem_raw);
+    unsigned *fr0 = reinterpret_cast<unsigned *>(s1 + C::S1);
+    unsigned *fr1 = fr0 + C::FRAG;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    // basis fragments: b0 = B[k = 8 ks + t][n = 8 nt + g], b1 = B[k + 4][n]; zero where k is padding
+    for (int f = tid; f < KS * NT * 32; f += C::THREADS)
+    {
+        const int l = f & 31, tt = f >> 5, ks = tt / NT, nt = tt - ks * NT;
+        const int k = 8 * ks + (l & 3), n = 8 * nt + (l >> 2);
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+        {
+            const float *b = m ? b1 : b0;
+            unsigned *fr   = m ? fr1 : fr0;
+            unsigned h0, l0, h1, l1;
+            tf32_split(k < NM ? b[k * NQ + n] : 0.f, h0, l0);
+            tf32_split(k + 4 < NM ? b[(k + 4) * NQ + n] : 0.f, h1, l1);
+            *reinterpret_cast<uint4 *>(fr + 4 * f) = make_uint4(h0, h1, l0, l1);
+        }
+    }
+
+    auto issue = [&](unsigned tile) {
+        const unsigned group = tile / PER, l0 = (tile % PER) * EL;
+        const float *gsrc    = in + (size_t)group * 32 * NM2 + l0;
+#pragma unroll 4
+        for (int ch = tid; ch < NM2 * 4; ch += C::THREADS)
+        {
+            const int idx = ch >> 2, part = ch & 3, q = idx / NM, u = idx + q; // u = nq*q + p
+            cp_async16(s1 + u * EL + 4 * (part ^ (u & 2)), gsrc + (size_t)idx * 32 + part * 4);
+        }
+        cp_async_commit();
+    };
+    const bool kpad = t == 3; // this lane's second column (k = t + 4) of the last k step is padding (k = nm)
+    // raw A fragments of one row / column: element offsets e0 (rows g) and e0 ^ 8 (rows g + 8), k = t and t + 4
+    auto load_a = [&](float (&a)[KS][4], const float *ap, int e0, int stride) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+        {
+            a[ks][0] = ap[ks * 8 * stride + e0];
+            a[ks][1] = ap[ks * 8 * stride + (e0 ^ 8)];
+            a[ks][2] = ap[(ks * 8 + 4) * stride + e0];
+            a[ks][3] = ap[(ks * 8 + 4) * stride + (e0 ^ 8)];
+        }
+        if (kpad)
+            a[KS - 1][2] = a[KS - 1][3] = 0.f; // must not contribute, whatever lies there (Inf, NaN)
+    };
+    auto mma_row = [&](float (&acc)[NT][4], const float (&a)[KS][4], const uint4 (&f)[KS][NT]) {
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+            acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+        {
+            unsigned hi[4], lo[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m)
+                tf32_split_fast(a[ks][m], hi[m], lo[m]);
+            // term-major: the NT accumulators are independent, the three terms of one accumulator are a chain
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+            {
+                const unsigned bh[2] = {f[ks][n].x, f[ks][n].y};
+                hmma1688_tf32(acc[n], lo, bh);
+            }
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+            {
+                const unsigned bl[2] = {f[ks][n].z, f[ks][n].w};
+                hmma1688_tf32(acc[n], hi, bl);
+            }
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+            {
+                const unsigned bh[2] = {f[ks][n].x, f[ks][n].y};
+                hmma1688_tf32(acc[n], hi, bh);
+            }
+        }
+    };
+    auto load_frags = [&](uint4 (&f)[KS][NT], const unsigned *fr) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+                f[ks][n] = *reinterpret_cast<const uint4 *>(fr + 4 * ((ks * NT + n) * 32 + lane));
+    };
+    // direction 0, row q: u = nq*q + 8 ks + t (+ 4): bit 1 of u is that of t
+    const int e0row = g ^ (4 * (t & 2));
+    // t1[q][i = 8 n + 2 t + h][e]: u = 32 q + i -- bit 1 = t & 1, bit 2 = t >> 1, bit 5 = q & 1, bit 6 = q >> 1 & 1
+    auto store_row = [&](int q, const float (&acc)[NT][4]) {
+        const int sw = (t ^ q) & 1, er = g ^ (8 * (((t >> 1) ^ (q >> 1)) & 1));
+        float *d0    = s1 + (q * NQ + 2 * t + sw) * EL;       // h = 0
+        float *d1    = s1 + (q * NQ + 2 * t + (sw ^ 1)) * EL; // h = 1
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+        {
+            d0[8 * n * EL + er]       = acc[n][0];
+            d1[8 * n * EL + er]       = acc[n][1];
+            d0[8 * n * EL + (er ^ 8)] = acc[n][2];
+            d1[8 * n * EL + (er ^ 8)] = acc[n][3];
+        }
+    };
 
 #pragma unroll 1
     for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
@@ -100,111 +341,62 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
         cp_async_wait<0>();
         __syncthreads();
 
-        double b[KS][NT];
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-            for (int n = 0; n < NT; ++n)
-                b[ks][n] = fb0[(ks * NT + n) * 32 + lane];
-
-        // direction 0: rows q of the 8 elements
-#pragma unroll 1
-        for (int q0 = warp; q0 < NM; q0 += RB * WARPS)
+        uint4 f[KS][NT];
+        load_frags(f, fr0);
+        // direction 0: rows q = warp + k*WARPS, in place (a row belongs to one warp)
         {
-            double a[RB][KS], acc[RB][NT][2];
+            float a[2][KS][4], acc[2][NT][4];
+            load_a(a[0], s1 + (warp * NQ + t) * EL, e0row, EL);
 #pragma unroll
-            for (int k = 0; k < RB; ++k)
+            for (int k = 0; k < C::ROWS; ++k)
             {
-                const int q = q0 + k * WARPS < NM ? q0 + k * WARPS : q0; // (clamped: recomputes row q0, stores nothing)
-                // u = nq*q + 4 ks + c: bit 1 of u is that of c
-                const double *ap = s1 + (q * NQ + c) * EL + (r ^ (2 * (c & 2)));
-#pragma unroll
-                for (int ks = 0; ks < KS; ++ks)
-                    a[k][ks] = ap[4 * ks * EL]; // the padded column reads the row's spare unit (never written by the gather)
-                if (kpad)
-                    a[k][KS - 1] = 0.0; // ... which must not contribute, whatever it is (Inf, NaN)
-#pragma unroll
-                for (int n = 0; n < NT; ++n)
-                    acc[k][n][0] = acc[k][n][1] = 0.0;
-            }
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-                for (int k = 0; k < RB; ++k)
-#pragma unroll
-                    for (int n = 0; n < NT; ++n)
-                        dmma884_ordered(acc[k][n], a[k][ks], b[ks][n]);
-#pragma unroll
-            for (int k = 0; k < RB; ++k)
-            {
-                const int q = q0 + k * WARPS;
+                const int q = warp + k * WARPS;
+                if (k + 1 < C::ROWS && q + WARPS < NM)
+                    load_a(a[(k + 1) & 1], s1 + ((q + WARPS) * NQ + t) * EL, e0row, EL);
                 if (q < NM)
-                {
-                    // u = 32 q + 8 n + 2 c + h: bit 1 = c & 1, bit 2 = c >> 1, bit 5 = q & 1, bit 6 = q >> 1 & 1
-                    const int sw = (c ^ q) & 1, er = r ^ (4 * (((c >> 1) ^ (q >> 1)) & 1));
-                    double *d0   = s1 + (q * NQ + 2 * c + sw) * EL + er;       // h = 0
-                    double *d1   = s1 + (q * NQ + 2 * c + (sw ^ 1)) * EL + er; // h = 1
-#pragma unroll
-                    for (int n = 0; n < NT; ++n)
-                    {
-                        d0[8 * n * EL] = acc[k][n][0];
-                        d1[8 * n * EL] = acc[k][n][1];
-                    }
-                }
+                    mma_row(acc[k & 1], a[k & 1], f);
+                if (k > 0)
+                    store_row(q - WARPS, acc[(k - 1) & 1]);
             }
+            if (warp + (C::ROWS - 1) * WARPS < NM)
+                store_row(warp + (C::ROWS - 1) * WARPS, acc[(C::ROWS - 1) & 1]);
         }
         __syncthreads();
 
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-            for (int n = 0; n < NT; ++n)
-                b[ks][n] = fb1[(ks * NT + n) * 32 + lane];
-
-        // direction 1: column i of the 8 elements, straight to global
-        const unsigned group = tile / PER, l0 = (tile % PER) * EL;
-        double *gout         = out + (size_t)group * 32 * C::NQ2 + l0 + r;
-#pragma unroll 1
-        for (int i0 = warp; i0 < NQ; i0 += RB * WARPS)
+        load_frags(f, fr1);
+        // direction 1: columns i = warp + k*WARPS, straight to global
         {
-            double a[RB][KS], acc[RB][NT][2];
-#pragma unroll
-            for (int k = 0; k < RB; ++k)
-            {
-                const int i = i0 + k * WARPS < NQ ? i0 + k * WARPS : i0;
-                // u = 32 (4 ks + c) + i: bit 1 = i >> 1, bit 2 = i >> 2, bit 5 = c & 1, bit 6 = c >> 1 -- none depends on ks
-                const double *ap = s1 + (c * NQ + (i ^ (((i >> 1) ^ c) & 1))) * EL + (r ^ (4 * (((i >> 2) ^ (c >> 1)) & 1)));
-#pragma unroll
-                for (int ks = 0; ks < KS; ++ks)
-                    a[k][ks] = ap[4 * ks * NQ * EL]; // q = nm (padding) reads the fragment area behind t1
-                if (kpad)
-                    a[k][KS - 1] = 0.0;
+            const unsigned group = tile / PER, l0 = (tile % PER) * EL;
+            float *gout          = out + (size_t)group * 32 * C::NQ2 + l0 + g;
+            // u = 32 (8 ks + t (+ 4)) + i: bit 1 = i >> 1, bit 2 = i >> 2, bit 5 = t & 1, bit 6 = t >> 1
+            auto col_ptr = [&](int i) { return s1 + (t * NQ + (i ^ (((i >> 1) ^ t) & 1))) * EL; };
+            auto col_e0  = [&](int i) { return g ^ (8 * (((i >> 2) ^ (t >> 1)) & 1)); };
+            auto store_col = [&](int i, const float (&acc)[NT][4]) {
+                float *dst = gout + (size_t)32 * ((2 * t) * NQ + i); // j = 8 n + 2 t + h
 #pragma unroll
                 for (int n = 0; n < NT; ++n)
-                    acc[k][n][0] = acc[k][n][1] = 0.0;
-            }
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-                for (int k = 0; k < RB; ++k)
-#pragma unroll
-                    for (int n = 0; n < NT; ++n)
-                        dmma884_ordered(acc[k][n], a[k][ks], b[ks][n]);
-#pragma unroll
-            for (int k = 0; k < RB; ++k)
-            {
-                const int i = i0 + k * WARPS;
-                if (i < NQ)
                 {
-                    double *dst = gout + (size_t)32 * ((2 * c) * NQ + i); // j = 8 n + 2 c + h
-#pragma unroll
-                    for (int n = 0; n < NT; ++n)
-                    {
-                        st_stream(dst + (size_t)32 * NQ * (8 * n), acc[k][n][0]);
-                        st_stream(dst + (size_t)32 * NQ * (8 * n + 1), acc[k][n][1]);
-                    }
+                    st_stream(dst + (size_t)32 * NQ * (8 * n), acc[n][0]);
+                    st_stream(dst + (size_t)32 * NQ * (8 * n + 1), acc[n][1]);
+                    st_stream(dst + (size_t)32 * NQ * (8 * n) + 8, acc[n][2]);
+                    st_stream(dst + (size_t)32 * NQ * (8 * n + 1) + 8, acc[n][3]);
                 }
+            };
+            float a[2][KS][4], acc[2][NT][4];
+            load_a(a[0], col_ptr(warp), col_e0(warp), NQ * EL);
+#pragma unroll
+            for (int k = 0; k < C::COLS; ++k)
+            {
+                const int i = warp + k * WARPS;
+                if (k + 1 < C::COLS && i + WARPS < NQ)
+                    load_a(a[(k + 1) & 1], col_ptr(i + WARPS), col_e0(i + WARPS), NQ * EL);
+                if (i < NQ)
+                    mma_row(acc[k & 1], a[k & 1], f);
+                if (k > 0)
+                    store_col(i - WARPS, acc[(k - 1) & 1]);
             }
+            if (warp + (C::COLS - 1) * WARPS < NQ)
+                store_col(warp + (C::COLS - 1) * WARPS, acc[(C::COLS - 1) & 1]);
         }
     }
 }
