@@ -426,10 +426,24 @@ int launch_quad_coamma(unsigned nelmt, const double *b0, const double *b1, const
     t_last_backend = "coa-mma";
     return launch_status();
 }
+// FP32 twin on the TF32 tensor-core path (3xTF32 split): 16 elements per tile
 template <int NQ, int WARPS>
-int launch_quad_coamma(unsigned, const float *, const float *, const float *, float *, cudaStream_t)
+int launch_quad_coamma(unsigned nelmt, const float *b0, const float *b1, const float *in, float *out, cudaStream_t stream)
 {
-    return B200FE_EUNSUPPORTED; // FP64 only (DMMA)
+    using C = QuadCoaMma32<NQ, WARPS>;
+    static_assert(C::SMEM <= (size_t)kSmemMax, "region does not fit shared memory");
+    static int occ[64] = {};
+    auto kernel        = bwdtrans_quad_coamma32_kernel<NQ, WARPS>;
+    int rc             = opt_in_smem(kernel, C::SMEM);
+    if (rc)
+        return rc;
+    const unsigned ntiles = nelmt / C::EL;
+    const unsigned fit    = (unsigned)(sm_count() * ctas_per_sm(kernel, C::THREADS, C::SMEM, occ));
+    const unsigned grid   = ntiles < fit ? ntiles : fit;
+    kernel<<<grid, C::THREADS, C::SMEM, stream>>>(b0, b1, in, out, ntiles);
+    count_launch();
+    t_last_backend = "coa-mma";
+    return launch_status();
 }
 
 // ---- element-major quads, lanes style (sumfac_lanes.cuh): bulk-copied slab, one row per thread and direction

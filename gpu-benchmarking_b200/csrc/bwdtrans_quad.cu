@@ -272,10 +272,11 @@ static int quad_tpe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cud
     }
 }
 
-// interleaved layout on the FP64 tensor cores (sumfac_coamma.cuh): the one compute-bound case
+// interleaved layout on the tensor cores with M = elements (sumfac_coamma.cuh): the one compute-bound case.
+// FP64 on DMMA, bit-identical; FP32 on 3xTF32 mma.sync, held to the component-wise 1e-5 bound of include/b200fe.h
 static bool quad_has_coamma(unsigned nq)
 {
-    return sizeof(T) == 8 && nq == 32;
+    return nq == 32;
 }
 
 template <>
@@ -294,7 +295,7 @@ int run_bwdtrans_quad<T>(Backend be, bool coa, unsigned nm0, unsigned nm1, unsig
             be = Backend::Generic;
         else if (coa)
             be = nq0 < kQuadLanesMinNq ? Backend::Tpe
-                 : (quad_has_coamma(nq0) && aligned16(in)) ? Backend::Mma // FP64 nq = 32: 0.50 against 0.29 (lanes)
+                 : (quad_has_coamma(nq0) && aligned16(in)) ? Backend::Mma // nq = 32: FP64 0.55 against 0.29 (lanes), FP32 0.48 against 0.33
                  : quad_has_lanes(nq0) ? Backend::Lanes
                                        : ((have & 1) ? Backend::Rows : Backend::Generic);
         else if (nq0 == 2 && sizeof(T) == 4)

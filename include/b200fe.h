@@ -28,13 +28,14 @@
  * Numerical contract.  Every back-end but one accumulates each output over p, then q, then r in ascending order
  * from 0 with fused multiply-adds -- the arithmetic nvcc generates for every reference variant
  * (benchmark04.cc:55-59, benchmark05.cc:65-69) -- and is BIT-IDENTICAL to the reference kernels (FP64 and FP32).
- * The exception is the FP32 tensor-core route (3xTF32 split; default for quad FP32 nq = 32): its products are
+ * The exception is the FP32 tensor-core route (3xTF32 split; default for quad FP32 nq = 32, both layouts): its products are
  * formed from TF32 halves and summed in the tensor core's order, so it agrees with the reference to rounding:
  *     |out - exact| <= 1e-5 * (|B1|^T |B0|^T |in|)   for every single output (component-wise; measured 2-3e-6),
  * which implies the norm-wise bound max|out - ref| <= 1e-5 * max|ref| of the north star, but NOT a bound relative
  * to an individual output that is itself the result of heavy cancellation (no floating-point dot product offers
  * that; the reference's own FFMA chain satisfies the same component-wise bound with a smaller constant).
- * b200fe_set_backend("rows") selects the bit-exact FP32 path where that matters more than speed.
+ * b200fe_set_backend("rows") (interleaved layout: "lanes") selects the bit-exact FP32 path where that matters more
+ * than speed.
  * IProductWRTBase has no counterpart in the reference: its oracle is PARITY-UNPINNED (adjoint identity only).
  *
  * Data layouts:  nm = nq - 1 modes per direction.
@@ -374,8 +375,9 @@ int b200fe_bwdtrans_hex_host_f32(unsigned nq0, unsigned nq1, unsigned nq2, size_
 
 /* ---- tuning / introspection (not part of the reference surface) -----------------
  * Force a back-end for the BwdTrans entry points of the calling process:
- * "auto" (default routing), "rows", "pipe", "mma", "nm1", "tpe", "lanes", "generic".  Returns 0 or
- * B200FE_EINVAL for an unknown name; an entry point then returns
+ * "auto" (default routing), "rows", "pipe", "mma", "umma", "nm1", "tpe", "lanes", "generic".  For the interleaved
+ * (_Coa) entry points "pipe" is the coa-pipe kernel (FP64 hexes nq = 8, 10) and "mma" the tensor-core kernel with
+ * M = elements (quads nq = 32).  Returns 0 or B200FE_EINVAL for an unknown name; an entry point then returns
  * B200FE_EUNSUPPORTED where the forced back-end has no instantiation.  Used by the tuner and the parity tests to
  * exercise every back-end through the same C ABI. */
 int b200fe_set_backend(const char *name);

@@ -53,9 +53,9 @@ def run_hex(kernel, suf, nq, nelmt, b, inp, nm=None):
 def assert_parity(got, want, suf, what=""):
     """Bit for bit with the oracle / the reference kernels -- every back-end accumulates in the reference's own
     order with fused multiply-adds -- except the FP32 tensor-core back-ends (3xTF32 split: "mma" = warp-level
-    mma.sync, "umma" = tcgen05), which agree to rounding and are held to north_star's FP32 tolerance here (norm-wise)
+    mma.sync, "umma" = tcgen05, "coa-mma" = mma.sync with M = elements in the interleaved layout), which agree to rounding and are held to north_star's FP32 tolerance here (norm-wise)
     and to the component-wise bound in tests/test_fullsize_gpu.py / tests/test_umma_gpu.py."""
-    if suf == "f32" and fe.last_backend() in ("mma", "umma"):
+    if suf == "f32" and fe.last_backend() in ("mma", "umma", "coa-mma"):
         err = rel_max(got, want)
         assert err < TOL["f32"], (what, fe.last_backend() + " f32", err)
     else:

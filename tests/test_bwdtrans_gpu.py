@@ -102,7 +102,7 @@ def test_quad_interleaved_entry_point(G, suf, nq):
     inp = oracle.to_coa(rnd(rng, nelmt * nm * nm, dt), nelmt, nm * nm)
     want = oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp, coa=True)
     got = G.run_quad("BwdTransQuadKernel_Coa", suf, nq, nq, nelmt, b0, b1, inp)
-    assert np.array_equal(got, want)
+    G.assert_parity(got, want, suf, f"coa nq={nq}")  # bit for bit, except FP32 nq = 32 on the tensor cores (to rounding)
 
 
 @pytest.mark.parametrize("suf", ["f64", "f32"])

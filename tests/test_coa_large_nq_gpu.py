@@ -3,9 +3,12 @@ back-ends (reference layout and kernels: benchmark04.cc:78-147, benchmark05.cc:1
 
   coa-pipe  FP64 hexes nq = 8, 10 (csrc/sumfac_coapipe.cuh): persistent CTAs, cp.async gather of [idx][e] tiles, three
             passes that keep the interleaved order, pass 1 in place          -- b200fe_set_backend("pipe")
-  coa-mma   FP64 quads nq = 32 (csrc/sumfac_coamma.cuh): DMMA with M = elements, t1 in place -- b200fe_set_backend("mma")
+  coa-mma   quads nq = 32 (csrc/sumfac_coamma.cuh): tensor cores with M = elements, t1 in place -- b200fe_set_backend("mma")
+            FP64 on DMMA; FP32 on mma.sync with the 3xTF32 split
 
-Both accumulate in the reference's order with fused multiply-adds and must reproduce the oracle BIT FOR BIT.  Sizes
+The FP64 kernels accumulate in the reference's order with fused multiply-adds and must reproduce the oracle BIT FOR
+BIT; the FP32 tensor-core kernel is held to the component-wise bound of include/b200fe.h,
+|out - exact| <= 1e-5 * (|B1|^T |B0|^T |in|) for every single output (exact = the oracle in double).  Sizes
 are chosen so that the persistent CTAs loop over several tiles (more tiles than resident CTAs), inputs differ per
 element and interleave group, and an element with non-finite modes must not leak into its neighbours (the tensor-core
 kernel pads K with a value it reads from shared memory and zero-selects).
@@ -90,15 +93,52 @@ def test_hex_fp64_coa_pipe_kernel_bit_exact(G, nq, nelmt):
         G.fe.set_backend("auto")
 
 
+def componentwise_quad(got_em, nq, nelmt, b0, b1, inp_em):
+    d = np.float64
+    want = oracle.bwdtrans_quad(nq, nq, nelmt, b0.astype(d), b1.astype(d), inp_em.astype(d))
+    scale = oracle.bwdtrans_quad(nq, nq, nelmt, np.abs(b0).astype(d), np.abs(b1).astype(d), np.abs(inp_em).astype(d))
+    assert not np.isnan(got_em).any()
+    return float((np.abs(got_em.astype(d) - want) / scale).max())
+
+
+@pytest.mark.parametrize("nelmt", [32, 32 * 7, 32 * 151])  # 302 tiles of 16 > 2 x 148 resident CTAs
+def test_quad_nq32_fp32_tensor_core_kernel_meets_the_componentwise_bound(G, nelmt):
+    nq = 32
+    b0, b1, inp_em = [x.astype(np.float32) for x in quad_case(nq, nelmt, 4150 + nelmt)]
+    inp = oracle.to_coa(inp_em, nelmt, (nq - 1) ** 2)
+    got = G.run_quad("BwdTransQuadKernel_Coa", "f32", nq, nq, nelmt, b0, b1, inp)
+    assert G.fe.last_backend() == "coa-mma"  # the default route
+    err = componentwise_quad(oracle.from_coa(got, nelmt, nq * nq), nq, nelmt, b0, b1, inp_em)
+    assert err < 1e-5, err
+    again = G.run_quad("BwdTransQuadKernel_Coa", "f32", nq, nq, nelmt, b0, b1, inp)
+    assert np.array_equal(again, got)  # deterministic
+    try:
+        G.fe.set_backend("lanes")  # the bit-exact FP32 kernel stays available
+        exact = G.run_quad("BwdTransQuadKernel_Coa", "f32", nq, nq, nelmt, b0, b1, inp)
+        assert G.fe.last_backend() == "lanes"
+        assert np.array_equal(oracle.from_coa(exact, nelmt, nq * nq), oracle.bwdtrans_quad(nq, nq, nelmt, b0, b1, inp_em))
+    finally:
+        G.fe.set_backend("auto")
+
+
+def test_quad_nq32_fp32_reference_synthetic_input(G):
+    """the reference's own synthetic data (benchmark04.cc:831-850: sin / cos tables, heavy cancellation) through the
+    oracle's generators: still inside the component-wise bound"""
+    nq, nelmt = 32, 64
+    b0 = oracle.gen_basis(nq - 1, nq, np.float32)
+    inp_em = oracle.gen_in(nelmt, (nq - 1) ** 2, np.float32)
+    got = G.run_quad("BwdTransQuadKernel_Coa", "f32", nq, nq, nelmt, b0, b0, oracle.to_coa(inp_em, nelmt, (nq - 1) ** 2))
+    assert G.fe.last_backend() == "coa-mma"
+    assert componentwise_quad(oracle.from_coa(got, nelmt, nq * nq), nq, nelmt, b0, b0, inp_em) < 1e-5
+
+
 def test_forced_back_ends_where_they_have_no_instantiation(G):
     b0, b1, inp_em = quad_case(16, 32, 1)
     bh, inph = hex_case(6, 32, 2)
     try:
         G.fe.set_backend("mma")
-        with pytest.raises(Exception):  # interleaved quads on the tensor cores: FP64 nq = 32 only
+        with pytest.raises(Exception):  # interleaved quads on the tensor cores: nq = 32 only
             G.run_quad("BwdTransQuadKernel_Coa", "f64", 16, 16, 32, b0, b1, oracle.to_coa(inp_em, 32, 225))
-        with pytest.raises(Exception):  # ... and no FP32 twin
-            G.run_quad("BwdTransQuadKernel_Coa", "f32", 32, 32, 32, *[x.astype(np.float32) for x in quad_case(32, 32, 3)])
         G.fe.set_backend("pipe")
         with pytest.raises(Exception):  # interleaved hexes: FP64 nq = 8, 10 only
             G.run_hex("BwdTransHexKernel_Coa", "f64", (6, 6, 6), 32, bh, oracle.to_coa(inph, 32, 125))

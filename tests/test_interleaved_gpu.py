@@ -66,8 +66,11 @@ def test_quad_lanes_backend_bit_exact(G, suf, nq):
     # the default routing: lanes, except FP32 nq <= 6 where the thread-per-element kernel measured faster and FP64
     # nq = 32 on the tensor cores (tests/test_coa_large_nq_gpu.py)
     got = G.run_quad("BwdTransQuadKernel_Coa", suf, nq, nq, nelmt, b0, b1, inp)
-    assert G.fe.last_backend() == ("tpe" if suf == "f32" and nq <= 6 else "coa-mma" if suf == "f64" and nq == 32 else "lanes")
-    assert np.array_equal(oracle.from_coa(got, nelmt, nq * nq), want_em)
+    assert G.fe.last_backend() == ("tpe" if suf == "f32" and nq <= 6 else "coa-mma" if nq == 32 else "lanes")
+    if suf == "f32" and nq == 32:  # 3xTF32 tensor-core route: to rounding (tests/test_coa_large_nq_gpu.py holds the bound)
+        G.assert_parity(oracle.from_coa(got, nelmt, nq * nq), want_em, suf)
+    else:
+        assert np.array_equal(oracle.from_coa(got, nelmt, nq * nq), want_em)
 
 
 @pytest.mark.parametrize("suf", ["f64", "f32"])
