@@ -45,6 +45,28 @@ template <int N> __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// predicated stores: a store behind `if (ok)` is a branch, and with a branch after every row's block ptxas contracts
+// the R rows of a pass one after the other (constants reloaded per row, two dependent DFMA chains in flight); a
+// predicated store keeps the pass one basic block, so the rows really share the loads and interleave their chains
+__device__ __forceinline__ void st_shared_if(double *p, double v, bool ok)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.f64 [%0], %1; }" ::"r"(smem_addr(p)), "d"(v), "r"((unsigned)ok)
+                 : "memory");
+}
+__device__ __forceinline__ void st_shared_if(float *p, float v, bool ok)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.shared.f32 [%0], %1; }" ::"r"(smem_addr(p)), "f"(v), "r"((unsigned)ok)
+                 : "memory");
+}
+__device__ __forceinline__ void st_stream_if(double *p, double v, bool ok)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.global.cs.f64 [%0], %1; }" ::"l"(p), "d"(v), "r"((unsigned)ok) : "memory");
+}
+__device__ __forceinline__ void st_stream_if(float *p, float v, bool ok)
+{
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q st.global.cs.f32 [%0], %1; }" ::"l"(p), "f"(v), "r"((unsigned)ok) : "memory");
+}
+
 // R rows at once: NQ outputs of each of R rows of NM register values against bank matrix BOFF, in blocks of IB outputs
 // whose basis values (one 16-byte uniform load per 2 doubles / 4 floats) are shared by the R rows; st(k, i, v) consumes
 // output i of row k.  A pass is ONE straight-line block per tile, R = ceil(rows / workers): with a loop over the rows
@@ -186,10 +208,7 @@ __device__ __noinline__ void hex_coapipe_body(const T *__restrict__ in, T *__res
                 for (int m = 0; m < G; ++m)
                     db[k][m] = wk + (r * NQ2 + q * NQ + (m ^ (rho & (G - 1)))) * EL + e;
             }
-            coa_rows<T, NM, NQ, B0, R>(x, [&](int k, int i, T v) {
-                if (ok[k])
-                    db[k][i & (G - 1)][(i & ~(G - 1)) * EL] = v;
-            });
+            coa_rows<T, NM, NQ, B0, R>(x, [&](int k, int i, T v) { st_shared_if(db[k][i & (G - 1)] + (i & ~(G - 1)) * EL, v, ok[k]); });
         }
         __syncthreads();
         // the slot is drained: the next tile's gather runs under passes 1 and 2
@@ -217,10 +236,7 @@ __device__ __noinline__ void hex_coapipe_body(const T *__restrict__ in, T *__res
                 for (int q = 0; q < NM; ++q)
                     x[k][q] = cb[k][q & (G - 1)][(q * NQ) * EL];
             }
-            coa_rows<T, NM, NQ, B1, R>(x, [&](int k, int j, T v) {
-                if (ok[k])
-                    cb[k][j & (G - 1)][(j * NQ) * EL] = v;
-            });
+            coa_rows<T, NM, NQ, B1, R>(x, [&](int k, int j, T v) { st_shared_if(cb[k][j & (G - 1)] + (j * NQ) * EL, v, ok[k]); });
         }
         __syncthreads();
 
@@ -247,12 +263,15 @@ __device__ __noinline__ void hex_coapipe_body(const T *__restrict__ in, T *__res
                     x[k][r] = sb[(r * NM) & (G - 1)][(r * NQ2) * EL];
                 dst[k] = gout + 32 * ji;
             }
-            coa_rows<T, NM, NQ, B2, R>(x, [&](int k, int kk, T v) {
-                if (ok[k])
-                    st_stream(dst[k] + (size_t)32 * NQ2 * kk, v);
-            });
+            coa_rows<T, NM, NQ, B2, R>(x, [&](int k, int kk, T v) { st_stream_if(dst[k] + (size_t)32 * NQ2 * kk, v, ok[k]); });
         }
     }
 }
 
+// Tried and dropped (tools/tune/lanes_probe.cu history, profiles/r02_coa_probe.csv): a two-slot input ring with one CTA
+// per SM (0.61-0.69 at nq = 10 FP64); pass 1 with a barrier between its loads and its in-place stores (0.69); a q-outer
+// form that fuses directions 0 and 1 in registers and reads the rows from the staged slot (39 % fewer shared-memory
+// wavefronts, but 150 registers and 12 warps per SM: 0.66); 32-byte tiles (EL = 4 doubles: 0.60).  What bounds this
+// kernel at ~0.7 is the shared-memory data path next to the FP64 pipe: every 8-byte warp access is two wavefronts, a row
+// costs 38 of them per 90 DFMAs (84 % of the LSU at FP64 peak), and the two pipes overlap only across warps.
 } // namespace b200fe
