@@ -430,6 +430,34 @@ static int hex_iprod_lanes_switch(unsigned nq, unsigned nelmt, const T *in, cons
     }
 }
 
+// persistent TMA-fed row kernel ("iprod-pipe", sumfac_iprod.cuh).  tools/ipl_probe.py at 64 Mi points, fraction of the
+// roofline unweighted / weighted (profiles/r02_ipl_probe_hex.csv), (E, THREADS, R) from a sweep of six shapes per case:
+//                 rows          lanes         pipe
+//   FP64 nq =  8  0.67 / 0.92   0.67 / 0.69   0.78 / 0.85   (4, 256, 1)
+//   FP64 nq = 10  0.59 / 0.72   --            0.77 / 0.98   (1, 128, 1)
+//   FP32 nq =  8  0.52 / 0.77   0.63 / 0.65   0.71 / 0.85   (4, 256, 1)
+//   FP32 nq = 10  0.31 / 0.43   0.64 / 0.65   0.67 / 0.87   (1, 128, 1)
+static bool hex_has_iprod_pipe(unsigned nq)
+{
+    return nq == 8 || nq == 10;
+}
+static bool hex_prefers_iprod_pipe(unsigned nq, bool weighted)
+{
+    return hex_has_iprod_pipe(nq) && !(sizeof(T) == 8 && nq == 8 && weighted); // that one stays on the row kernel
+}
+static int hex_iprod_pipe_switch(unsigned nq, unsigned nelmt, const T *in, const T *w, T *out, cudaStream_t s)
+{
+    switch (nq)
+    {
+    case 8:
+        return launch_hex_iprod_pipe<T, 8, 4, 256, 1>(nelmt, in, w, out, s);
+    case 10:
+        return launch_hex_iprod_pipe<T, 10, 1, 128, 1>(nelmt, in, w, out, s);
+    default:
+        return B200FE_EUNSUPPORTED;
+    }
+}
+
 template <>
 int run_iproduct_hex<T>(Backend be, unsigned nq, unsigned nelmt, const T *b0, const T *b1, const T *b2, const T *w,
                         const T *in, T *out, cudaStream_t stream)
@@ -440,15 +468,20 @@ int run_iproduct_hex<T>(Backend be, unsigned nq, unsigned nelmt, const T *b0, co
     const bool has_any = hex_has_iprod_lanes(nq, false) || (nq == 8 && sizeof(T) == 8);
     if (be == Backend::Lanes && !(has_any && aligned))
         return B200FE_EUNSUPPORTED;
-    const bool lanes = be == Backend::Lanes || (be == Backend::Auto && hex_has_iprod_lanes(nq, w != nullptr) && aligned);
-    if (!lanes && be != Backend::Auto && be != Backend::Rows)
+    if (be == Backend::Pipe && !(hex_has_iprod_pipe(nq) && aligned))
+        return B200FE_EUNSUPPORTED;
+    const bool pipe  = be == Backend::Pipe || (be == Backend::Auto && hex_prefers_iprod_pipe(nq, w != nullptr) && aligned);
+    const bool lanes = !pipe && (be == Backend::Lanes || (be == Backend::Auto && hex_has_iprod_lanes(nq, w != nullptr) && aligned));
+    if (!lanes && !pipe && be != Backend::Auto && be != Backend::Rows)
         return B200FE_EUNSUPPORTED;
     std::lock_guard<std::mutex> lock(bank_lock_of_current_device());
     const T *bases[3]   = {b0, b1, b2};
     int rc = fill_basis_bank<T>(g_bank, 3, bases, (int)nq - 1, (int)nq, true, stream); // transposed
     if (rc)
         return rc;
-    rc = lanes ? hex_iprod_lanes_switch(nq, nelmt, in, w, out, stream) : hex_iprod_switch(nq, nelmt, in, w, out, stream);
+    rc = pipe    ? hex_iprod_pipe_switch(nq, nelmt, in, w, out, stream)
+         : lanes ? hex_iprod_lanes_switch(nq, nelmt, in, w, out, stream)
+                 : hex_iprod_switch(nq, nelmt, in, w, out, stream);
     // the fill is enqueued: record the bank's event on the error path too, or another stream's next fill could
     // overlap it
     const int rel = release_basis_bank(g_bank, stream);

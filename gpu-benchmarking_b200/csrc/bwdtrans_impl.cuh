@@ -552,6 +552,33 @@ int launch_hex_iprod(unsigned nelmt, const T *in, const T *w, T *out, cudaStream
     return launch_status();
 }
 
+// IProductWRTBase hex, persistent TMA-fed row kernel (sumfac_iprod.cuh, "iprod-pipe"): in / w 16-byte aligned
+template <typename T, int NQ, int E, int THREADS, int R>
+int launch_hex_iprod_pipe(unsigned nelmt, const T *in, const T *w, T *out, cudaStream_t stream)
+{
+    using CW = HexIprodPipe<T, NQ, E, true>;
+    using CP = HexIprodPipe<T, NQ, E, false>;
+    static_assert(CW::SMEM <= (size_t)kSmemMax, "tile does not fit shared memory");
+    static int occ_w[64] = {}, occ_p[64] = {};
+    const unsigned ntiles = (nelmt + E - 1) / E;
+    auto go = [&](auto kernel, size_t smem, int *occ) -> int {
+        int rc = opt_in_smem(kernel, smem);
+        if (rc)
+            return rc;
+        const unsigned fit  = (unsigned)(sm_count() * ctas_per_sm(kernel, THREADS, smem, occ));
+        const unsigned grid = ntiles < fit ? ntiles : fit;
+        B200FE_CUDA_TRY(launch_pdl(kernel, grid, THREADS, smem, stream, in, w, out, nelmt, ntiles));
+        return 0;
+    };
+    int rc = w ? go(iproduct_hex_pipe_kernel<T, NQ, E, THREADS, R, true>, CW::SMEM, occ_w)
+               : go(iproduct_hex_pipe_kernel<T, NQ, E, THREADS, R, false>, CP::SMEM, occ_p);
+    if (rc)
+        return rc;
+    count_launch();
+    t_last_backend = "iprod-pipe";
+    return launch_status();
+}
+
 // IProductWRTBase, lanes style (sumfac_iprod_lanes.cuh): in / w 16-byte aligned, even nq
 template <typename T, int NQ, int EL> int launch_quad_iprod_lanes(unsigned nelmt, const T *in, const T *w, T *out, cudaStream_t stream)
 {

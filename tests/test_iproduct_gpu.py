@@ -187,3 +187,55 @@ def test_lanes_kernel_forced_bit_exact(G, dim, suf, nq, weighted):
                           d_out.data_ptr())
     finally:
         G.fe.set_backend("auto")
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("suf,nq", [("f64", 8), ("f64", 10), ("f32", 8), ("f32", 10)])
+def test_hex_pipe_kernel_bit_exact_and_default_route(G, suf, nq, weighted):
+    """sumfac_iprod.cuh, persistent TMA-fed twin of the hex row kernel (round 2): forced and through the default
+    routing; one tile, ragged last tile, more tiles than resident CTAs (every CTA loops and refills its ring); a slab
+    that is not 16-byte aligned leaves the route (bulk copies need it) and is refused when forced; nothing is written
+    outside `out`"""
+    import torch
+    dt, nm = G.NP[suf], nq - 1
+    tdt = torch.float64 if suf == "f64" else torch.float32
+    rng = np.random.default_rng(1700 + nq)
+    b = [rng.standard_normal(nm * nq).astype(dt) for _ in range(3)]
+    d_b = [G.dev(x) for x in b]
+    for nelmt in (1, 5, 1001, 148 * 8 * 4 * 2 + 3):
+        inp = rng.standard_normal(nelmt * nq ** 3).astype(dt)
+        w = (rng.random(nelmt * nq ** 3) + 0.5).astype(dt) if weighted else None
+        want = oracle.iproduct_hex(nq, nq, nq, nelmt, *b, inp, w)
+        d_in, d_w = G.dev(inp), (G.dev(w) if weighted else None)
+        for forced in (True, False):
+            d_out = torch.full((nelmt * nm ** 3 + 2,), float("nan"), dtype=tdt, device="cuda")
+            try:
+                if forced:
+                    G.fe.set_backend("pipe")
+                G.fe.iproduct(suf, (nq,) * 3, nelmt, [x.data_ptr() for x in d_b], d_in.data_ptr(),
+                              d_out.data_ptr() + inp.itemsize, weights=d_w.data_ptr() if weighted else 0)
+                default_is_pipe = not (suf == "f64" and nq == 8 and weighted)  # that case measured faster on the row kernel
+                assert G.fe.last_backend() == ("iprod-pipe" if forced or default_is_pipe else "iprod-rows")
+            finally:
+                G.fe.set_backend("auto")
+            got = G.host(d_out)
+            assert np.isnan(got[0]) and np.isnan(got[-1])
+            assert np.array_equal(got[1:-1], want), (suf, nq, nelmt, forced, G.rel_max(got[1:-1], want))
+    # misaligned input slab
+    nelmt = 37
+    inp = rng.standard_normal(nelmt * nq ** 3).astype(dt)
+    want = oracle.iproduct_hex(nq, nq, nq, nelmt, *b, inp, None)
+    big_in = torch.zeros(inp.size + 4, dtype=tdt, device="cuda")
+    big_in[1:1 + inp.size] = G.dev(inp)
+    d_out = torch.full((nelmt * nm ** 3,), float("nan"), dtype=tdt, device="cuda")
+    G.fe.iproduct(suf, (nq,) * 3, nelmt, [x.data_ptr() for x in d_b], big_in.data_ptr() + inp.itemsize, d_out.data_ptr())
+    assert G.fe.last_backend() == "iprod-rows"
+    assert np.array_equal(G.host(d_out), want)
+    try:
+        G.fe.set_backend("pipe")
+        with pytest.raises(G.fe.B200feError):
+            G.fe.iproduct(suf, (nq,) * 3, nelmt, [x.data_ptr() for x in d_b], big_in.data_ptr() + inp.itemsize, d_out.data_ptr())
+        with pytest.raises(G.fe.B200feError):  # no instantiation at other nq, none for quads
+            G.fe.iproduct(suf, (6,) * 3, 8, [x.data_ptr() for x in d_b], d_out.data_ptr(), d_out.data_ptr())
+    finally:
+        G.fe.set_backend("auto")

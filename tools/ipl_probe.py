@@ -19,7 +19,8 @@ PEAK = 6546.9
 def main():
     st = torch.cuda.current_stream().cuda_stream
     print("op,nq,dtype,weighted,variant,backend,ms,hbm_frac,same_bits")
-    for dim, nqs in ((2, (4, 6, 8, 10, 12, 14, 16)), (3, (4, 6, 8, 10))):
+    only_hex = len(sys.argv) > 1 and sys.argv[1] == "hex"
+    for dim, nqs in ((3, (8, 10)),) if only_hex else ((2, (4, 6, 8, 10, 12, 14, 16)), (3, (4, 6, 8, 10))):
         for suf, tdt, size in (("f64", torch.float64, 8), ("f32", torch.float32, 4)):
             for nq in nqs:
                 nm = nq - 1
@@ -30,7 +31,7 @@ def main():
                 y = torch.empty(nelmt * nm ** dim, dtype=tdt, device="cuda")
                 for weighted in (0, 1):
                     ref = None
-                    variants = [("rows", None), ("mma", None), ("lanes", None)]  # tile sizes: tools/tune/iprod_probe.cu
+                    variants = [("rows", None), ("mma", None), ("lanes", None), ("pipe", None)]  # pipe: hexes nq = 8, 10  # tile sizes: tools/tune/iprod_probe.cu
                     for be, el in variants:
                         fe.set_backend(be)
                         def call():
