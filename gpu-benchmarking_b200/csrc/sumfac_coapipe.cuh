@@ -271,7 +271,9 @@ __device__ __noinline__ void hex_coapipe_body(const T *__restrict__ in, T *__res
 // Tried and dropped (tools/tune/lanes_probe.cu history, profiles/r02_coa_probe.csv): a two-slot input ring with one CTA
 // per SM (0.61-0.69 at nq = 10 FP64); pass 1 with a barrier between its loads and its in-place stores (0.69); a q-outer
 // form that fuses directions 0 and 1 in registers and reads the rows from the staged slot (39 % fewer shared-memory
-// wavefronts, but 150 registers and 12 warps per SM: 0.66); 32-byte tiles (EL = 4 doubles: 0.60).  What bounds this
+// wavefronts, but 150 registers and 12 warps per SM: 0.66); 32-byte tiles (EL = 4 doubles: 0.60); the gather as one small
+// bulk (TMA) copy per index of the tile (64 / 128 bytes each, issued by one warp, completion on an mbarrier) instead of
+// cp.async: 3.4x SLOWER (0.21) -- the copy engine is made for kilobytes per instruction, not for 729 tiny ones.  What bounds this
 // kernel at ~0.7 is the shared-memory data path next to the FP64 pipe: every 8-byte warp access is two wavefronts, a row
 // costs 38 of them per 90 DFMAs (84 % of the LSU at FP64 peak), and the two pipes overlap only across warps.
 } // namespace b200fe
