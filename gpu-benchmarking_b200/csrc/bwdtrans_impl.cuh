@@ -433,7 +433,7 @@ int launch_quad_coamma(unsigned nelmt, const float *b0, const float *b1, const f
     using C = QuadCoaMma32<NQ, WARPS>;
     static_assert(C::SMEM <= (size_t)kSmemMax, "region does not fit shared memory");
     static int occ[64] = {};
-    auto kernel        = bwdtrans_quad_coamma32_kernel<NQ, WARPS>;
+    auto kernel        = bwdtrans_quad_coamma32_kernel<NQ, WARPS, 3>; // 3 CTAs per SM (72 KB, 168 registers)
     int rc             = opt_in_smem(kernel, C::SMEM);
     if (rc)
         return rc;

@@ -200,10 +200,11 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
 // M = 16 elements: a tile is 16 consecutive elements of an interleave group, the unit (one index of the tile) is again
 // 64 bytes, so region, gather and the two-bit swizzles are those of the FP64 kernel with 8-float quarters.  A lane's A
 // fragment is (e = g, g + 8) x (k = t, t + 4): four 4-byte loads per k step, each conflict-free across the warp.  The
-// data is split on the fly (3 ALU instructions per value), the basis once per CTA into a fragment area in shared
-// memory ([ks][n][lane] x {hi b0, hi b1, lo b0, lo b1}: one 16-byte load per fragment, reloaded per direction).
-// Measured (tools/tune/lanes_probe.cu): 0.48 of the roofline, HMMA pipe 59 % busy (profiles/r02_ncu_quad32_f32_coamma.txt);
-// issuing two rows' chains interleaved instead of prefetching the next row was slower (0.45).
+// data is split on the fly (3 ALU instructions per value); the basis sits in a fragment-ordered area in shared memory
+// ([ks][n][lane] x {b0, b1}, raw FP32: 8 KB for both matrices) and is loaded + split once per direction and tile.
+// Measured (tools/tune/lanes_probe.cu): 0.49 of the roofline with 4 warps x 3 CTAs per SM (168 registers, 72 KB; 0.48 with
+// two CTAs at 254 registers), HMMA pipe 59 % busy (profiles/r02_ncu_quad32_f32_coamma.txt); issuing two rows' chains
+// interleaved instead of prefetching the next row was slower (0.45).
 // Not bit-identical to the reference's FFMA chain: held to the component-wise 1e-5 bound of include/b200fe.h like the
 // element-major tensor-core kernels (measured 7e-7 of the largest output); b200fe_set_backend("lanes") keeps the
 // bit-exact kernel.
@@ -213,15 +214,15 @@ template <int NQ, int WARPS> struct QuadCoaMma32
     static constexpr int EL = 16, NM = NQ - 1, NM2 = NM * NM, NQ2 = NQ * NQ;
     static constexpr int KS = NQ / 8, NT = NQ / 8;
     static constexpr int S1   = NQ * NQ * EL;       // floats: nm rows of nq units + one spare row
-    static constexpr int FRAG = KS * NT * 32 * 4;   // words per basis matrix
+    static constexpr int FRAG = KS * NT * 32 * 2;   // words per basis matrix: [ks][n][lane] x {b0, b1}, raw FP32
     static constexpr size_t SMEM = (size_t)(S1 + 2 * FRAG) * sizeof(float);
     static constexpr int THREADS = WARPS * 32;
     static constexpr int PER = 32 / EL;
     static constexpr int ROWS = (NM + WARPS - 1) / WARPS, COLS = (NQ + WARPS - 1) / WARPS; // per warp
 };
 
-template <int NQ, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2)
+template <int NQ, int WARPS, int MINB = 2>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
     bwdtrans_quad_coamma32_kernel(const float *__restrict__ b0, const float *__restrict__ b1,
                                   const float *__restrict__ in, float *__restrict__ out, unsigned ntiles)
 {
@@ -229,8 +230,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
     constexpr int NM = C::NM, NM2 = C::NM2, KS = C::KS, NT = C::NT, EL = C::EL, PER = C::PER;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s1     = reinterpret_cast<float *>(smem_raw);
-    unsigned *fr0 = reinterpret_cast<unsigned *>(s1 + C::S1);
-    unsigned *fr1 = fr0 + C::FRAG;
+    float *fr0 = s1 + C::S1;
+    float *fr1 = fr0 + C::FRAG;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -240,16 +241,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
     {
         const int l = f & 31, tt = f >> 5, ks = tt / NT, nt = tt - ks * NT;
         const int k = 8 * ks + (l & 3), n = 8 * nt + (l >> 2);
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
-        {
-            const float *b = m ? b1 : b0;
-            unsigned *fr   = m ? fr1 : fr0;
-            unsigned h0, l0, h1, l1;
-            tf32_split(k < NM ? b[k * NQ + n] : 0.f, h0, l0);
-            tf32_split(k + 4 < NM ? b[(k + 4) * NQ + n] : 0.f, h1, l1);
-            *reinterpret_cast<uint4 *>(fr + 4 * f) = make_uint4(h0, h1, l0, l1);
-        }
+        *reinterpret_cast<float2 *>(fr0 + 2 * f) = make_float2(k < NM ? b0[k * NQ + n] : 0.f, k + 4 < NM ? b0[(k + 4) * NQ + n] : 0.f);
+        *reinterpret_cast<float2 *>(fr1 + 2 * f) = make_float2(k < NM ? b1[k * NQ + n] : 0.f, k + 4 < NM ? b1[(k + 4) * NQ + n] : 0.f);
     }
 
     auto issue = [&](unsigned tile) {
@@ -309,12 +302,17 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
             }
         }
     };
-    auto load_frags = [&](uint4 (&f)[KS][NT], const unsigned *fr) {
+    // one 8-byte load per fragment, split here (exactly: both halves rounded to tf32) once per direction and tile
+    auto load_frags = [&](uint4 (&f)[KS][NT], const float *fr) {
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
             for (int n = 0; n < NT; ++n)
-                f[ks][n] = *reinterpret_cast<const uint4 *>(fr + 4 * ((ks * NT + n) * 32 + lane));
+            {
+                const float2 v = *reinterpret_cast<const float2 *>(fr + 2 * ((ks * NT + n) * 32 + lane));
+                tf32_split(v.x, f[ks][n].x, f[ks][n].z);
+                tf32_split(v.y, f[ks][n].y, f[ks][n].w);
+            }
     };
     // direction 0, row q: u = nq*q + 8 ks + t (+ 4): bit 1 of u is that of t
     const int e0row = g ^ (4 * (t & 2));

@@ -205,8 +205,8 @@ template <typename T> struct Case
 #define CM(NQ, WARPS)                                                                                        \
     c.run_args("coa-mma WARPS=" #WARPS, bwdtrans_quad_coamma_kernel<NQ, WARPS>, 0u, WARPS * 32,                \
                QuadCoaMma<NQ, WARPS>::SMEM, (const double *)c.b[0], (const double *)c.b[1], (const double *)c.in, c.out, c.nelmt / 8);
-#define CM32(NQ, WARPS)                                                                                      \
-    c.run_args("coa-mma32 WARPS=" #WARPS, bwdtrans_quad_coamma32_kernel<NQ, WARPS>, 0u, WARPS * 32,            \
+#define CM32(NQ, WARPS, MB)                                                                                  \
+    c.run_args("coa-mma32 WARPS=" #WARPS " MINB=" #MB, bwdtrans_quad_coamma32_kernel<NQ, WARPS, MB>, 0u, WARPS * 32, \
                QuadCoaMma32<NQ, WARPS>::SMEM, (const float *)c.b[0], (const float *)c.b[1], (const float *)c.in, c.out, c.nelmt / 16);
 
 int main(int argc, char **argv)
@@ -244,7 +244,7 @@ int main(int argc, char **argv)
     {
         Case<float> c;
         c.setup(2, 32);
-        QL(float, 32, 16) CM32(32, 4) CM32(32, 6) CM32(32, 8) CM32(32, 2)
+        QL(float, 32, 16) CM32(32, 4, 2) CM32(32, 4, 3) CM32(32, 3, 3) CM32(32, 2, 3) CM32(32, 6, 2) CM32(32, 5, 3)
         c.teardown();
         return 0;
     }
@@ -261,7 +261,7 @@ int main(int argc, char **argv)
         cf.setup(2, 32);
         {
             auto &c = cf;
-            CM32(32, 4)
+            CM32(32, 4, 2)
         }
         cf.teardown();
         return 0;
