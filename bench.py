@@ -301,6 +301,9 @@ def main():
         raise SystemExit("bench.py: device is not compute capability 10.x (B200)")
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # rank 0's stdout carries exactly one JSON line: NCCL's own banner / debug output (the boxes export
+        # NCCL_DEBUG=VERSION, which prints "NCCL version ..." to stdout) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ngpus = world
 
