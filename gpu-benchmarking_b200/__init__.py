@@ -12,7 +12,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libb200fe.so")
+LIB_PATH = os.environ.get("B200FE_LIB") or os.path.join(_HERE, "libb200fe.so")  # (B200FE_LIB: an experimental build)
 HEADER = os.path.join(ROOT, "include", "b200fe.h")
 
 E_OK, E_INVAL, E_UNSUPPORTED, E_ALIGN, E_NODEVICE = 0, -1, -2, -3, -4
