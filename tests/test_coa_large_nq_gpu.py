@@ -258,3 +258,25 @@ def test_baseline_size_every_element_equal(G, which):
     torch.cuda.synchronize()
     view = d_out.reshape(nelmt // 32, nq ** dim, 32)
     assert bool((view == G.dev(want).reshape(1, -1, 1)).all())
+
+
+def test_quad_nq32_fp32_baseline_size_every_element_equal(G):
+    """64 Mi points on the FP32 tensor-core kernel: identical elements must give identical outputs in every (group,
+    lane) -- bit for bit, the kernel is deterministic -- and element 0 meets the component-wise bound"""
+    import torch
+    nq, nm = 32, 31
+    nelmt = (64 << 20) // nq ** 2 // 32 * 32
+    rng = np.random.default_rng(4600)
+    b0, b1 = rnd(rng, nm * nq, np.float32), rnd(rng, nm * nq, np.float32)
+    one = rnd(rng, nm * nm, np.float32)
+    d_in = G.dev(one).repeat_interleave(32).reshape(1, -1).repeat(nelmt // 32, 1).reshape(-1).contiguous()
+    d_b0, d_b1 = G.dev(b0), G.dev(b1)
+    d_out = torch.empty(nelmt * nq * nq, dtype=torch.float32, device="cuda")
+    G.fe.bwdtrans_quad("BwdTransQuadKernel_Coa", "f32", nq, nq, nelmt, d_b0.data_ptr(), d_b1.data_ptr(), d_in.data_ptr(),
+                       d_out.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    assert G.fe.last_backend() == "coa-mma"
+    torch.cuda.synchronize()
+    view = d_out.reshape(nelmt // 32, nq * nq, 32)
+    first = view[0, :, 0].clone()
+    assert bool((view == first.reshape(1, -1, 1)).all())
+    assert componentwise_quad(G.host(first), nq, 1, b0, b1, one) < 1e-5
