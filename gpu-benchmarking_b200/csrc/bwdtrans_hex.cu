@@ -434,7 +434,7 @@ static int hex_iprod_lanes_switch(unsigned nq, unsigned nelmt, const T *in, cons
 // roofline unweighted / weighted (profiles/r02_ipl_probe_hex.csv), (E, THREADS, R) from a sweep of six shapes per case:
 //                 rows          lanes         pipe
 //   FP64 nq =  8  0.67 / 0.92   0.67 / 0.69   0.78 / 0.85   (4, 256, 1)
-//   FP64 nq = 10  0.59 / 0.72   --            0.77 / 0.98   (1, 128, 1)
+//   FP64 nq = 10  0.59 / 0.72   --            0.83 / 0.98   (3, 320, 1) unweighted, (1, 128, 1) weighted
 //   FP32 nq =  8  0.52 / 0.77   0.63 / 0.65   0.71 / 0.85   (4, 256, 1)
 //   FP32 nq = 10  0.31 / 0.43   0.64 / 0.65   0.67 / 0.87   (1, 128, 1)
 static bool hex_has_iprod_pipe(unsigned nq)
@@ -452,6 +452,9 @@ static int hex_iprod_pipe_switch(unsigned nq, unsigned nelmt, const T *in, const
     case 8:
         return launch_hex_iprod_pipe<T, 8, 4, 256, 1>(nelmt, in, w, out, s);
     case 10:
+        if constexpr (sizeof(T) == 8)
+            if (!w) // unweighted FP64: 3 elements x 320 threads (one round per pass) 0.83 against 0.78
+                return launch_hex_iprod_pipe<T, 10, 3, 320, 1>(nelmt, in, w, out, s);
         return launch_hex_iprod_pipe<T, 10, 1, 128, 1>(nelmt, in, w, out, s);
     default:
         return B200FE_EUNSUPPORTED;
