@@ -94,6 +94,11 @@ def set_bank_fill(mode):
     _check("b200fe_set_bank_fill", lib().b200fe_set_bank_fill(mode.encode()))
 
 
+def set_gather(mode):
+    """ "tma" (tiled TMA through a tensor map, default) | "cp.async": how the coa-pipe kernels fetch their tile"""
+    _check("b200fe_set_gather", lib().b200fe_set_gather(mode.encode()))
+
+
 QUAD_WSP = ("BwdTransQuadKernel", "BwdTransQuadKernel_Coa", "BwdTransQuadKernel_QP", "BwdTransQuadKernel_QP_1D")
 QUAD_NOWSP = ("BwdTransQuadKernel_QP_Shared", "BwdTransQuadKernel_QP_1D_Shared")
 HEX_WSP = ("BwdTransHexKernel", "BwdTransHexKernel_Coa", "BwdTransHexKernel_QP", "BwdTransHexKernel_QP_1D")

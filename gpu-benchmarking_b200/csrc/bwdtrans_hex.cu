@@ -205,8 +205,8 @@ static int hex_lanes_switch(unsigned nq, unsigned nelmt, const T *in, T *out, cu
 
 // interleaved layout, coa-pipe back-end (sumfac_coapipe.cuh): FP64 at the nq where a plane of the element no longer
 // fits the registers of a lanes worker.  tools/tune/lanes_probe.cu at 64 Mi points (profiles/r02_coa_probe.csv):
-//   nq = 10   lanes (q-outer) 0.49   coa-pipe 0.72 (16 elements per tile = whole 128-byte lines, 50 workers, 1 CTA / SM)
-//   nq =  8   lanes (planes)  0.81   coa-pipe 0.87 ( 8 elements per tile, 32 workers, 3 CTAs / SM)
+//   nq = 10   lanes (q-outer) 0.49   coa-pipe 0.74 (8 elements per tile, 52 workers, 2 CTAs / SM; 0.70 with the cp.async gather)
+//   nq =  8   lanes (planes)  0.81   coa-pipe 0.89 (8 elements per tile, 32 workers, 3 CTAs / SM; 0.87 with the cp.async gather)
 static bool hex_has_coapipe(unsigned nq)
 {
     return sizeof(T) == 8 && (nq == 8 || nq == 10);
@@ -216,7 +216,7 @@ static int hex_coapipe_switch(unsigned nq, unsigned nelmt, const T *in, T *out, 
     if constexpr (sizeof(T) == 8)
     {
         if (nq == 10)
-            return launch_hex_coapipe<T, 10, 16, 50, 1>(nelmt, in, out, s);
+            return launch_hex_coapipe<T, 10, 8, 52, 2>(nelmt, in, out, s);
         if (nq == 8)
             return launch_hex_coapipe<T, 8, 8, 32, 2>(nelmt, in, out, s);
     }

@@ -391,16 +391,33 @@ template <typename T, int NQ, int EL, int NW, int MINB>
 int launch_hex_coapipe(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
 {
     using C = HexCoaPipe<T, NQ, EL, NW>;
-    static_assert(C::SMEM <= (size_t)kSmemMax, "slot + work region do not fit shared memory");
-    static int occ[64] = {};
-    auto kernel        = bwdtrans_hex_coapipe_kernel<T, NQ, EL, NW, MINB>;
-    int rc             = opt_in_smem(kernel, C::SMEM);
-    if (rc)
-        return rc;
+    static_assert(C::SMEM_TMA <= (size_t)kSmemMax, "slot + work region do not fit shared memory");
+    static int occ[64] = {}, occ_tma[64] = {};
     const unsigned ntiles = nelmt / EL; // nelmt % 32 == 0 is checked at the C ABI: every tile is full
-    const unsigned fit    = (unsigned)(sm_count() * ctas_per_sm(kernel, C::THREADS, C::SMEM, occ));
-    const unsigned grid   = ntiles < fit ? ntiles : fit;
-    B200FE_CUDA_TRY(launch_pdl(kernel, grid, C::THREADS, C::SMEM, stream, in, out, ntiles));
+    // the gather through a tensor map of the interleaved array (tiled TMA, one instruction per 256 indices); without the
+    // driver entry point (or if the encode is refused) the 16-byte cp.async gather, same kernel otherwise
+    CUtensorMap map;
+    if (g_tensor_map_gather.load(std::memory_order_relaxed) &&
+        make_coa_tensor_map<T>(&map, in, (unsigned)C::NM3, nelmt / 32, (unsigned)EL, (unsigned)C::BOXR))
+    {
+        auto kernel = bwdtrans_hex_coapipe_tma_kernel<T, NQ, EL, NW, MINB>;
+        int rc      = opt_in_smem(kernel, C::SMEM_TMA);
+        if (rc)
+            return rc;
+        const unsigned fit  = (unsigned)(sm_count() * ctas_per_sm(kernel, C::THREADS, C::SMEM_TMA, occ_tma));
+        const unsigned grid = ntiles < fit ? ntiles : fit;
+        B200FE_CUDA_TRY(launch_pdl(kernel, grid, C::THREADS, C::SMEM_TMA, stream, map, out, ntiles));
+    }
+    else
+    {
+        auto kernel = bwdtrans_hex_coapipe_kernel<T, NQ, EL, NW, MINB>;
+        int rc      = opt_in_smem(kernel, C::SMEM);
+        if (rc)
+            return rc;
+        const unsigned fit  = (unsigned)(sm_count() * ctas_per_sm(kernel, C::THREADS, C::SMEM, occ));
+        const unsigned grid = ntiles < fit ? ntiles : fit;
+        B200FE_CUDA_TRY(launch_pdl(kernel, grid, C::THREADS, C::SMEM, stream, in, out, ntiles));
+    }
     count_launch();
     t_last_backend = "coa-pipe";
     return launch_status();

@@ -18,6 +18,7 @@ thread_local const char *t_last_backend = "none";
 thread_local unsigned long long t_bank_tag = 0; // common.cuh: non-zero only inside a b200fe_plan_* call
 static std::atomic<unsigned long long> g_next_plan_id{1};
 static std::atomic<int> g_forced_backend{-1}; // -1: per-entry-point default
+std::atomic<int> g_tensor_map_gather{1};      // common.cuh: tiled-TMA gather of the interleaved hex tiles (sumfac_coapipe.cuh)
 std::atomic<int> g_bank_fill_mode{0};         // common.cuh: 0 kernel + programmatic dependent launch, 1 staging + cudaMemcpyToSymbolAsync
 
 static Backend pick(Backend preferred)
@@ -460,6 +461,19 @@ int b200fe_set_bank_fill(const char *mode)
         g_bank_fill_mode = 0;
     else if (!strcmp(mode, "memcpy"))
         g_bank_fill_mode = 1;
+    else
+        return B200FE_EINVAL;
+    return B200FE_OK;
+}
+
+int b200fe_set_gather(const char *mode)
+{
+    if (!mode)
+        return B200FE_EINVAL;
+    if (!strcmp(mode, "tma"))
+        g_tensor_map_gather = 1;
+    else if (!strcmp(mode, "cp.async"))
+        g_tensor_map_gather = 0;
     else
         return B200FE_EINVAL;
     return B200FE_OK;

@@ -201,6 +201,9 @@ extern thread_local unsigned long long t_bank_tag;
 // cudaMemcpyToSymbolAsync (device to device) moves it into the bank -- only documented CUDA behaviour (constant
 // memory written by the runtime, ordinary stream order), ~3 us more stream time per per-call operator.
 extern std::atomic<int> g_bank_fill_mode;
+// b200fe_set_gather (capi.cu): 1 (default) = the interleaved hex kernels gather their tile by tiled TMA through a tensor
+// map where the driver offers the encoder, 0 = always the cp.async gather
+extern std::atomic<int> g_tensor_map_gather;
 
 // Bank layout: matrix d occupies rows [d*nrows, (d+1)*nrows) of `pitch` values each, pitch = the row length
 // rounded up to a whole 16-byte vector (bank_pitch), so that every row -- and every block of 2 / 4 consecutive

@@ -12,12 +12,16 @@
 //     pass 0   rows (r, q):  in[r][q][.]  -> s1[r][q][i]
 //     pass 1   rows (r, i):  s1[r][.][i]  -> s2[r][j][i]
 //     pass 2   rows (j, i):  s2[.][j][i]  -> out[.][j][i]   straight to global, runs of EL values
-// The gather of the tile (runs of EL*sizeof(T) = 32 / 64 / 128 bytes, 128 bytes apart) is done with 16-byte
-// cp.async copies: asynchronous, no registers held, whole sectors.  Persistent CTAs; shared memory is the input slot
+// The gather of the tile (runs of EL*sizeof(T) = 64 / 128 bytes, 256 bytes apart) is TILED TMA: the interleaved array is
+// described to the copy engine as a rank-3 tensor {32 elements, nm^3 indices, groups} (tensormap.h) and a box of
+// {EL, 256, 1} lands dense, as [idx][e], in the slot -- one cp.async.bulk.tensor instruction per 256 indices, issued by
+// one thread, completion on an mbarrier (SASS UTMALDG).  Without the driver entry point that encodes the map the same
+// kernel gathers with 16-byte cp.async copies issued by every thread (0.70 instead of 0.74 at nq = 10: the copies compete
+// with the passes for the LSU / MIO queues).  Persistent CTAs; shared memory is the input slot
 // plus ONE work region of nm planes x nq x nq indices: pass 0 goes slot -> work (s1[r][q][i], nm of a plane's nq
 // rows), after which the slot is free and the next tile's gather is issued at once (it lands under passes 1 and 2);
 // pass 1 runs IN PLACE, column by column (s2[r][j][i] overwrites s1[r][q = j][i], a thread owns its column, no barrier
-// inside the pass); pass 2 goes work -> global.  Three barriers per tile.  104 KB at nq = 10 FP64 with 8 elements
+// inside the pass); pass 2 goes work -> global.  Three barriers per tile.  107 KB at nq = 10 FP64 with 8 elements
 // per tile: two CTAs per SM, each with its own prefetch.
 // Bank conflicts: a warp touches 32/EL rows at once, U = EL*sizeof(T) bytes each (64 here: two per bank window).  The
 // row stride of the slot is nm*U (nm odd: consecutive rows alternate between the halves of a window).  The work
@@ -28,6 +32,7 @@
 #pragma once
 
 #include "sumfac_lanes.cuh"
+#include "tensormap.h"
 
 namespace b200fe
 {
@@ -43,6 +48,15 @@ __device__ __forceinline__ void cp_async_commit()
 template <int N> __device__ __forceinline__ void cp_async_wait()
 {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// one box of a rank-3 tensor map -> shared memory (tiled TMA), completion on an mbarrier
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                     smem_addr(smem_dst)),
+                 "l"(map), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
 }
 
 // predicated stores: a store behind `if (ok)` is a branch, and with a branch after every row's block ptxas contracts
@@ -139,21 +153,37 @@ template <typename T, int NQ, int EL, int NW> struct HexCoaPipe
     static constexpr int SW  = NM * NQ2 * EL;  // the work region: planes of nq x nq indices (s1 fills nm of the nq rows)
     static constexpr size_t SMEM = (size_t)(SIN + SW) * sizeof(T);
     static constexpr int PER = 32 / EL; // tiles per interleave group
+    // tiled-TMA gather: boxes of {EL, 256, 1} (a shared-memory destination must be 128-byte aligned, so the box height is
+    // a power of two; the rows of the last box beyond nm^3 are out of bounds in the map and arrive as zeros)
+    static constexpr int BOXR = 256, NBOX = (NM3 + BOXR - 1) / BOXR;
+    static constexpr int SIN_TMA = NBOX * BOXR * EL;
+    static constexpr size_t SMEM_TMA = (size_t)(SIN_TMA + SW) * sizeof(T) + 16; // + the mbarrier
 };
 
-template <typename T, int NQ, int EL, int NW, int MINB>
-__device__ __noinline__ void hex_coapipe_body(const T *__restrict__ in, T *__restrict__ out, unsigned ntiles);
+// TMAP: the gather is NBOX tiled-TMA copies (cp.async.bulk.tensor through a tensor map of the interleaved array, issued
+// by one thread, completion on an mbarrier) instead of 16-byte cp.async copies issued by every thread.
+template <typename T, int NQ, int EL, int NW, int MINB, bool TMAP>
+__device__ __noinline__ void hex_coapipe_body(const T *__restrict__ in, T *__restrict__ out, unsigned ntiles,
+                                              const CUtensorMap *map);
 
 template <typename T, int NQ, int EL, int NW, int MINB = 1>
 __global__ void __launch_bounds__(HexCoaPipe<T, NQ, EL, NW>::THREADS, MINB)
     bwdtrans_hex_coapipe_kernel(const T *__restrict__ in, T *__restrict__ out, unsigned ntiles)
 {
     pdl_wait(); // programmatic dependent of the bank fill; the body is a real call (common.cuh)
-    hex_coapipe_body<T, NQ, EL, NW, MINB>(in, out, ntiles);
+    hex_coapipe_body<T, NQ, EL, NW, MINB, false>(in, out, ntiles, nullptr);
+}
+template <typename T, int NQ, int EL, int NW, int MINB = 1>
+__global__ void __launch_bounds__(HexCoaPipe<T, NQ, EL, NW>::THREADS, MINB)
+    bwdtrans_hex_coapipe_tma_kernel(const __grid_constant__ CUtensorMap map, T *__restrict__ out, unsigned ntiles)
+{
+    pdl_wait();
+    hex_coapipe_body<T, NQ, EL, NW, MINB, true>(nullptr, out, ntiles, &map);
 }
 
-template <typename T, int NQ, int EL, int NW, int MINB>
-__device__ __noinline__ void hex_coapipe_body(const T *__restrict__ in, T *__restrict__ out, unsigned ntiles)
+template <typename T, int NQ, int EL, int NW, int MINB, bool TMAP>
+__device__ __noinline__ void hex_coapipe_body(const T *__restrict__ in, T *__restrict__ out, unsigned ntiles,
+                                              const CUtensorMap *map)
 {
     using C           = HexCoaPipe<T, NQ, EL, NW>;
     constexpr int NM = C::NM, NM2 = C::NM2, NM3 = C::NM3, NQ2 = C::NQ2, G = C::G, PER = C::PER;
@@ -161,30 +191,57 @@ __device__ __noinline__ void hex_coapipe_body(const T *__restrict__ in, T *__res
     constexpr int VW = 16 / (int)sizeof(T), CH = C::U / 16; // values per 16-byte chunk, chunks per index
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T *slot = reinterpret_cast<T *>(smem_raw);
-    T *wk   = slot + C::SIN; // the work region: s1[r][q][i] after pass 0, s2[r][j][i] (in place) after pass 1
+    T *wk   = slot + (TMAP ? C::SIN_TMA : C::SIN); // the work region: s1[r][q][i] after pass 0, s2[r][j][i] (in place) after pass 1
 
     const int tid = threadIdx.x, e = tid % EL;
     const int w   = tid / EL < NW ? tid / EL : (1 << 20); // the threads that pad the last warp own no row (ok = false)
 
+    uint64_t *bar = reinterpret_cast<uint64_t *>(wk + C::SW); // (TMAP only)
+    if constexpr (TMAP)
+    {
+        if (tid == 0)
+        {
+            mbar_init(bar, 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+    }
     auto issue = [&](unsigned tile) {
         const unsigned group = tile / PER, l0 = (tile % PER) * EL;
-        const T *g           = in + (size_t)group * 32 * NM3 + l0;
-#pragma unroll 4
-        for (int c = tid; c < NM3 * CH; c += C::THREADS)
+        if constexpr (TMAP)
         {
-            const int idx = c / CH, part = c - idx * CH;
-            cp_async16(slot + c * VW, g + (size_t)idx * 32 + part * VW);
+            if (tid == 0) // (called behind a barrier: every generic-proxy read of the slot is done)
+            {
+                fence_proxy_async();
+                mbar_arrive_expect_tx(bar, (unsigned)(C::SIN_TMA * sizeof(T))); // whole boxes, the zero-filled rows too
+#pragma unroll
+                for (int b = 0; b < C::NBOX; ++b)
+                    tma_load_3d(slot + b * C::BOXR * EL, map, (int)l0, b * C::BOXR, (int)group, bar);
+            }
         }
-        cp_async_commit();
+        else
+        {
+            const T *g = in + (size_t)group * 32 * NM3 + l0;
+#pragma unroll 4
+            for (int c = tid; c < NM3 * CH; c += C::THREADS)
+            {
+                const int idx = c / CH, part = c - idx * CH;
+                cp_async16(slot + c * VW, g + (size_t)idx * 32 + part * VW);
+            }
+            cp_async_commit();
+        }
     };
 
-    unsigned tile = blockIdx.x;
+    unsigned tile = blockIdx.x, it = 0;
     if (tile < ntiles)
         issue(tile);
 #pragma unroll 1
-    for (; tile < ntiles; tile += gridDim.x)
+    for (; tile < ntiles; tile += gridDim.x, ++it)
     {
-        cp_async_wait<0>();
+        if constexpr (TMAP)
+            mbar_wait(bar, it & 1u);
+        else
+            cp_async_wait<0>();
         __syncthreads(); // the tile has landed; every warp has left pass 2 of the previous tile (the work region is free)
 
         // pass 0: rows rho = (r, q); worker w takes rho = w, w + NW, ... all at once.  Row (r, q) of the work region

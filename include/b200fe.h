@@ -389,6 +389,12 @@ int b200fe_set_backend(const char *name);
  *                       documented CUDA behaviour, ~3 us more stream time per per-call operator (plans skip the
  *                       fill either way).  Results are bit-identical.  Process-wide; returns 0 or B200FE_EINVAL. */
 int b200fe_set_bank_fill(const char *mode);
+/* How the interleaved (_Coa) hex kernels of round 2 (coa-pipe: FP64 nq = 8, 10) fetch their tile: "tma" (default) =
+ * tiled TMA (cp.async.bulk.tensor) through a tensor map of the interleaved array, encoded per call with the driver's
+ * cuTensorMapEncodeTiled (looked up through the runtime; if the driver does not offer it the library falls back by
+ * itself); "cp.async" = 16-byte asynchronous copies issued by every thread.  Same kernel, bit-identical results.
+ * Process-wide; returns 0 or B200FE_EINVAL. */
+int b200fe_set_gather(const char *mode);
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -77,12 +77,13 @@ def test_no_kernel_reads_the_constant_bank_before_its_dependency_wait():
 
 def test_the_library_carries_blackwell_tensor_core_code():
     """SASS evidence of the tcgen05 path (csrc/sumfac_umma.cuh): UTCHMMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st,
-    UBLKCP = bulk (TMA) copies; DMMA = the FP64 tensor path (tcgen05 has no f64 kind)"""
+    UBLKCP = bulk (TMA) copies, UTMALDG = tiled TMA through a tensor map (the gather of the interleaved layout,
+    csrc/sumfac_coapipe.cuh); DMMA = the FP64 tensor path (tcgen05 has no f64 kind)"""
     import subprocess
     import pytest
     exe = "/usr/local/cuda/bin/cuobjdump"
     if not os.path.exists(exe):
         pytest.skip("cuobjdump not available")
     sass = subprocess.run([exe, "-sass", fe.LIB_PATH], capture_output=True, text=True, check=True).stdout
-    for op in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "DMMA", "UTCBAR"):
+    for op in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "DMMA", "UTCBAR"):
         assert sass.count(op) > 0, op

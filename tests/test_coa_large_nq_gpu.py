@@ -132,6 +132,26 @@ def test_quad_nq32_fp32_reference_synthetic_input(G):
     assert componentwise_quad(oracle.from_coa(got, nelmt, nq * nq), nq, nelmt, b0, b0, inp_em) < 1e-5
 
 
+@pytest.mark.parametrize("nq,nelmt", [(10, 32 * 80), (8, 32 * 250)])
+def test_hex_coa_pipe_gather_routes_agree(G, nq, nelmt):
+    """the tile is gathered by tiled TMA through a tensor map (default) or, where the driver does not offer the
+    encoder, by 16-byte cp.async copies: same kernel otherwise, same bits -- b200fe_set_gather forces either"""
+    b, inp_em = hex_case(nq, nelmt, 4250 + nq)
+    want_em = oracle.bwdtrans_hex(nq, nq, nq, nelmt, *b, inp_em)
+    inp = oracle.to_coa(inp_em, nelmt, (nq - 1) ** 3)
+    try:
+        for mode in ("cp.async", "tma"):
+            G.fe.set_gather(mode)
+            n0 = G.fe.launch_count()
+            got = G.run_hex("BwdTransHexKernel_Coa", "f64", (nq, nq, nq), nelmt, b, inp)
+            assert G.fe.last_backend() == "coa-pipe" and G.fe.launch_count() - n0 == 2  # bank fill + operator
+            assert np.array_equal(oracle.from_coa(got, nelmt, nq ** 3), want_em), mode
+        with pytest.raises(Exception):
+            G.fe.set_gather("ldg")
+    finally:
+        G.fe.set_gather("tma")
+
+
 def test_forced_back_ends_where_they_have_no_instantiation(G):
     b0, b1, inp_em = quad_case(16, 32, 1)
     bh, inph = hex_case(6, 32, 2)

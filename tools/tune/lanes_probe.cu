@@ -202,6 +202,15 @@ template <typename T> struct Case
 #define CP(T, NQ, EL, NW, MB)                                                                                \
     c.run_args("coa-pipe EL=" #EL " NW=" #NW " MINB=" #MB, bwdtrans_hex_coapipe_kernel<T, NQ, EL, NW, MB>, 0u,  \
                HexCoaPipe<T, NQ, EL, NW>::THREADS, HexCoaPipe<T, NQ, EL, NW>::SMEM, (const T *)c.in, c.out, c.nelmt / EL);
+#define CPT(T, NQ, EL, NW, MB)                                                                               \
+    {                                                                                                        \
+        CUtensorMap tm;                                                                                      \
+        if (!make_coa_tensor_map<T>(&tm, c.in, HexCoaPipe<T, NQ, EL, NW>::NM3, c.nelmt / 32, EL, HexCoaPipe<T, NQ, EL, NW>::BOXR)) \
+            printf("# tensor map encode failed\n");                                                          \
+        else                                                                                                 \
+            c.run_args("coa-pipe tma EL=" #EL " NW=" #NW " MINB=" #MB, bwdtrans_hex_coapipe_tma_kernel<T, NQ, EL, NW, MB>, 0u, \
+                       HexCoaPipe<T, NQ, EL, NW>::THREADS, HexCoaPipe<T, NQ, EL, NW>::SMEM_TMA, tm, c.out, c.nelmt / EL); \
+    }
 #define CM(NQ, WARPS)                                                                                        \
     c.run_args("coa-mma WARPS=" #WARPS, bwdtrans_quad_coamma_kernel<NQ, WARPS>, 0u, WARPS * 32,                \
                QuadCoaMma<NQ, WARPS>::SMEM, (const double *)c.b[0], (const double *)c.b[1], (const double *)c.in, c.out, c.nelmt / 8);
@@ -238,6 +247,17 @@ int main(int argc, char **argv)
             CP(float, 10, 16, 25, 2) CP(float, 10, 16, 50, 1) CP(float, 10, 16, 34, 2) CP(float, 10, 32, 25, 1) CP(float, 10, 32, 17, 1)
             c.teardown();
         }
+        return 0;
+    }
+    if (which == 9)
+    {
+        Case<double> c;
+        c.setup(3, 10);
+        CPT(double, 10, 8, 52, 2) CPT(double, 10, 8, 50, 2) CPT(double, 10, 8, 54, 2) CPT(double, 10, 8, 56, 2) CPT(double, 10, 8, 34, 2) CPT(double, 10, 8, 27, 2) CPT(double, 10, 8, 60, 2)
+        c.teardown();
+        c.setup(3, 8);
+        CPT(double, 8, 8, 32, 2) CPT(double, 8, 8, 32, 3) CPT(double, 8, 8, 28, 3) CPT(double, 8, 8, 22, 3) CPT(double, 8, 8, 34, 3) CPT(double, 8, 8, 36, 2)
+        c.teardown();
         return 0;
     }
     if (which == 3) // FP32 quad nq = 32 on the TF32 tensor-core path (not bit-identical: prints the error)

@@ -17,6 +17,9 @@ namespace b200fe
 {
 std::atomic<unsigned long long> g_launch_count{0};
 thread_local const char *t_last_backend = "none";
+thread_local unsigned long long t_bank_tag = 0;
+std::atomic<int> g_bank_fill_mode{0};
+std::atomic<int> g_tensor_map_gather{1};
 } // namespace b200fe
 using namespace b200fe;
 
