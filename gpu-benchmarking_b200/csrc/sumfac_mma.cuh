@@ -227,10 +227,12 @@ __device__ __forceinline__ void dmma884_ordered(double (&c)[2], double a, double
                  : "d"(a), "d"(b));
 }
 
-template <int NQ, int DS, int MB, int NROWS, bool SWZ = false>
+// PRE: the basis fragments of this lane are handed over in registers (pre[ks*NT + n]) instead of being fetched from the
+// fragment area at the start of every pass -- the kernels whose groups are always full (G = 1) load them once per warp
+template <int NQ, int DS, int MB, int NROWS, bool SWZ = false, bool PRE = false>
 __device__ __forceinline__ void mma_pass_data_rows_full(const double *__restrict__ src,
                                                         const double *__restrict__ fragB, double *__restrict__ dst,
-                                                        int lane)
+                                                        int lane, const double *pre = nullptr)
 {
     constexpr int NM = NQ - 1, KS = (NM + 3) / 4, NT = (NQ + 7) / 8, MT = (NROWS + 7) / 8;
     constexpr int NBLK = (MT + MB - 1) / MB;
@@ -245,7 +247,7 @@ __device__ __forceinline__ void mma_pass_data_rows_full(const double *__restrict
     for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
         for (int n = 0; n < NT; ++n)
-            b[ks][n] = fragB[(ks * NT + n) * 32 + lane];
+            b[ks][n] = PRE ? pre[ks * NT + n] : fragB[(ks * NT + n) * 32 + lane];
 
     double a[2][MB][KS];
     auto load_block = [&](int blk, double (&dstA)[MB][KS]) {
@@ -303,10 +305,10 @@ __device__ __forceinline__ void mma_pass_data_rows_full(const double *__restrict
 // needs NCOLS % 8 == 0.  A tile of 8 columns may straddle two groups when W % 8 != 0: the lanes past
 // the group boundary then add one compile-time constant to their address (a predicated add per tile).
 template <int NQ, int W, int STRIDE, int DG, int DM, int NB, bool TO_GLOBAL, bool VEC, int NCOLS, bool SUMSQ = false,
-          bool SWZ_SRC = false>
+          bool SWZ_SRC = false, bool PRE = false>
 __device__ __forceinline__ void mma_pass_basis_rows_full(const double *__restrict__ src,
                                                          const double *__restrict__ fragA, double *__restrict__ dst,
-                                                         int lane, double &ss)
+                                                         int lane, double &ss, const double *pre = nullptr)
 {
     constexpr int NM = NQ - 1, KS = (NM + 3) / 4, MT = (NQ + 7) / 8, NTT = NCOLS / 8;
     constexpr int NBLK = (NTT + NB - 1) / NB;
@@ -327,7 +329,7 @@ __device__ __forceinline__ void mma_pass_basis_rows_full(const double *__restric
     for (int m = 0; m < MT; ++m)
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks)
-            a[m][ks] = fragA[(m * KS + ks) * 32 + lane];
+            a[m][ks] = PRE ? pre[m * KS + ks] : fragA[(m * KS + ks) * 32 + lane];
 
     double b[2][NB][KS];
     auto load_block = [&](int blk, double (&dstB)[NB][KS]) {
@@ -650,6 +652,25 @@ __global__ void __launch_bounds__(WARPS * 32)
     if (g < ngroups)
         by_bar = mma_fetch_group<G, C::NM3>(slot, bar, in, g, nelmt, lane);
 
+    // G = 1: every group is a whole element, so every pass is the unrolled one and this lane's basis fragments never
+    // change: they live in registers for the whole kernel instead of being fetched from the fragment area by every pass
+    // of every element (6 of ~100 shared-memory instructions per element; the L1 data pipe is what bounds this kernel)
+    constexpr bool PRE = G == 1 && (G * C::NM * NQ) % 8 == 0 && (G * C::NQ2) % 8 == 0;
+    constexpr int MT   = (NQ + 7) / 8;
+    double p0[PRE ? C::KS * C::NT : 1], p1[PRE ? MT * C::KS : 1], p2[PRE ? MT * C::KS : 1];
+    if constexpr (PRE)
+    {
+#pragma unroll
+        for (int f = 0; f < C::KS * C::NT; ++f)
+            p0[f] = frag0[f * 32 + lane];
+#pragma unroll
+        for (int f = 0; f < MT * C::KS; ++f)
+        {
+            p1[f] = frag1[f * 32 + lane];
+            p2[f] = frag2[f * 32 + lane];
+        }
+    }
+
     for (; g < ngroups; g += nw)
     {
         const size_t e0 = (size_t)g * G;
@@ -661,17 +682,34 @@ __global__ void __launch_bounds__(WARPS * 32)
             parity ^= 1u;
         }
         // direction 0: s1[(e,r,q)][i] = sum_p in[(e,r,q)][p] B0[p][i]
-        mma_dir_data<NQ, C::S1, MB0, G * C::NM2, C::SWZ>(s_in, frag0, s1, ne * C::NM2, lane);
+        if constexpr (PRE)
+            mma_pass_data_rows_full<NQ, C::S1, MB0, G * C::NM2, C::SWZ, true>(s_in, frag0, s1, lane, p0);
+        else
+            mma_dir_data<NQ, C::S1, MB0, G * C::NM2, C::SWZ>(s_in, frag0, s1, ne * C::NM2, lane);
         __syncwarp();
         if (g + nw < ngroups)
             by_bar = mma_fetch_group<G, C::NM3>(slot, bar, in, g + nw, nelmt, lane);
         // direction 1: s2[(e,r)][j][i] = sum_q B1[q][j] s1[(e,r)][q][i]
-        mma_dir_basis<NQ, NQ, C::S1, C::S2, NQ, NB, false, G * NM * NQ, false, C::SWZ>(s1, frag1, s2, ne * NM * NQ, true, lane,
-                                                                                      ss);
+        if constexpr (PRE)
+            mma_pass_basis_rows_full<NQ, NQ, C::S1, C::S2, NQ, NB, false, true, G * NM * NQ, false, C::SWZ, true>(s1, frag1, s2,
+                                                                                                             lane, ss, p1);
+        else
+            mma_dir_basis<NQ, NQ, C::S1, C::S2, NQ, NB, false, G * NM * NQ, false, C::SWZ>(s1, frag1, s2, ne * NM * NQ, true,
+                                                                                          lane, ss);
         __syncwarp();
         // direction 2: out[e][k][(j,i)] = sum_r B2[r][k] s2[e][r][(j,i)]
-        mma_dir_basis<NQ, C::NQ2, C::S2, C::NQ3, C::NQ2, NB, true, G * C::NQ2, SUMSQ>(
-            s2, frag2, out + e0 * C::NQ3, ne * C::NQ2, out_vec != 0, lane, ss);
+        if constexpr (PRE)
+        {
+            if (out_vec != 0)
+                mma_pass_basis_rows_full<NQ, C::NQ2, C::S2, C::NQ3, C::NQ2, NB, true, true, G * C::NQ2, SUMSQ, false, true>(
+                    s2, frag2, out + e0 * C::NQ3, lane, ss, p2);
+            else
+                mma_pass_basis_rows_full<NQ, C::NQ2, C::S2, C::NQ3, C::NQ2, NB, true, false, G * C::NQ2, SUMSQ, false, true>(
+                    s2, frag2, out + e0 * C::NQ3, lane, ss, p2);
+        }
+        else
+            mma_dir_basis<NQ, C::NQ2, C::S2, C::NQ3, C::NQ2, NB, true, G * C::NQ2, SUMSQ>(
+                s2, frag2, out + e0 * C::NQ3, ne * C::NQ2, out_vec != 0, lane, ss);
         __syncwarp(); // s1 / s2 are rewritten by the next group
     }
     if (SUMSQ)
