@@ -28,7 +28,10 @@
 // 29 TFLOP/s = 79 % of the FP64 tensor peak (the ceiling at that peak is 0.70; the element-major DMMA kernel holds
 // 0.60; the lanes kernel this replaces 0.29).  Steps on the way: two-slot ring + fragments reloaded from shared
 // memory at every phase change, one CTA per SM: 0.45 (tensor pipe idle through every gather issue, reload and barrier);
-// the swizzles below: 0.46; in-place rows, two CTAs per SM: 0.50; registers + pipeline: 0.55.
+// the swizzles below: 0.46; in-place rows, two CTAs per SM: 0.50; registers + pipeline: 0.55.  Tried and dropped: the
+// gather by tiled TMA (one box of {8, nm, 1} per row q; the copy engine cannot apply the input swizzle, so the direction-0
+// loads replay 2-way): 0.42 -- and at 255 registers the kernel is sensitive to anything that costs one more (the same
+// source with an unused mbarrier pointer spilled 16 bytes and fell to 0.46).
 // Bank conflicts.  An 8-byte access is served a half warp at a time: fragment rows 0-3 (4 elements = 32 bytes) x the 4
 // fragment columns, which therefore have to fall into the four 32-byte quarters of a 128-byte bank window.  The tile's
 // unit is 64 bytes (index u, 8 elements), so consecutive u alternate between the two halves and a two-bit swizzle does
@@ -54,40 +57,16 @@ template <int NQ, int WARPS> struct QuadCoaMma
     static constexpr int EL = 8, NM = NQ - 1, NM2 = NM * NM, NQ2 = NQ * NQ;
     static constexpr int KS = (NM + 3) / 4, NT = NQ / 8;
     static constexpr int S1 = NQ * NQ * EL; // the region: nm rows of nq units + one spare row (the zero-selected k padding of direction 1 reads it)
-    static constexpr size_t SMEM = (size_t)S1 * sizeof(double) + 16; // + the mbarrier of the tiled-TMA gather
+    static constexpr size_t SMEM = (size_t)S1 * sizeof(double);
     static constexpr int THREADS = WARPS * 32;
     static constexpr int PER = 32 / EL;
     static constexpr int ROWS = (NM + WARPS - 1) / WARPS, COLS = (NQ + WARPS - 1) / WARPS; // per warp
 };
 
-// TMAP: the tile is gathered by tiled TMA (tensormap.h: boxes of {8 elements, nm indices, 1 group}, one per row q,
-// issued by one thread, completion on an mbarrier) instead of 16-byte cp.async copies from every thread.  The copy
-// engine cannot apply the input swizzle below, so the direction-0 A loads then replay 2-way -- the price for taking
-// 3 844 copies and their address arithmetic per tile off the instruction stream.
-template <int NQ, int WARPS, bool TMAP>
-__device__ __forceinline__ void quad_coamma_body(const double *__restrict__ b0, const double *__restrict__ b1,
-                                                 const double *__restrict__ in, double *__restrict__ out, unsigned ntiles,
-                                                 const CUtensorMap *map);
-
 template <int NQ, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 2)
     bwdtrans_quad_coamma_kernel(const double *__restrict__ b0, const double *__restrict__ b1,
                                 const double *__restrict__ in, double *__restrict__ out, unsigned ntiles)
-{
-    quad_coamma_body<NQ, WARPS, false>(b0, b1, in, out, ntiles, nullptr);
-}
-template <int NQ, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2)
-    bwdtrans_quad_coamma_tma_kernel(const __grid_constant__ CUtensorMap map, const double *__restrict__ b0,
-                                    const double *__restrict__ b1, double *__restrict__ out, unsigned ntiles)
-{
-    quad_coamma_body<NQ, WARPS, true>(b0, b1, nullptr, out, ntiles, &map);
-}
-
-template <int NQ, int WARPS, bool TMAP>
-__device__ __forceinline__ void quad_coamma_body(const double *__restrict__ b0, const double *__restrict__ b1,
-                                                 const double *__restrict__ in, double *__restrict__ out, unsigned ntiles,
-                                                 const CUtensorMap *map)
 {
     using C = QuadCoaMma<NQ, WARPS>;
     constexpr int NM = C::NM, NM2 = C::NM2, KS = C::KS, NT = C::NT, EL = C::EL, PER = C::PER;
@@ -110,39 +89,16 @@ __device__ __forceinline__ void quad_coamma_body(const double *__restrict__ b0, 
         }
     const bool kpad = 4 * (KS - 1) + c >= NM; // this lane's column of the last k step is padding
 
-    uint64_t *bar = reinterpret_cast<uint64_t *>(s1 + C::S1); // (TMAP only)
-    if constexpr (TMAP)
-    {
-        if (tid == 0)
-        {
-            mbar_init(bar, 1);
-            mbar_fence_init();
-        }
-    }
     auto issue = [&](unsigned tile) {
         const unsigned group = tile / PER, l0 = (tile % PER) * EL;
-        if constexpr (TMAP)
-        {
-            if (tid == 0) // row q: one box of {8, nm, 1} to units [nq*q, nq*q + nm)
-            {
-                fence_proxy_async();
-                mbar_arrive_expect_tx(bar, (unsigned)(NM2 * EL * sizeof(double)));
-#pragma unroll 1
-                for (int q = 0; q < NM; ++q)
-                    tma_load_3d(s1 + q * NQ * EL, map, (int)l0, q * NM, (int)group, bar);
-            }
-        }
-        else
-        {
-            const double *g = in + (size_t)group * 32 * NM2 + l0;
+        const double *g      = in + (size_t)group * 32 * NM2 + l0;
 #pragma unroll 4
-            for (int ch = tid; ch < NM2 * 4; ch += C::THREADS)
-            {
-                const int idx = ch >> 2, part = ch & 3, q = idx / NM, u = idx + q; // u = nq*q + p
-                cp_async16(s1 + u * EL + 2 * (part ^ (u & 2)), g + (size_t)idx * 32 + part * 2);
-            }
-            cp_async_commit();
+        for (int ch = tid; ch < NM2 * 4; ch += C::THREADS)
+        {
+            const int idx = ch >> 2, part = ch & 3, q = idx / NM, u = idx + q; // u = nq*q + p
+            cp_async16(s1 + u * EL + 2 * (part ^ (u & 2)), g + (size_t)idx * 32 + part * 2);
         }
+        cp_async_commit();
     };
     auto load_a = [&](double (&a)[KS], const double *ap, int stride) {
 #pragma unroll
@@ -162,7 +118,7 @@ __device__ __forceinline__ void quad_coamma_body(const double *__restrict__ b0, 
                 dmma884_ordered(acc[n], a[ks], f[ks][n]);
     };
     // A fragments of row q (direction 0): u = nq*q + 4 ks + c, bit 1 of u is that of c
-    auto row_ptr = [&](int q) { return s1 + (q * NQ + c) * EL + (TMAP ? r : (r ^ (2 * (c & 2)))); };
+    auto row_ptr = [&](int q) { return s1 + (q * NQ + c) * EL + (r ^ (2 * (c & 2))); };
     // t1[q][i = 8 n + 2 c + h]: u = 32 q + i -- bit 1 = c & 1, bit 2 = c >> 1, bit 5 = q & 1, bit 6 = q >> 1 & 1
     auto store_row = [&](int q, const double (&acc)[NT][2]) {
         const int sw = (c ^ q) & 1, er = r ^ (4 * (((c >> 1) ^ (q >> 1)) & 1));
@@ -180,16 +136,12 @@ __device__ __forceinline__ void quad_coamma_body(const double *__restrict__ b0, 
         return s1 + (c * NQ + (i ^ (((i >> 1) ^ c) & 1))) * EL + (r ^ (4 * (((i >> 2) ^ (c >> 1)) & 1)));
     };
 
-    unsigned it = 0;
 #pragma unroll 1
-    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it)
+    for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
     {
         __syncthreads(); // every warp has left direction 1 of the previous tile
         issue(tile);
-        if constexpr (TMAP)
-            mbar_wait(bar, it & 1u);
-        else
-            cp_async_wait<0>();
+        cp_async_wait<0>();
         __syncthreads();
 
         // direction 0: rows q = warp + k*WARPS, in place (a row belongs to one warp)

@@ -214,15 +214,6 @@ template <typename T> struct Case
 #define CM(NQ, WARPS)                                                                                        \
     c.run_args("coa-mma WARPS=" #WARPS, bwdtrans_quad_coamma_kernel<NQ, WARPS>, 0u, WARPS * 32,                \
                QuadCoaMma<NQ, WARPS>::SMEM, (const double *)c.b[0], (const double *)c.b[1], (const double *)c.in, c.out, c.nelmt / 8);
-#define CMT(NQ, WARPS)                                                                                       \
-    {                                                                                                        \
-        CUtensorMap tm;                                                                                      \
-        if (!make_coa_tensor_map<double>(&tm, c.in, QuadCoaMma<NQ, WARPS>::NM2, c.nelmt / 32, 8, NQ - 1))      \
-            printf("# tensor map encode failed\n");                                                          \
-        else                                                                                                 \
-            c.run_args("coa-mma tma WARPS=" #WARPS, bwdtrans_quad_coamma_tma_kernel<NQ, WARPS>, 0u, WARPS * 32, \
-                       QuadCoaMma<NQ, WARPS>::SMEM, tm, (const double *)c.b[0], (const double *)c.b[1], c.out, c.nelmt / 8); \
-    }
 #define CM32(NQ, WARPS, MB)                                                                                  \
     c.run_args("coa-mma32 WARPS=" #WARPS " MINB=" #MB, bwdtrans_quad_coamma32_kernel<NQ, WARPS, MB>, 0u, WARPS * 32, \
                QuadCoaMma32<NQ, WARPS>::SMEM, (const float *)c.b[0], (const float *)c.b[1], (const float *)c.in, c.out, c.nelmt / 16);
@@ -256,14 +247,6 @@ int main(int argc, char **argv)
             CP(float, 10, 16, 25, 2) CP(float, 10, 16, 50, 1) CP(float, 10, 16, 34, 2) CP(float, 10, 32, 25, 1) CP(float, 10, 32, 17, 1)
             c.teardown();
         }
-        return 0;
-    }
-    if (which == 10)
-    {
-        Case<double> c;
-        c.setup(2, 32);
-        CM(32, 4) CMT(32, 4) CMT(32, 3) CMT(32, 6)
-        c.teardown();
         return 0;
     }
     if (which == 9)
