@@ -94,6 +94,10 @@ def set_bank_fill(mode):
     _check("b200fe_set_bank_fill", lib().b200fe_set_bank_fill(mode.encode()))
 
 
+def tensor_map_available():
+    return bool(lib().b200fe_tensor_map_available())
+
+
 def set_gather(mode):
     """ "tma" (tiled TMA through a tensor map, default) | "cp.async": how the coa-pipe kernels fetch their tile"""
     _check("b200fe_set_gather", lib().b200fe_set_gather(mode.encode()))

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "dispatch.h"
+#include "tensormap.h"
 #include "vec_kernels.h"
 
 namespace b200fe
@@ -464,6 +465,11 @@ int b200fe_set_bank_fill(const char *mode)
     else
         return B200FE_EINVAL;
     return B200FE_OK;
+}
+
+int b200fe_tensor_map_available(void)
+{
+    return tensor_map_encoder() != nullptr;
 }
 
 int b200fe_set_gather(const char *mode)

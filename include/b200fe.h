@@ -395,6 +395,8 @@ int b200fe_set_bank_fill(const char *mode);
  * itself); "cp.async" = 16-byte asynchronous copies issued by every thread.  Same kernel, bit-identical results.
  * Process-wide; returns 0 or B200FE_EINVAL. */
 int b200fe_set_gather(const char *mode);
+/* 1 when the driver offers cuTensorMapEncodeTiled (the "tma" gather is then really the one that runs), else 0. */
+int b200fe_tensor_map_available(void);
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -87,3 +87,13 @@ def test_the_library_carries_blackwell_tensor_core_code():
     sass = subprocess.run([exe, "-sass", fe.LIB_PATH], capture_output=True, text=True, check=True).stdout
     for op in ("UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "DMMA", "UTCBAR"):
         assert sass.count(op) > 0, op
+
+
+def test_tensor_map_lookup_is_safe_without_a_driver():
+    """the tiled-TMA gather needs the driver's cuTensorMapEncodeTiled, looked up through the runtime at first use; on a
+    machine without a driver (this container) the lookup must simply report 'not available' (the kernels then gather with
+    cp.async) -- no crash, no sticky CUDA error"""
+    assert fe.lib().b200fe_tensor_map_available() in (0, 1)
+    assert fe.lib().b200fe_set_gather(b"tma") == 0 and fe.lib().b200fe_set_gather(b"cp.async") == 0
+    assert fe.lib().b200fe_set_gather(b"nonsense") < 0
+    assert fe.lib().b200fe_set_gather(b"tma") == 0

@@ -136,6 +136,7 @@ def test_quad_nq32_fp32_reference_synthetic_input(G):
 def test_hex_coa_pipe_gather_routes_agree(G, nq, nelmt):
     """the tile is gathered by tiled TMA through a tensor map (default) or, where the driver does not offer the
     encoder, by 16-byte cp.async copies: same kernel otherwise, same bits -- b200fe_set_gather forces either"""
+    assert G.fe.tensor_map_available(), "the driver on a B200 box offers cuTensorMapEncodeTiled: the TMA route must be live"
     b, inp_em = hex_case(nq, nelmt, 4250 + nq)
     want_em = oracle.bwdtrans_hex(nq, nq, nq, nelmt, *b, inp_em)
     inp = oracle.to_coa(inp_em, nelmt, (nq - 1) ** 3)
