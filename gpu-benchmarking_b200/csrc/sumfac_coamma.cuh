@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(WARPS * 32, 2)
 {
     using C = QuadCoaMma<NQ, WARPS>;
     constexpr int NM = C::NM, NM2 = C::NM2, KS = C::KS, NT = C::NT, EL = C::EL, PER = C::PER;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *s1 = reinterpret_cast<double *>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_raw128[]; // (own name: the TU also declares smem_raw with 16-byte alignment)
+    double *s1 = reinterpret_cast<double *>(smem_raw128);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r = lane >> 2, c = lane & 3; // fragment row (element) / column
@@ -231,8 +231,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
 {
     using C = QuadCoaMma32<NQ, WARPS>;
     constexpr int NM = C::NM, NM2 = C::NM2, KS = C::KS, NT = C::NT, EL = C::EL, PER = C::PER;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *s1     = reinterpret_cast<float *>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_raw128[]; // (own name: the TU also declares smem_raw with 16-byte alignment)
+    float *s1     = reinterpret_cast<float *>(smem_raw128);
     float *fr0 = s1 + C::S1;
     float *fr1 = fr0 + C::FRAG;
 

@@ -189,8 +189,8 @@ __device__ __noinline__ void hex_coapipe_body(const T *__restrict__ in, T *__res
     constexpr int NM = C::NM, NM2 = C::NM2, NM3 = C::NM3, NQ2 = C::NQ2, G = C::G, PER = C::PER;
     constexpr int BP = bank_pitch<T>(NQ), B0 = 0, B1 = NM * BP, B2 = 2 * NM * BP;
     constexpr int VW = 16 / (int)sizeof(T), CH = C::U / 16; // values per 16-byte chunk, chunks per index
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    T *slot = reinterpret_cast<T *>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_raw128[]; // (own name: the TU also declares smem_raw with 16-byte alignment)
+    T *slot = reinterpret_cast<T *>(smem_raw128);
     T *wk   = slot + (TMAP ? C::SIN_TMA : C::SIN); // the work region: s1[r][q][i] after pass 0, s2[r][j][i] (in place) after pass 1
 
     const int tid = threadIdx.x, e = tid % EL;
