@@ -699,9 +699,25 @@ int launch_quad_iprod_mma(unsigned, const float *, const float *, const float *,
     return B200FE_EUNSUPPORTED;
 }
 
+// VW elements per thread as one 16-byte vector where in / out are 16-byte aligned (sumfac_tpe.cuh).  Measured per call at
+// 64 Mi points, one element per thread -> vector: FP32 quad nq = 2 0.62 -> 0.73; everywhere else it LOSES (FP32 quad
+// nq = 3 0.83 -> 0.77, FP32 hex nq = 2 0.76 -> 0.69, FP64 hex nq = 2 0.87 -> 0.83, FP64 quads unchanged), so only that
+// one case takes it.
+template <typename T, int NQ> constexpr int tpe_vw(int dim)
+{
+    return (dim == 2 && NQ == 2 && sizeof(T) == 4) ? 4 : 1;
+}
 template <typename T, int NQ> int launch_quad_tpe_coa(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
 {
-    constexpr int THREADS = 128;
+    constexpr int THREADS = 128, VW = tpe_vw<T, NQ>(2);
+    if (VW > 1 && aligned16(in) && aligned16(out))
+    {
+        const unsigned grid = (nelmt / VW + THREADS - 1) / THREADS;
+        bwdtrans_quad_tpe_coa_kernel<T, NQ, THREADS, VW><<<grid, THREADS, 0, stream>>>(in, out, nelmt);
+        count_launch();
+        t_last_backend = "tpe";
+        return launch_status();
+    }
     const unsigned grid   = (nelmt + THREADS - 1) / THREADS;
     bwdtrans_quad_tpe_coa_kernel<T, NQ, THREADS><<<grid, THREADS, 0, stream>>>(in, out, nelmt);
     count_launch();
@@ -780,7 +796,15 @@ int launch_hex_mma(unsigned nelmt, const double *b0, const double *b1, const dou
 
 template <typename T, int NQ> int launch_hex_tpe_coa(unsigned nelmt, const T *in, T *out, cudaStream_t stream)
 {
-    constexpr int THREADS = 128;
+    constexpr int THREADS = 128, VW = tpe_vw<T, NQ>(3);
+    if (VW > 1 && aligned16(in) && aligned16(out))
+    {
+        const unsigned grid = (nelmt / VW + THREADS - 1) / THREADS;
+        bwdtrans_hex_tpe_coa_kernel<T, NQ, THREADS, VW><<<grid, THREADS, 0, stream>>>(in, out, nelmt);
+        count_launch();
+        t_last_backend = "tpe";
+        return launch_status();
+    }
     const unsigned grid   = (nelmt + THREADS - 1) / THREADS;
     bwdtrans_hex_tpe_coa_kernel<T, NQ, THREADS><<<grid, THREADS, 0, stream>>>(in, out, nelmt);
     count_launch();
