@@ -330,7 +330,10 @@ __device__ __noinline__ void hex_coapipe_body(const T *__restrict__ in, T *__res
 // form that fuses directions 0 and 1 in registers and reads the rows from the staged slot (39 % fewer shared-memory
 // wavefronts, but 150 registers and 12 warps per SM: 0.66); 32-byte tiles (EL = 4 doubles: 0.60); the gather as one small
 // bulk (TMA) copy per index of the tile (64 / 128 bytes each, issued by one warp, completion on an mbarrier) instead of
-// cp.async: 3.4x SLOWER (0.21) -- the copy engine is made for kilobytes per instruction, not for 729 tiny ones.  What bounds this
+// cp.async: 3.4x SLOWER (0.21) -- the copy engine is made for kilobytes per instruction, not for 729 tiny ones.  And the
+// other way round, the tiled-TMA gather in front of the lanes PLANE kernel (sumfac_lanes.cuh; boxes into the region that
+// later holds t2, planes pulled into registers from there): 0.41-0.50 where the direct loads hold 0.73-0.95 -- that kernel
+// wants its nm^2 loads per thread in flight from HBM, not a staged tile behind one more barrier.  What bounds this
 // kernel at ~0.7 is the shared-memory data path next to the FP64 pipe: every 8-byte warp access is two wavefronts, a row
 // costs 38 of them per 90 DFMAs (84 % of the LSU at FP64 peak), and the two pipes overlap only across warps.
 } // namespace b200fe
